@@ -1,0 +1,206 @@
+/*
+ * libofb - B200 (sm_100a) kernels for the OmniFusion tangent-patch inference path.
+ *
+ * C ABI: plain pointers and sizes, no torch types.  Every tensor pointer is a
+ * DEVICE pointer unless the parameter says "host"; the caller owns every buffer
+ * it passes in; all calls are asynchronous and ordered on the cudaStream_t passed
+ * as `stream` (a void* so the header needs no CUDA include); nothing here calls
+ * cudaDeviceSynchronize.  Return value: 0 = OK, negative = error, message in
+ * ofb_last_error() (thread-local).  A handle is bound to one device and is not
+ * concurrently callable from two threads.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to
+ * the OmniFusion repository).
+ *
+ * Activation layout inside the library ("folded NHWC"): image index b*N+n
+ * (panorama b, patch n), then H, W, C with C contiguous.
+ */
+#ifndef OFB_H_
+#define OFB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFB_VERSION 100
+
+typedef struct ofb_handle ofb_handle;
+
+int ofb_version(void);
+const char* ofb_last_error(void);
+
+/* Selects the CUDA device the calling thread's subsequent operator calls launch on
+ * (the library links its own CUDA runtime, whose current device is independent of the
+ * host framework's).  Engine calls (ofb_forward_f32 ...) use the handle's device. */
+int ofb_set_device(int device);
+
+/* ---------------------------------------------------------------- resamplers */
+
+/* Layout selector for patch tensors. */
+enum {
+  OFB_LAYOUT_REF = 0,    /* reference layout (B,C,Ph,Pw,N), N innermost            */
+  OFB_LAYOUT_FOLDED = 1  /* folded NHWC (B*N,Ph,Pw,Cpad), Cpad = C rounded up to 4
+                            when C == 3, else C                                      */
+};
+
+/* equi2pers sampling: equi_pers/equi2pers_v3.py:106-113 (F.grid_sample bilinear /
+ * border / align_corners=True on the gnomonic grid, then F.unfold into patches).
+ * erp (B,C,He,We); grid (N,Ph,Pw,2) = the reference's normalised [lon,lat] grid,
+ * built once on the host (equi2pers_v3.py:86-104); out per `layout`. */
+int ofb_equi2pers_f32(const float* erp, int B, int C, int He, int We,
+                      const float* grid, int N, int Ph, int Pw,
+                      float* out, int layout, void* stream);
+
+/* The integer neighbour indices the sampler above uses (x0 = floor(ix), y0 =
+ * floor(iy)); exposed so tests can check them bit-exactly.  x0,y0: (N,Ph,Pw) int32. */
+int ofb_equi2pers_taps(const float* grid, int N, int Ph, int Pw, int He, int We,
+                       int32_t* x0, int32_t* y0, void* stream);
+
+/* pers2equi apply: equi_pers/pers2equi_v3.py:169-196 (4-tap gather per covering
+ * patch, thresholded L1-normalised weights, sum over taps and patches).
+ * The dense (N,He,We) tap table of pers2equi_v3.py:109-152 is passed as CSR over
+ * ERP pixels holding only the entries whose normalised weight vector is non-zero:
+ *   rowptr (He*We+1) int32; idx (nnz) packed n<<24 | y0<<16 | x0<<8 | dy<<1 | dx
+ *   with y1=y0+dy, x1=x0+dx (the reference's clamped x1,y1); w (nnz,4) float32 =
+ *   normalised [wa,wb,wc,wd] for taps (y0,x0),(y1,x0),(y0,x1),(y1,x1).
+ * pers per `layout` (OFB_LAYOUT_FOLDED here means (B*N,Ph,Pw,C)); out (B,C,He,We). */
+int ofb_pers2equi_f32(const float* pers, int B, int C, int N, int Ph, int Pw, int layout,
+                      const int32_t* rowptr, const uint32_t* idx, const float* w,
+                      int He, int We, float* out, void* stream);
+
+/* Confidence merge: model/spherical_model_iterative.py:372-378.
+ * pred_w (B*N,Ph,Pw) = relu(pred)*sigmoid(weight), conf (B*N,Ph,Pw) = sigmoid(weight);
+ * out (B,1,He,We) = blend(pred_w) / (blend(conf) + 1e-8*[blend(conf) <= 1e-8]). */
+int ofb_blend_conf_f32(const float* pred_w, const float* conf, int B, int N, int Ph, int Pw,
+                       const int32_t* rowptr, const uint32_t* idx, const float* w,
+                       int He, int We, float* out, void* stream);
+
+/* ------------------------------------------------------------ network kernels */
+
+enum { OFB_ACT_NONE = 0, OFB_ACT_RELU = 1, OFB_ACT_GELU = 2 };
+enum { OFB_ENGINE_AUTO = 0, OFB_ENGINE_SIMT = 1, OFB_ENGINE_TC = 2 };
+
+/* One 2-D convolution over folded NHWC, replacing a Conv3d((k,k,1)) + BatchNorm3d
+ * (+ residual) (+ ReLU) group of model/spherical_model_iterative.py:322-369 or an
+ * nn.Linear of model/blocks.py (n = rows, h = w = 1, k = 1).
+ *   y = act(conv(cat(in0,in1)) * scale + shift + residual)
+ * in0 (n,h,w,c0), in1 (n,h,w,c1) or NULL; wgt (cout, k, k, c0+c1) ("OHWI");
+ * scale/shift (cout) or NULL (= 1 / 0); residual (n,oh,ow,cout) or NULL. */
+typedef struct {
+  const float* in0; const float* in1; int c0, c1;
+  int n, h, w;
+  const float* wgt; int k, stride, pad, cout;
+  const float* scale; const float* shift; const float* residual;
+  int act;
+  float* out;
+  int engine;
+} ofb_conv_desc;
+int ofb_conv_f32(const ofb_conv_desc* d, void* stream);
+
+/* Stem: Conv3d(3->64, 7x7 s2 p3) + BN + ReLU, spherical_model_iterative.py:322.
+ * in (n,h,w,4) (4th channel ignored), wgt (64,7,7,4) OHWI-padded, out (n,h/2,w/2,64). */
+int ofb_stem_f32(const float* in, int n, int h, int w, const float* wgt,
+                 const float* scale, const float* shift, float* out, void* stream);
+
+/* F.max_pool3d((3,3,1), s(2,2,1), p(1,1,0)), spherical_model_iterative.py:323. */
+int ofb_maxpool3x3s2_f32(const float* in, int n, int h, int w, int c, float* out, void* stream);
+
+/* F.interpolate(bilinear, align_corners=False) x2, spherical_model_iterative.py:338-367.
+ * If img_bias (n,c) is given it is added to every source pixel first (the token
+ * broadcast-add of :334-335). in (n,h,w,c) -> out (n,2h,2w,c). */
+int ofb_upsample2x_f32(const float* in, const float* img_bias, int n, int h, int w, int c,
+                       float* out, void* stream);
+
+/* Point embedding: mlp_points1/2, spherical_model_iterative.py:290-305,319-320,387-393.
+ * pts (N,cin,p,p) NCHW (the xyz table, or [cx,cy,1,cx,cy] for the single-stage model);
+ * depth (imgs,p,p) or NULL scales the first 3 channels per image; base (imgs,p,p,64)
+ * is added to the result (layer1 + point_feat, :325). out (imgs,p,p,64). */
+int ofb_point_embed_f32(const float* pts, int N, int cin, int p, const float* depth, int imgs,
+                        const float* w1, const float* s1, const float* t1,
+                        const float* w2, const float* s2, const float* t2,
+                        const float* base, float* out, void* stream);
+
+/* Token packing: spherical_model_iterative.py:330-331 + pos_emb add (:244).
+ * down (imgs,4,4,32) -> tokens (imgs,512) with index c*16+i*4+j, + pos_emb[n]. */
+int ofb_token_pack_f32(const float* down, const float* pos_emb, int imgs, int N,
+                       float* tokens, void* stream);
+
+/* nn.LayerNorm over the last dim (model/blocks.py:76,81; encoder_norm eps 1e-6). */
+int ofb_layernorm_f32(const float* x, const float* gamma, const float* beta, int rows, int dim,
+                      float eps, float* y, void* stream);
+
+/* Attention core, model/blocks.py:50-62: q (rows,512), kv (rows,1024) [k | v],
+ * rows = B*N, heads of 128; softmax(q k^T / sqrt(128)) v -> out (rows,512). */
+int ofb_attention_f32(const float* q, const float* kv, int B, int N, int heads, int head_dim,
+                      float* out, void* stream);
+
+/* Heads: pred / weight_pred 3x3 convs + relu / sigmoid / product,
+ * spherical_model_iterative.py:371-374.  x (imgs,h,w,32); w_pred,w_conf (3,3,32);
+ * pred_out = relu(pred) * (confidence ? sigmoid(conf) : 1); conf_out = sigmoid(conf)
+ * (written only when confidence != 0). */
+int ofb_heads_f32(const float* x, int imgs, int h, int w,
+                  const float* w_pred, float b_pred, const float* w_conf, float b_conf,
+                  int confidence, float* pred_out, float* conf_out, void* stream);
+
+/* Abs-Rel partial sums, metrics.py:7-9: out[0] += sum(|p*scale-g|/g over mask), out[1] += count.
+ * `out` must be zeroed by the caller. */
+int ofb_absrel_partial(const float* pred, const float* gt, const uint8_t* mask, size_t n,
+                       float scale, double* out, void* stream);
+
+/* ------------------------------------------------------------------- engine */
+
+int ofb_create(int device, ofb_handle** out);
+int ofb_destroy(ofb_handle* h);
+
+/* Geometry tables (device pointers, kept alive by the caller until the next
+ * ofb_set_geometry / ofb_destroy).  grid_hi (N,P,P,2), grid_lo (N,p,p,2) with p=P/4,
+ * pts (N,pts_c,p,p): xyz (pts_c=3, iterative) or [cx,cy,1,cx,cy] (pts_c=5, single-stage). */
+typedef struct {
+  int n_patch, patch, erp_h, erp_w;
+  const float* grid_hi; const float* grid_lo; const float* pts; int pts_c;
+  const int32_t* blend_rowptr; const uint32_t* blend_idx; const float* blend_w;
+} ofb_geometry;
+int ofb_set_geometry(ofb_handle* h, const ofb_geometry* g);
+
+/* Weights in the reference state_dict layout (HOST pointers, float32), by name:
+ * model/spherical_model_iterative.py:254-305 / model/spherical_model.py:191-235.
+ * Repacked (OHWI, BN folded to scale/shift) and copied to the device. */
+typedef struct {
+  const char* name; const float* data; int ndim; int64_t shape[5];
+} ofb_tensor_desc;
+int ofb_load_weights(ofb_handle* h, const ofb_tensor_desc* tensors, int count, int single_stage);
+
+/* spherical_fusion.forward: model/spherical_model_iterative.py:308-456 (single_stage=0,
+ * returns `iters` maps) or model/spherical_model.py:238-314 (iters must be 1).
+ * rgb (B,3,He,We); out_depth: HOST array of `iters` device pointers, each (B,1,He,We). */
+int ofb_forward_f32(ofb_handle* h, const float* rgb, int B, int iters, int confidence,
+                    float* const* out_depth, void* stream);
+
+/* Engine knobs: conv engine (OFB_ENGINE_*), panoramas per internal chunk (0 = auto),
+ * reuse of the iteration-invariant stem/layer1 across iterations (1 = on, default). */
+int ofb_set_option(ofb_handle* h, const char* key, int value);
+
+/* Copies a named intermediate of the last forward (last chunk, last iteration) into
+ * dst (device, `capacity` floats); returns the element count, or negative.  Names:
+ * patches, conv1, pool, layer1_pre, layer1, layer2, layer3, layer4, tokens, encoded,
+ * de_conv0_1, de_conv1_1, de_conv2_1, de_conv3_1, de_conv4_0, pred_patch, conf_patch. */
+int64_t ofb_get_activation(ofb_handle* h, const char* name, float* dst, int64_t capacity,
+                           int dims[4], void* stream);
+
+/* Per-launch timing: while enabled, ofb_forward_f32 brackets every kernel launch with CUDA
+ * events on the launch stream.  ofb_profile_report waits for them and writes one line per
+ * kernel class, "name launches total_ms algorithmic_flops algorithmic_bytes\n"; returns the
+ * number of bytes written and clears the records. */
+int ofb_profile_enable(ofb_handle* h, int on);
+int ofb_profile_report(ofb_handle* h, char* buf, int capacity);
+
+/* Kernel launches issued by this library on the calling thread since the last reset. */
+int64_t ofb_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFB_H_ */

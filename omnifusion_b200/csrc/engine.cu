@@ -1,0 +1,635 @@
+// Engine: owns the packed weights, the workspace and the forward schedule of the
+// OmniFusion patch network (model/spherical_model_iterative.py:308-456 and
+// model/spherical_model.py:238-314 of the reference), launching libofb's kernels on the
+// caller's stream.  Host-side orchestration only; no device synchronisation.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace ofb {
+
+static thread_local std::string g_err;
+static thread_local long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+void count_launch(int n) { g_launches += n; }
+
+int conv_simt(const ofb_conv_desc* d, cudaStream_t s);
+int conv_tc(const ofb_conv_desc* d, cudaStream_t s);
+bool conv_tc_supported(const ofb_conv_desc* d);
+
+int conv_dispatch(const ofb_conv_desc* d, cudaStream_t s) {
+  OFB_CHECK(d && d->in0 && d->wgt && d->out, "conv: null pointer");
+  OFB_CHECK(d->n > 0 && d->h > 0 && d->w > 0 && d->k > 0 && d->stride > 0, "conv: bad shape");
+  if (d->engine == OFB_ENGINE_TC) {
+    OFB_CHECK(conv_tc_supported(d), "conv: shape not supported by the tcgen05 engine");
+    return conv_tc(d, s);
+  }
+  if (d->engine == OFB_ENGINE_AUTO && conv_tc_supported(d)) return conv_tc(d, s);
+  return conv_simt(d, s);
+}
+
+struct ConvW {
+  float* w = nullptr; float* scale = nullptr; float* shift = nullptr;
+  int cout = 0, cin = 0, k = 0;
+};
+struct Mlp { float *w1, *s1, *t1, *w2, *s2, *t2; int cin; };
+struct Block {
+  float *n1g, *n1b, *n2g, *n2b;
+  ConvW q, kv, proj, fc1, fc2;
+};
+struct Act { float* p = nullptr; int n = 0, h = 0, w = 0, c = 0; };
+
+}  // namespace ofb
+
+using namespace ofb;
+
+struct ofb_handle {
+  int device = 0;
+  bool single = false, has_geo = false, has_weights = false;
+  ofb_geometry geo{};
+  std::map<std::string, ConvW> conv;
+  Block blk[6];
+  float *pos_emb = nullptr, *enc_g = nullptr, *enc_b = nullptr;
+  int pos_patches = 0;
+  ConvW down;
+  float *pred_w = nullptr, *conf_w = nullptr;
+  float pred_b = 0.f, conf_b = 0.f;
+  Mlp mlp[2]{};
+  std::vector<void*> owned;        // device allocations for weights
+  // workspace
+  float* ws = nullptr; size_t ws_floats = 0; size_t ws_used = 0;
+  int engine = OFB_ENGINE_AUTO, chunk = 0, dedup = 1;
+  std::map<std::string, Act> acts;
+  // optional per-launch timing (ofb_profile_enable)
+  bool profile = false;
+  struct Rec { std::string name; double flops, bytes; cudaEvent_t e0, e1; };
+  std::vector<Rec> recs;
+};
+
+namespace ofb {
+
+static int dev_upload(ofb_handle* h, const std::vector<float>& v, float** out) {
+  float* d = nullptr;
+  OFB_CUDA(cudaMalloc(&d, v.size() * sizeof(float)));
+  h->owned.push_back(d);
+  OFB_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+  *out = d;
+  return 0;
+}
+
+typedef std::map<std::string, const ofb_tensor_desc*> TMap;
+
+static const ofb_tensor_desc* find(const TMap& m, const std::string& name) {
+  auto it = m.find(name);
+  if (it == m.end()) { set_error("load_weights: missing tensor '%s'", name.c_str()); return nullptr; }
+  return it->second;
+}
+static long long numel(const ofb_tensor_desc* t) {
+  long long n = 1;
+  for (int i = 0; i < t->ndim; ++i) n *= t->shape[i];
+  return n;
+}
+
+// (O,I,kh,kw[,1]) or (O,I) -> OHWI, optional zero padding of I to cin_pad
+static int pack_conv(ofb_handle* h, const TMap& m, const std::string& wname, ConvW* cw, int cin_pad = 0) {
+  const ofb_tensor_desc* t = find(m, wname);
+  if (!t) return -1;
+  OFB_CHECK(t->ndim >= 2, "load_weights: '%s' must have >= 2 dims", wname.c_str());
+  int O = (int)t->shape[0], I = (int)t->shape[1];
+  int kh = t->ndim >= 3 ? (int)t->shape[2] : 1, kw = t->ndim >= 4 ? (int)t->shape[3] : 1;
+  OFB_CHECK(kh == kw, "load_weights: '%s' non-square kernel", wname.c_str());
+  OFB_CHECK(t->ndim < 5 || t->shape[4] == 1, "load_weights: '%s' trailing dim must be 1", wname.c_str());
+  int Ip = cin_pad ? cin_pad : I;
+  std::vector<float> p((size_t)O * kh * kw * Ip, 0.f);
+  for (int o = 0; o < O; ++o)
+    for (int i = 0; i < I; ++i)
+      for (int y = 0; y < kh; ++y)
+        for (int x = 0; x < kw; ++x)
+          p[(((size_t)o * kh + y) * kw + x) * Ip + i] = t->data[(((size_t)o * I + i) * kh + y) * kw + x];
+  cw->cout = O; cw->cin = Ip; cw->k = kh;
+  return dev_upload(h, p, &cw->w);
+}
+
+static int pack_vec(ofb_handle* h, const TMap& m, const std::string& name, float** out, int expect = -1) {
+  const ofb_tensor_desc* t = find(m, name);
+  if (!t) return -1;
+  OFB_CHECK(expect < 0 || numel(t) == expect, "load_weights: '%s' has %lld elements, expected %d", name.c_str(), numel(t), expect);
+  std::vector<float> v(t->data, t->data + numel(t));
+  return dev_upload(h, v, out);
+}
+
+// BatchNorm (eval) -> y = x*scale + shift
+static int pack_bn(ofb_handle* h, const TMap& m, const std::string& prefix, int c, float eps, float** scale, float** shift) {
+  const ofb_tensor_desc *g = find(m, prefix + ".weight"), *b = find(m, prefix + ".bias"),
+                        *mu = find(m, prefix + ".running_mean"), *var = find(m, prefix + ".running_var");
+  if (!g || !b || !mu || !var) return -1;
+  OFB_CHECK(numel(g) == c && numel(b) == c && numel(mu) == c && numel(var) == c, "load_weights: '%s' BN size mismatch", prefix.c_str());
+  std::vector<float> s(c), t(c);
+  for (int i = 0; i < c; ++i) {
+    double sc = (double)g->data[i] / sqrt((double)var->data[i] + (double)eps);
+    s[i] = (float)sc;
+    t[i] = (float)((double)b->data[i] - (double)mu->data[i] * sc);
+  }
+  if (dev_upload(h, s, scale)) return -1;
+  return dev_upload(h, t, shift);
+}
+
+static int conv_bn(ofb_handle* h, const TMap& m, const std::string& key, const std::string& wname, const std::string& bn) {
+  ConvW cw;
+  if (pack_conv(h, m, wname, &cw)) return -1;
+  if (pack_bn(h, m, bn, cw.cout, 1e-5f, &cw.scale, &cw.shift)) return -1;
+  h->conv[key] = cw;
+  return 0;
+}
+
+static int linear(ofb_handle* h, const TMap& m, const std::string& prefix, bool bias, ConvW* cw) {
+  if (pack_conv(h, m, prefix + ".weight", cw)) return -1;
+  if (bias && pack_vec(h, m, prefix + ".bias", &cw->shift, cw->cout)) return -1;
+  return 0;
+}
+
+static int load_mlp(ofb_handle* h, const TMap& m, const std::string& p, Mlp* o) {
+  const ofb_tensor_desc* w1 = find(m, p + ".0.weight");
+  if (!w1) return -1;
+  o->cin = (int)w1->shape[1];
+  if (pack_vec(h, m, p + ".0.weight", &o->w1, 16 * o->cin)) return -1;
+  if (pack_bn(h, m, p + ".1", 16, 1e-5f, &o->s1, &o->t1)) return -1;
+  if (pack_vec(h, m, p + ".3.weight", &o->w2, 64 * 16)) return -1;
+  return pack_bn(h, m, p + ".4", 64, 1e-5f, &o->s2, &o->t2);
+}
+
+static void free_weights(ofb_handle* h) {
+  for (void* p : h->owned) cudaFree(p);
+  h->owned.clear();
+  h->conv.clear();
+  h->has_weights = false;
+}
+
+static const int kBlocks[4] = {3, 4, 6, 3};
+static const int kChan[4] = {64, 128, 256, 512};
+
+static int load_all(ofb_handle* h, const TMap& m, bool single) {
+  // stem: (64,3,7,7,1) -> OHWI with the input channel padded to 4
+  ConvW stem;
+  if (pack_conv(h, m, "conv1.weight", &stem, 4)) return -1;
+  if (pack_bn(h, m, "bn1", 64, 1e-5f, &stem.scale, &stem.shift)) return -1;
+  h->conv["stem"] = stem;
+  for (int l = 0; l < 4; ++l)
+    for (int b = 0; b < kBlocks[l]; ++b) {
+      std::string p = "layer" + std::to_string(l + 1) + "." + std::to_string(b);
+      if (conv_bn(h, m, p + ".conv1", p + ".conv1.weight", p + ".bn1")) return -1;
+      if (conv_bn(h, m, p + ".conv2", p + ".conv2.weight", p + ".bn2")) return -1;
+      if (m.count(p + ".downsample.0.weight"))
+        if (conv_bn(h, m, p + ".ds", p + ".downsample.0.weight", p + ".downsample.1")) return -1;
+    }
+  if (linear(h, m, single ? "down" : "down1", true, &h->down)) return -1;
+  const ofb_tensor_desc* pe = find(m, "transformer.pos_emb");
+  if (!pe) return -1;
+  h->pos_patches = (int)pe->shape[1];
+  if (pack_vec(h, m, "transformer.pos_emb", &h->pos_emb, h->pos_patches * 512)) return -1;
+  if (pack_vec(h, m, "transformer.encoder_norm.weight", &h->enc_g, 512)) return -1;
+  if (pack_vec(h, m, "transformer.encoder_norm.bias", &h->enc_b, 512)) return -1;
+  for (int i = 0; i < 6; ++i) {
+    std::string p = "transformer.layer." + std::to_string(i);
+    Block& B = h->blk[i];
+    if (pack_vec(h, m, p + ".norm1.weight", &B.n1g, 512) || pack_vec(h, m, p + ".norm1.bias", &B.n1b, 512) ||
+        pack_vec(h, m, p + ".norm2.weight", &B.n2g, 512) || pack_vec(h, m, p + ".norm2.bias", &B.n2b, 512))
+      return -1;
+    if (linear(h, m, p + ".attn.q", false, &B.q) || linear(h, m, p + ".attn.kv", false, &B.kv) ||
+        linear(h, m, p + ".attn.proj", true, &B.proj) || linear(h, m, p + ".mlp.fc1", true, &B.fc1) ||
+        linear(h, m, p + ".mlp.fc2", true, &B.fc2))
+      return -1;
+  }
+  const char* dec[9] = {"de_conv0_0", "de_conv0_1", "de_conv1_0", "de_conv1_1", "de_conv2_0",
+                        "de_conv2_1", "de_conv3_0", "de_conv3_1", "de_conv4_0"};
+  for (int i = 0; i < 9; ++i)
+    if (conv_bn(h, m, dec[i], std::string(dec[i]) + ".conv.weight", std::string(dec[i]) + ".bn")) return -1;
+  // heads: (1,32,3,3,1) -> (3,3,32)
+  ConvW hp, hc;
+  if (pack_conv(h, m, "pred.weight", &hp) || pack_conv(h, m, "weight_pred.weight", &hc)) return -1;
+  h->pred_w = hp.w; h->conf_w = hc.w;
+  const ofb_tensor_desc *pb = find(m, "pred.bias"), *cb = find(m, "weight_pred.bias");
+  if (!pb || !cb) return -1;
+  h->pred_b = pb->data[0]; h->conf_b = cb->data[0];
+  if (single) {
+    if (load_mlp(h, m, "mlp_points", &h->mlp[0])) return -1;
+  } else {
+    if (load_mlp(h, m, "mlp_points1", &h->mlp[0]) || load_mlp(h, m, "mlp_points2", &h->mlp[1])) return -1;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ workspace
+struct Plan {
+  ofb_handle* h; size_t off = 0;
+  float* take(size_t n) {
+    size_t a = (off + 63) & ~(size_t)63;   // 256-byte alignment
+    off = a + n;
+    return h->ws ? h->ws + a : nullptr;
+  }
+};
+
+struct Buffers {
+  float *patches, *conv1, *pool, *l1t, *l1a, *l1b, *layer1_pre, *layer1;
+  float *l2t, *l2a, *l2b, *l2d, *layer2, *l3t, *l3a, *l3b, *l3d, *layer3, *l4t, *l4a, *l4b, *l4d, *layer4;
+  float *down, *tok, *ln, *q, *kv, *att, *tok2, *fc1, *enc;
+  float *up0, *d00, *d01, *up1, *d10, *d11, *up2, *d20, *d21, *up3, *d30, *d31, *up4, *d40;
+  float *pred, *conf, *depth_p;
+};
+
+static size_t plan_buffers(ofb_handle* h, int imgs, int P, Buffers* b) {
+  Plan pl{h};
+  size_t I = (size_t)imgs;
+  int p2 = P / 2, p4 = P / 4, p8 = P / 8, p16 = P / 16, p32 = P / 32;
+  b->patches = pl.take(I * P * P * 4);
+  b->conv1 = pl.take(I * p2 * p2 * 64);
+  b->pool = pl.take(I * p4 * p4 * 64);
+  size_t s1 = I * p4 * p4 * 64, s2 = I * p8 * p8 * 128, s3 = I * p16 * p16 * 256, s4 = I * p32 * p32 * 512;
+  b->l1t = pl.take(s1); b->l1a = pl.take(s1); b->l1b = pl.take(s1); b->layer1_pre = pl.take(s1); b->layer1 = pl.take(s1);
+  b->l2t = pl.take(s2); b->l2a = pl.take(s2); b->l2b = pl.take(s2); b->l2d = pl.take(s2); b->layer2 = pl.take(s2);
+  b->l3t = pl.take(s3); b->l3a = pl.take(s3); b->l3b = pl.take(s3); b->l3d = pl.take(s3); b->layer3 = pl.take(s3);
+  b->l4t = pl.take(s4); b->l4a = pl.take(s4); b->l4b = pl.take(s4); b->l4d = pl.take(s4); b->layer4 = pl.take(s4);
+  b->down = pl.take(I * 512); b->tok = pl.take(I * 512); b->ln = pl.take(I * 512); b->q = pl.take(I * 512);
+  b->kv = pl.take(I * 1024); b->att = pl.take(I * 512); b->tok2 = pl.take(I * 512); b->fc1 = pl.take(I * 2048);
+  b->enc = pl.take(I * 512);
+  b->up0 = pl.take(I * p16 * p16 * 512); b->d00 = pl.take(I * p16 * p16 * 256); b->d01 = pl.take(I * p16 * p16 * 128);
+  b->up1 = pl.take(I * p8 * p8 * 128); b->d10 = pl.take(I * p8 * p8 * 128); b->d11 = pl.take(I * p8 * p8 * 64);
+  b->up2 = pl.take(I * p4 * p4 * 64); b->d20 = pl.take(I * p4 * p4 * 64); b->d21 = pl.take(I * p4 * p4 * 64);
+  b->up3 = pl.take(I * p2 * p2 * 64); b->d30 = pl.take(I * p2 * p2 * 64); b->d31 = pl.take(I * p2 * p2 * 32);
+  b->up4 = pl.take(I * P * P * 32); b->d40 = pl.take(I * P * P * 32);
+  b->pred = pl.take(I * P * P); b->conf = pl.take(I * P * P); b->depth_p = pl.take(I * p4 * p4);
+  return pl.off;
+}
+
+static int ensure_workspace(ofb_handle* h, int imgs, int P, Buffers* b) {
+  Buffers tmp;
+  float* saved = h->ws;
+  h->ws = nullptr;
+  size_t need = plan_buffers(h, imgs, P, &tmp);
+  h->ws = saved;
+  if (need > h->ws_floats) {
+    if (h->ws) cudaFree(h->ws);
+    h->ws = nullptr; h->ws_floats = 0;
+    OFB_CUDA(cudaMalloc(&h->ws, need * sizeof(float)));
+    h->ws_floats = need;
+  }
+  plan_buffers(h, imgs, P, b);
+  return 0;
+}
+
+// ----------------------------------------------------------------- schedule
+struct Ctx { ofb_handle* h; cudaStream_t s; int imgs; };
+
+// Brackets one launch with CUDA events on the launch stream when profiling is on.
+struct Prof {
+  ofb_handle* h; cudaStream_t s; bool on;
+  Prof(ofb_handle* h_, cudaStream_t s_, const std::string& name, double flops, double bytes) : h(h_), s(s_), on(h_->profile) {
+    if (!on) return;
+    ofb_handle::Rec r; r.name = name; r.flops = flops; r.bytes = bytes;
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, s);
+    h->recs.push_back(r);
+  }
+  ~Prof() { if (on) cudaEventRecord(h->recs.back().e1, s); }
+};
+
+static std::string conv_class(const ofb_conv_desc& d) {
+  char buf[96];
+  int oh = (d.h + 2 * d.pad - d.k) / d.stride + 1;
+  snprintf(buf, sizeof(buf), "conv%dx%ds%d_c%d_o%d_@%d", d.k, d.k, d.stride, d.c0 + d.c1, d.cout, oh);
+  return buf;
+}
+static void conv_work(const ofb_conv_desc& d, double* flops, double* bytes) {
+  double oh = (d.h + 2 * d.pad - d.k) / d.stride + 1, ow = (d.w + 2 * d.pad - d.k) / d.stride + 1;
+  double M = (double)d.n * oh * ow, K = (double)d.k * d.k * (d.c0 + d.c1);
+  *flops = 2.0 * M * d.cout * K;
+  *bytes = 4.0 * ((double)d.n * d.h * d.w * (d.c0 + d.c1) + M * d.cout * (d.residual ? 2 : 1) + (double)d.cout * K);
+}
+
+static int run_conv(Ctx& c, const ConvW& w, const float* in0, int c0, const float* in1, int c1, int hh, int ww,
+                    int stride, int pad, const float* residual, int act, float* out) {
+  ofb_conv_desc d{};
+  d.in0 = in0; d.in1 = in1; d.c0 = c0; d.c1 = c1; d.n = c.imgs; d.h = hh; d.w = ww;
+  d.wgt = w.w; d.k = w.k; d.stride = stride; d.pad = pad; d.cout = w.cout;
+  d.scale = w.scale; d.shift = w.shift; d.residual = residual; d.act = act; d.out = out;
+  d.engine = c.h->engine;
+  OFB_CHECK(w.w && w.cin == c0 + c1, "forward: conv weight/channel mismatch (%d vs %d+%d)", w.cin, c0, c1);
+  double fl, by;
+  conv_work(d, &fl, &by);
+  Prof pr(c.h, c.s, conv_class(d), fl, by);
+  return conv_dispatch(&d, c.s);
+}
+
+static int run_linear(Ctx& c, const ConvW& w, const float* in, const float* residual, int act, float* out) {
+  ofb_conv_desc d{};
+  d.in0 = in; d.c0 = w.cin; d.n = c.imgs; d.h = 1; d.w = 1;
+  d.wgt = w.w; d.k = 1; d.stride = 1; d.pad = 0; d.cout = w.cout;
+  d.scale = nullptr; d.shift = w.shift; d.residual = residual; d.act = act; d.out = out;
+  d.engine = c.h->engine;
+  double fl, by;
+  conv_work(d, &fl, &by);
+  char nm[64];
+  snprintf(nm, sizeof(nm), "linear_k%d_o%d", w.cin, w.cout);
+  Prof pr(c.h, c.s, nm, fl, by);
+  return conv_dispatch(&d, c.s);
+}
+
+// torchvision BasicBlock stack: relu(bn2(conv2(relu(bn1(conv1 x)))) + identity/downsample)
+static int run_res_layer(Ctx& c, int l, const float* in, int cin, int hin, float* tmp, float* pa, float* pb,
+                         float* ds, float* out_final) {
+  int ch = kChan[l], nb = kBlocks[l];
+  int stride = l == 0 ? 1 : 2;
+  int hout = hin / stride;
+  const float* x = in;
+  int xc = cin, xh = hin;
+  for (int b = 0; b < nb; ++b) {
+    std::string p = "layer" + std::to_string(l + 1) + "." + std::to_string(b);
+    int st = b == 0 ? stride : 1;
+    float* y = (b == nb - 1) ? out_final : ((b & 1) ? pb : pa);
+    if (run_conv(c, c.h->conv[p + ".conv1"], x, xc, nullptr, 0, xh, xh, st, 1, nullptr, OFB_ACT_RELU, tmp)) return -1;
+    const float* idn = x;
+    auto it = c.h->conv.find(p + ".ds");
+    if (it != c.h->conv.end()) {
+      if (run_conv(c, it->second, x, xc, nullptr, 0, xh, xh, st, 0, nullptr, OFB_ACT_NONE, ds)) return -1;
+      idn = ds;
+    }
+    if (run_conv(c, c.h->conv[p + ".conv2"], tmp, ch, nullptr, 0, hout, hout, 1, 1, idn, OFB_ACT_RELU, y)) return -1;
+    x = y; xc = ch; xh = hout;
+  }
+  return 0;
+}
+
+static void reg(ofb_handle* h, const char* name, float* p, int n, int hh, int ww, int cc) {
+  Act a; a.p = p; a.n = n; a.h = hh; a.w = ww; a.c = cc;
+  h->acts[name] = a;
+}
+
+static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int confidence,
+                         float* const* outs, size_t out_off, cudaStream_t s) {
+  const ofb_geometry& g = h->geo;
+  const int N = g.n_patch, P = g.patch, p4 = P / 4, He = g.erp_h, We = g.erp_w;
+  const int imgs = Bc * N;
+  Buffers b;
+  if (ensure_workspace(h, imgs, P, &b)) return -1;
+  Ctx c{h, s, imgs};
+  void* vs = (void*)s;
+
+  for (int it = 0; it < iters; ++it) {
+    bool reuse = it > 0 && h->dedup;
+    if (!reuse) {
+      // equi2pers(rgb, P) -> patches; stem; pool; layer1 (spherical_model_iterative.py:315,322-324)
+      { Prof pr(h, s, "e2p_rgb", 0.0, 4.0*((double)Bc*3*He*We + (double)imgs*P*P*4));
+      if (ofb_equi2pers_f32(rgb, Bc, 3, He, We, g.grid_hi, N, P, P, b.patches, OFB_LAYOUT_FOLDED, vs)) return -1; }
+      const ConvW& st = h->conv["stem"];
+      { Prof pr(h, s, "stem7x7", 0.0, 4.0*((double)imgs*P*P*4 + (double)imgs*(P/2)*(P/2)*64));
+      if (ofb_stem_f32(b.patches, imgs, P, P, st.w, st.scale, st.shift, b.conv1, vs)) return -1; }
+      { Prof pr(h, s, "maxpool", 0.0, 4.0*((double)imgs*(P/2)*(P/2)*64 + (double)imgs*p4*p4*64));
+      if (ofb_maxpool3x3s2_f32(b.conv1, imgs, P / 2, P / 2, 64, b.pool, vs)) return -1; }
+      if (run_res_layer(c, 0, b.pool, 64, p4, b.l1t, b.l1a, b.l1b, nullptr, b.layer1_pre)) return -1;
+    }
+    // point embedding added to layer1 (:319-320,325 / :385-393)
+    const float* depth = nullptr;
+    if (it > 0) {
+      { Prof pr(h, s, "e2p_depth", 0.0, 4.0*((double)Bc*He*We + (double)imgs*p4*p4));
+      if (ofb_equi2pers_f32(outs[it - 1] + out_off, Bc, 1, He, We, g.grid_lo, N, p4, p4, b.depth_p,
+                            OFB_LAYOUT_FOLDED, vs)) return -1; }
+      depth = b.depth_p;
+    }
+    const Mlp& mp = h->mlp[it > 0 ? 1 : 0];
+    OFB_CHECK(mp.cin == g.pts_c, "forward: point table has %d channels, mlp expects %d", g.pts_c, mp.cin);
+    { Prof pr(h, s, "point_embed", 0.0, 4.0*((double)imgs*p4*p4*128));
+    if (ofb_point_embed_f32(g.pts, N, mp.cin, p4, depth, imgs, mp.w1, mp.s1, mp.t1, mp.w2, mp.s2, mp.t2,
+                            b.layer1_pre, b.layer1, vs)) return -1; }
+    if (run_res_layer(c, 1, b.layer1, 64, p4, b.l2t, b.l2a, b.l2b, b.l2d, b.layer2)) return -1;
+    if (run_res_layer(c, 2, b.layer2, 128, P / 8, b.l3t, b.l3a, b.l3b, b.l3d, b.layer3)) return -1;
+    if (run_res_layer(c, 3, b.layer3, 256, P / 16, b.l4t, b.l4a, b.l4b, b.l4d, b.layer4)) return -1;
+
+    // tokens: down1 1x1 conv (+bias) over the 4x4x512 map -> (imgs,512) (:330-331)
+    {
+      Ctx c16{h, s, imgs * 16};
+      if (run_linear(c16, h->down, b.layer4, nullptr, OFB_ACT_NONE, b.down)) return -1;
+    }
+    OFB_CHECK(h->pos_patches == N, "forward: pos_emb has %d patches, geometry has %d", h->pos_patches, N);
+    { Prof pr(h, s, "token_pack", 0.0, 4.0*((double)imgs*1024));
+    if (ofb_token_pack_f32(b.down, h->pos_emb, imgs, N, b.tok, vs)) return -1; }
+    float* x = b.tok;
+    float* y = b.tok2;
+    for (int i = 0; i < 6; ++i) {   // Transformer_Block, model/blocks.py:84-88
+      Block& B = h->blk[i];
+      { Prof pr(h, s, "layernorm", 0.0, 4.0*((double)imgs*1024));
+      if (ofb_layernorm_f32(x, B.n1g, B.n1b, imgs, 512, 1e-5f, b.ln, vs)) return -1; }
+      if (run_linear(c, B.q, b.ln, nullptr, OFB_ACT_NONE, b.q)) return -1;
+      if (run_linear(c, B.kv, b.ln, nullptr, OFB_ACT_NONE, b.kv)) return -1;
+      { Prof pr(h, s, "attention", 0.0, 4.0*((double)imgs*2048));
+      if (ofb_attention_f32(b.q, b.kv, Bc, N, 4, 128, b.att, vs)) return -1; }
+      if (run_linear(c, B.proj, b.att, x, OFB_ACT_NONE, y)) return -1;          // y = x + proj(att)
+      { Prof pr(h, s, "layernorm", 0.0, 4.0*((double)imgs*1024));
+      if (ofb_layernorm_f32(y, B.n2g, B.n2b, imgs, 512, 1e-5f, b.ln, vs)) return -1; }
+      if (run_linear(c, B.fc1, b.ln, nullptr, OFB_ACT_GELU, b.fc1)) return -1;
+      if (run_linear(c, B.fc2, b.fc1, y, OFB_ACT_NONE, x)) return -1;           // x = y + fc2(gelu(fc1))
+    }
+    { Prof pr(h, s, "layernorm", 0.0, 4.0*((double)imgs*1024));
+    if (ofb_layernorm_f32(x, h->enc_g, h->enc_b, imgs, 512, 1e-6f, b.enc, vs)) return -1; }
+
+    // decoder (:337-369); the token broadcast-add (:334-335) is fused into the first upsample
+    { Prof pr(h, s, "upsample2x_c512", 0.0, 4.0*5.0*(double)imgs*(P / 32)*(P / 32)*512);
+    if (ofb_upsample2x_f32(b.layer4, b.enc, imgs, P / 32, P / 32, 512, b.up0, vs)) return -1; }
+    if (run_conv(c, h->conv["de_conv0_0"], b.up0, 512, nullptr, 0, P / 16, P / 16, 1, 1, nullptr, OFB_ACT_RELU, b.d00)) return -1;
+    if (run_conv(c, h->conv["de_conv0_1"], b.d00, 256, b.layer3, 256, P / 16, P / 16, 1, 1, nullptr, OFB_ACT_RELU, b.d01)) return -1;
+    { Prof pr(h, s, "upsample2x_c128", 0.0, 4.0*5.0*(double)imgs*(P / 16)*(P / 16)*128);
+    if (ofb_upsample2x_f32(b.d01, nullptr, imgs, P / 16, P / 16, 128, b.up1, vs)) return -1; }
+    if (run_conv(c, h->conv["de_conv1_0"], b.up1, 128, nullptr, 0, P / 8, P / 8, 1, 1, nullptr, OFB_ACT_RELU, b.d10)) return -1;
+    if (run_conv(c, h->conv["de_conv1_1"], b.d10, 128, b.layer2, 128, P / 8, P / 8, 1, 1, nullptr, OFB_ACT_RELU, b.d11)) return -1;
+    { Prof pr(h, s, "upsample2x_c64", 0.0, 4.0*5.0*(double)imgs*(P / 8)*(P / 8)*64);
+    if (ofb_upsample2x_f32(b.d11, nullptr, imgs, P / 8, P / 8, 64, b.up2, vs)) return -1; }
+    if (run_conv(c, h->conv["de_conv2_0"], b.up2, 64, nullptr, 0, p4, p4, 1, 1, nullptr, OFB_ACT_RELU, b.d20)) return -1;
+    if (run_conv(c, h->conv["de_conv2_1"], b.d20, 64, b.layer1, 64, p4, p4, 1, 1, nullptr, OFB_ACT_RELU, b.d21)) return -1;
+    { Prof pr(h, s, "upsample2x_c64", 0.0, 4.0*5.0*(double)imgs*(p4)*(p4)*64);
+    if (ofb_upsample2x_f32(b.d21, nullptr, imgs, p4, p4, 64, b.up3, vs)) return -1; }
+    if (run_conv(c, h->conv["de_conv3_0"], b.up3, 64, nullptr, 0, P / 2, P / 2, 1, 1, nullptr, OFB_ACT_RELU, b.d30)) return -1;
+    if (run_conv(c, h->conv["de_conv3_1"], b.d30, 64, b.conv1, 64, P / 2, P / 2, 1, 1, nullptr, OFB_ACT_RELU, b.d31)) return -1;
+    { Prof pr(h, s, "upsample2x_c32", 0.0, 4.0*5.0*(double)imgs*(P / 2)*(P / 2)*32);
+    if (ofb_upsample2x_f32(b.d31, nullptr, imgs, P / 2, P / 2, 32, b.up4, vs)) return -1; }
+    if (run_conv(c, h->conv["de_conv4_0"], b.up4, 32, nullptr, 0, P, P, 1, 1, nullptr, OFB_ACT_RELU, b.d40)) return -1;
+
+    // heads + ERP merge (:371-380)
+    { Prof pr(h, s, "heads", 0.0, 4.0*((double)imgs*P*P*34));
+    if (ofb_heads_f32(b.d40, imgs, P, P, h->pred_w, h->pred_b, h->conf_w, h->conf_b, confidence, b.pred, b.conf, vs)) return -1; }
+    float* out = outs[it] + out_off;
+    if (confidence) {
+      { Prof pr(h, s, "blend_conf", 0.0, 4.0*((double)imgs*P*P*2 + (double)Bc*He*We));
+      if (ofb_blend_conf_f32(b.pred, b.conf, Bc, N, P, P, g.blend_rowptr, g.blend_idx, g.blend_w, He, We, out, vs)) return -1; }
+    } else {
+      { Prof pr(h, s, "pers2equi", 0.0, 4.0*((double)imgs*P*P + (double)Bc*He*We));
+      if (ofb_pers2equi_f32(b.pred, Bc, 1, N, P, P, OFB_LAYOUT_FOLDED, g.blend_rowptr, g.blend_idx, g.blend_w, He, We, out, vs)) return -1; }
+    }
+  }
+  reg(h, "patches", b.patches, imgs, P, P, 4); reg(h, "conv1", b.conv1, imgs, P / 2, P / 2, 64);
+  reg(h, "pool", b.pool, imgs, p4, p4, 64); reg(h, "layer1_pre", b.layer1_pre, imgs, p4, p4, 64);
+  reg(h, "layer1", b.layer1, imgs, p4, p4, 64); reg(h, "layer2", b.layer2, imgs, P / 8, P / 8, 128);
+  reg(h, "layer3", b.layer3, imgs, P / 16, P / 16, 256); reg(h, "layer4", b.layer4, imgs, P / 32, P / 32, 512);
+  reg(h, "tokens", b.down, imgs, 4, 4, 32); reg(h, "encoded", b.enc, imgs, 1, 1, 512);
+  reg(h, "de_conv0_1", b.d01, imgs, P / 16, P / 16, 128); reg(h, "de_conv1_1", b.d11, imgs, P / 8, P / 8, 64);
+  reg(h, "de_conv2_1", b.d21, imgs, p4, p4, 64); reg(h, "de_conv3_1", b.d31, imgs, P / 2, P / 2, 32);
+  reg(h, "de_conv4_0", b.d40, imgs, P, P, 32); reg(h, "pred_patch", b.pred, imgs, P, P, 1);
+  reg(h, "conf_patch", b.conf, imgs, P, P, 1);
+  return 0;
+}
+
+}  // namespace ofb
+
+// ------------------------------------------------------------------ C ABI
+extern "C" int ofb_version(void) { return OFB_VERSION; }
+extern "C" const char* ofb_last_error(void) { return g_err.c_str(); }
+extern "C" int64_t ofb_launch_count(int reset) {
+  long long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+extern "C" int ofb_set_device(int device) {
+  OFB_CUDA(cudaSetDevice(device));
+  return 0;
+}
+
+extern "C" int ofb_conv_f32(const ofb_conv_desc* d, void* stream) { return conv_dispatch(d, (cudaStream_t)stream); }
+
+extern "C" int ofb_create(int device, ofb_handle** out) {
+  OFB_CHECK(out, "create: null out pointer");
+  int count = 0;
+  OFB_CUDA(cudaGetDeviceCount(&count));
+  OFB_CHECK(device >= 0 && device < count, "create: device %d out of range (%d visible)", device, count);
+  cudaDeviceProp prop;
+  OFB_CUDA(cudaGetDeviceProperties(&prop, device));
+  OFB_CHECK(prop.major == 10, "create: libofb is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+  OFB_CUDA(cudaSetDevice(device));
+  ofb_handle* h = new ofb_handle();
+  h->device = device;
+  *out = h;
+  return 0;
+}
+
+extern "C" int ofb_destroy(ofb_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  free_weights(h);
+  if (h->ws) cudaFree(h->ws);
+  delete h;
+  return 0;
+}
+
+extern "C" int ofb_set_geometry(ofb_handle* h, const ofb_geometry* g) {
+  OFB_CHECK(h && g, "set_geometry: null pointer");
+  OFB_CHECK(g->grid_hi && g->grid_lo && g->pts && g->blend_rowptr && g->blend_idx && g->blend_w, "set_geometry: null table");
+  OFB_CHECK(g->patch == 128, "set_geometry: the token path is hard-wired to patch 128 (32*(P/32)^2 == 512), got %d", g->patch);
+  OFB_CHECK(g->n_patch > 0 && g->n_patch <= 64, "set_geometry: n_patch must be in [1,64], got %d", g->n_patch);
+  OFB_CHECK(g->pts_c == 3 || g->pts_c == 5, "set_geometry: pts_c must be 3 or 5");
+  h->geo = *g;
+  h->has_geo = true;
+  return 0;
+}
+
+extern "C" int ofb_load_weights(ofb_handle* h, const ofb_tensor_desc* tensors, int count, int single_stage) {
+  OFB_CHECK(h && tensors && count > 0, "load_weights: bad arguments");
+  OFB_CUDA(cudaSetDevice(h->device));
+  free_weights(h);
+  TMap m;
+  for (int i = 0; i < count; ++i) {
+    OFB_CHECK(tensors[i].name && tensors[i].data, "load_weights: tensor %d has null name/data", i);
+    m[tensors[i].name] = &tensors[i];
+  }
+  h->single = single_stage != 0;
+  if (load_all(h, m, h->single)) { free_weights(h); return -1; }
+  h->has_weights = true;
+  return 0;
+}
+
+extern "C" int ofb_set_option(ofb_handle* h, const char* key, int value) {
+  OFB_CHECK(h && key, "set_option: null pointer");
+  if (!strcmp(key, "engine")) h->engine = value;
+  else if (!strcmp(key, "chunk")) h->chunk = value;
+  else if (!strcmp(key, "dedup")) h->dedup = value;
+  else OFB_CHECK(false, "set_option: unknown key '%s'", key);
+  return 0;
+}
+
+extern "C" int ofb_forward_f32(ofb_handle* h, const float* rgb, int B, int iters, int confidence,
+                               float* const* out_depth, void* stream) {
+  OFB_CHECK(h && rgb && out_depth, "forward: null pointer");
+  OFB_CHECK(h->has_geo, "forward: ofb_set_geometry has not been called");
+  OFB_CHECK(h->has_weights, "forward: ofb_load_weights has not been called");
+  OFB_CHECK(B > 0 && iters >= 1, "forward: bad batch/iters");
+  OFB_CHECK(!h->single || iters == 1, "forward: the single-stage model runs exactly one iteration");
+  OFB_CUDA(cudaSetDevice(h->device));
+  for (int i = 0; i < iters; ++i) OFB_CHECK(out_depth[i], "forward: out_depth[%d] is null", i);
+  int N = h->geo.n_patch;
+  int chunk = h->chunk > 0 ? h->chunk : (576 / N > 0 ? 576 / N : 1);
+  size_t plane = (size_t)h->geo.erp_h * h->geo.erp_w;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    int Bc = B - b0 < chunk ? B - b0 : chunk;
+    if (forward_chunk(h, rgb + (size_t)b0 * 3 * plane, Bc, iters, confidence, out_depth, (size_t)b0 * plane,
+                      (cudaStream_t)stream))
+      return -1;
+  }
+  return 0;
+}
+
+extern "C" int ofb_profile_enable(ofb_handle* h, int on) {
+  OFB_CHECK(h, "profile_enable: null handle");
+  h->profile = on != 0;
+  return 0;
+}
+
+extern "C" int ofb_profile_report(ofb_handle* h, char* buf, int capacity) {
+  OFB_CHECK(h && buf && capacity > 0, "profile_report: bad arguments");
+  struct Agg { int n = 0; double ms = 0, flops = 0, bytes = 0; };
+  std::map<std::string, Agg> agg;
+  std::vector<std::string> order;
+  for (auto& r : h->recs) {
+    OFB_CUDA(cudaEventSynchronize(r.e1));
+    float ms = 0.f;
+    OFB_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    if (!agg.count(r.name)) order.push_back(r.name);
+    Agg& a = agg[r.name];
+    a.n++; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
+  }
+  h->recs.clear();
+  int off = 0;
+  for (auto& k : order) {
+    Agg& a = agg[k];
+    int w = snprintf(buf + off, capacity - off, "%s %d %.6f %.6e %.6e\n", k.c_str(), a.n, a.ms, a.flops, a.bytes);
+    if (w < 0 || w >= capacity - off) break;
+    off += w;
+  }
+  return off;
+}
+
+extern "C" int64_t ofb_get_activation(ofb_handle* h, const char* name, float* dst, int64_t capacity, int dims[4],
+                                      void* stream) {
+  OFB_CHECK(h && name, "get_activation: null pointer");
+  auto it = h->acts.find(name);
+  OFB_CHECK(it != h->acts.end(), "get_activation: unknown activation '%s'", name);
+  const Act& a = it->second;
+  int64_t n = (int64_t)a.n * a.h * a.w * a.c;
+  if (dims) { dims[0] = a.n; dims[1] = a.h; dims[2] = a.w; dims[3] = a.c; }
+  if (dst) {
+    OFB_CHECK(capacity >= n, "get_activation: capacity %lld < %lld", (long long)capacity, (long long)n);
+    OFB_CUDA(cudaMemcpyAsync(dst, a.p, n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  }
+  return n;
+}

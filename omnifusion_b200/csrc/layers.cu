@@ -1,0 +1,461 @@
+// Bandwidth-bound network kernels over folded NHWC: stem conv, max-pool, 2x bilinear
+// upsample, point embedding, token packing, LayerNorm, attention core, depth/confidence heads.
+#include "common.cuh"
+
+namespace ofb {
+
+// ----------------------------------------------------------------------- stem
+// Conv 7x7 s2 p3, 3(+1 pad)->64, BN, ReLU (spherical_model_iterative.py:322).
+// CTA: 8x16 output pixels x 64 couts; 128 threads, each 2 pixels (rows r, r+4) x 32 couts.
+// Input halo tile (21x37 float4) and the whole 50 KB filter live in shared memory.
+constexpr int STEM_TH = 8, STEM_TW = 16;
+constexpr int STEM_IH = STEM_TH * 2 + 5, STEM_IW = STEM_TW * 2 + 5;
+constexpr int STEM_SMEM = (49 * 4 * 64 + STEM_IH * STEM_IW * 4) * 4;
+
+__global__ void __launch_bounds__(128)
+stem_kernel(const float* __restrict__ in, int n, int h, int w, const float* __restrict__ wgt,
+            const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  float* sw = smem;                               // [tap][c][64]
+  float4* si = reinterpret_cast<float4*>(smem + 49 * 4 * 64);  // [IH][IW]
+  const int oh_n = h / 2, ow_n = w / 2;
+  const int tiles_w = ow_n / STEM_TW, tiles_h = oh_n / STEM_TH;
+  int t = blockIdx.x;
+  int img = t / (tiles_w * tiles_h);
+  int r = t - img * tiles_w * tiles_h;
+  int th = r / tiles_w, tw = r - th * tiles_w;
+  int oh0 = th * STEM_TH, ow0 = tw * STEM_TW;
+  int ih0 = oh0 * 2 - 3, iw0 = ow0 * 2 - 3;
+  const int tid = threadIdx.x;
+  // weights: global OHWI (64,7,7,4) -> smem [tap][c][co]
+  for (int i = tid; i < 64 * 49 * 4; i += 128) {
+    int co = i / (49 * 4), rem = i - co * 49 * 4;
+    sw[rem * 64 + co] = __ldg(&wgt[i]);
+  }
+  for (int i = tid; i < STEM_IH * STEM_IW; i += 128) {
+    int y = i / STEM_IW, x = i - y * STEM_IW;
+    int ih = ih0 + y, iw = iw0 + x;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ih >= 0 && ih < h && iw >= 0 && iw < w)
+      v = __ldg(reinterpret_cast<const float4*>(in + ((size_t)(img * h + ih) * w + iw) * 4));
+    si[i] = v;
+  }
+  __syncthreads();
+  int half = tid >> 6;                 // cout half: 32 couts
+  int p = tid & 63;                    // pixel pair id
+  int pr = p / STEM_TW, pc = p - pr * STEM_TW;   // pr in [0,4)
+  float acc0[32], acc1[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc0[j] = acc1[j] = 0.f;
+  for (int kh = 0; kh < 7; ++kh) {
+    for (int kw = 0; kw < 7; ++kw) {
+      float4 x0 = si[(pr * 2 + kh) * STEM_IW + pc * 2 + kw];
+      float4 x1 = si[((pr + 4) * 2 + kh) * STEM_IW + pc * 2 + kw];
+      const float* wp = sw + (kh * 7 + kw) * 4 * 64 + half * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 w0 = *reinterpret_cast<const float4*>(wp + j);
+        float4 w1 = *reinterpret_cast<const float4*>(wp + 64 + j);
+        float4 w2 = *reinterpret_cast<const float4*>(wp + 128 + j);
+        acc0[j] += x0.x * w0.x + x0.y * w1.x + x0.z * w2.x;
+        acc0[j + 1] += x0.x * w0.y + x0.y * w1.y + x0.z * w2.y;
+        acc0[j + 2] += x0.x * w0.z + x0.y * w1.z + x0.z * w2.z;
+        acc0[j + 3] += x0.x * w0.w + x0.y * w1.w + x0.z * w2.w;
+        acc1[j] += x1.x * w0.x + x1.y * w1.x + x1.z * w2.x;
+        acc1[j + 1] += x1.x * w0.y + x1.y * w1.y + x1.z * w2.y;
+        acc1[j + 2] += x1.x * w0.z + x1.y * w1.z + x1.z * w2.z;
+        acc1[j + 3] += x1.x * w0.w + x1.y * w1.w + x1.z * w2.w;
+      }
+    }
+  }
+  float* o0 = out + ((size_t)(img * oh_n + oh0 + pr) * ow_n + ow0 + pc) * 64 + half * 32;
+  float* o1 = o0 + (size_t)4 * ow_n * 64;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    float4 s = __ldg(reinterpret_cast<const float4*>(scale + half * 32 + j));
+    float4 b = __ldg(reinterpret_cast<const float4*>(shift + half * 32 + j));
+    float4 v0, v1;
+    v0.x = fmaxf(acc0[j] * s.x + b.x, 0.f); v0.y = fmaxf(acc0[j + 1] * s.y + b.y, 0.f);
+    v0.z = fmaxf(acc0[j + 2] * s.z + b.z, 0.f); v0.w = fmaxf(acc0[j + 3] * s.w + b.w, 0.f);
+    v1.x = fmaxf(acc1[j] * s.x + b.x, 0.f); v1.y = fmaxf(acc1[j + 1] * s.y + b.y, 0.f);
+    v1.z = fmaxf(acc1[j + 2] * s.z + b.z, 0.f); v1.w = fmaxf(acc1[j + 3] * s.w + b.w, 0.f);
+    st4(o0 + j, v0);
+    st4(o1 + j, v1);
+  }
+}
+
+// -------------------------------------------------------------------- maxpool
+__global__ void maxpool_kernel(const float* __restrict__ in, int n, int h, int w, int c4,
+                               float* __restrict__ out) {
+  int oh_n = h / 2, ow_n = w / 2;
+  size_t total = (size_t)n * oh_n * ow_n * c4;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % c4);
+  size_t r = i / c4;
+  int ow = (int)(r % ow_n); r /= ow_n;
+  int oh = (int)(r % oh_n);
+  int img = (int)(r / oh_n);
+  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  const float4* src = reinterpret_cast<const float4*>(in);
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+    int ih = oh * 2 + dy;
+    if (ih < 0 || ih >= h) continue;
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      int iw = ow * 2 + dx;
+      if (iw < 0 || iw >= w) continue;
+      float4 v = __ldg(&src[((size_t)(img * h + ih) * w + iw) * c4 + c]);
+      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+  }
+  reinterpret_cast<float4*>(out)[i] = m;
+}
+
+// ------------------------------------------------------------------- upsample
+// F.interpolate(scale 2, bilinear, align_corners=False): src = (dst+0.5)/2-0.5 clamped at 0,
+// i1 = min(i0+1, size-1), lambda in {0, .25, .75}.  Same expression tree as ATen's
+// upsample_bilinear2d: h0*(w0*a + w1*b) + h1*(w0*c + w1*d).
+__global__ void upsample2x_kernel(const float* __restrict__ in, const float* __restrict__ img_bias,
+                                  int n, int h, int w, int c4, float* __restrict__ out) {
+  int oh_n = h * 2, ow_n = w * 2;
+  size_t total = (size_t)n * oh_n * ow_n * c4;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % c4);
+  size_t r = i / c4;
+  int ow = (int)(r % ow_n); r /= ow_n;
+  int oh = (int)(r % oh_n);
+  int img = (int)(r / oh_n);
+  float sy = fmaxf(0.5f * (oh + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.5f * (ow + 0.5f) - 0.5f, 0.f);
+  int y0 = (int)sy, x0 = (int)sx;
+  int y1 = y0 + (y0 < h - 1), x1 = x0 + (x0 < w - 1);
+  float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
+  const float4* src = reinterpret_cast<const float4*>(in) + (size_t)img * h * w * c4 + c;
+  float4 a = __ldg(&src[((size_t)y0 * w + x0) * c4]);
+  float4 b = __ldg(&src[((size_t)y0 * w + x1) * c4]);
+  float4 cc = __ldg(&src[((size_t)y1 * w + x0) * c4]);
+  float4 d = __ldg(&src[((size_t)y1 * w + x1) * c4]);
+  if (img_bias) {
+    float4 bb = __ldg(reinterpret_cast<const float4*>(img_bias) + (size_t)img * c4 + c);
+    a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+    b.x += bb.x; b.y += bb.y; b.z += bb.z; b.w += bb.w;
+    cc.x += bb.x; cc.y += bb.y; cc.z += bb.z; cc.w += bb.w;
+    d.x += bb.x; d.y += bb.y; d.z += bb.z; d.w += bb.w;
+  }
+  float4 o;
+  o.x = hy * (hx * a.x + lx * b.x) + ly * (hx * cc.x + lx * d.x);
+  o.y = hy * (hx * a.y + lx * b.y) + ly * (hx * cc.y + lx * d.y);
+  o.z = hy * (hx * a.z + lx * b.z) + ly * (hx * cc.z + lx * d.z);
+  o.w = hy * (hx * a.w + lx * b.w) + ly * (hx * cc.w + lx * d.w);
+  reinterpret_cast<float4*>(out)[i] = o;
+}
+
+// ---------------------------------------------------------------- point embed
+// 16 threads per pixel, 4 of the 64 output channels each; the 16-wide hidden layer is
+// recomputed per thread (48 FMA) - the kernel is bound by its 256 B/pixel store.
+__global__ void point_embed_kernel(const float* __restrict__ pts, int N, int cin, int p,
+                                   const float* __restrict__ depth, int imgs,
+                                   const float* __restrict__ w1, const float* __restrict__ s1,
+                                   const float* __restrict__ t1, const float* __restrict__ w2,
+                                   const float* __restrict__ s2, const float* __restrict__ t2,
+                                   const float* __restrict__ base, float* __restrict__ out) {
+  size_t total = (size_t)imgs * p * p * 16;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int g = (int)(i & 15);
+  size_t pix = i >> 4;
+  int xy = (int)(pix % (p * p));
+  int img = (int)(pix / (p * p));
+  int n = img % N;
+  float in[5];
+  float dsc = depth ? __ldg(&depth[pix]) : 1.f;
+  for (int c = 0; c < cin; ++c) {
+    float v = __ldg(&pts[((size_t)n * cin + c) * p * p + xy]);
+    in[c] = (depth && c < 3) ? v * dsc : v;
+  }
+  float hid[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    float a = 0.f;
+    for (int c = 0; c < cin; ++c) a += in[c] * __ldg(&w1[k * cin + c]);
+    hid[k] = fmaxf(a * __ldg(&s1[k]) + __ldg(&t1[k]), 0.f);
+  }
+  float o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int co = g * 4 + j;
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a += hid[k] * __ldg(&w2[co * 16 + k]);
+    o[j] = fmaxf(a * __ldg(&s2[co]) + __ldg(&t2[co]), 0.f);
+  }
+  size_t off = pix * 64 + g * 4;
+  float4 v = make_float4(o[0], o[1], o[2], o[3]);
+  if (base) {
+    float4 b = __ldg(reinterpret_cast<const float4*>(base + off));
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+  }
+  st4(out + off, v);
+}
+
+// ----------------------------------------------------------------- token pack
+__global__ void token_pack_kernel(const float* __restrict__ down, const float* __restrict__ pos,
+                                  int imgs, int N, float* __restrict__ tokens) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= imgs * 512) return;
+  int img = i >> 9, t = i & 511;
+  int c = t >> 4, ij = t & 15;
+  tokens[i] = down[(size_t)img * 512 + ij * 32 + c] + __ldg(&pos[(img % N) * 512 + t]);
+}
+
+// ------------------------------------------------------------------ layernorm
+// One warp per row; mean, then variance of the centred values (two passes in registers).
+template <int DIM>
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, int rows, float eps,
+                                 float* __restrict__ y) {
+  constexpr int PER = DIM / 32;
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (size_t)row * DIM;
+  float v[PER];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; i += 4) {
+    float4 t = ld4(xr + (i / 4) * 128 + lane * 4);
+    v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+    s += t.x + t.y + t.z + t.w;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  float mean = s / DIM;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { float d = v[i] - mean; q += d * d; }
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  float rstd = rsqrtf(q / DIM + eps);
+  // rsqrtf is approximate (2 ulp); one Newton step makes it correctly-rounded-ish
+  float var = q / DIM + eps;
+  rstd = rstd * (1.5f - 0.5f * var * rstd * rstd);
+#pragma unroll
+  for (int i = 0; i < PER; i += 4) {
+    int col = (i / 4) * 128 + lane * 4;
+    float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    float4 b = __ldg(reinterpret_cast<const float4*>(beta + col));
+    float4 o;
+    o.x = (v[i] - mean) * rstd * g.x + b.x;
+    o.y = (v[i + 1] - mean) * rstd * g.y + b.y;
+    o.z = (v[i + 2] - mean) * rstd * g.z + b.z;
+    o.w = (v[i + 3] - mean) * rstd * g.w + b.w;
+    st4(y + (size_t)row * DIM + col, o);
+  }
+}
+
+// ------------------------------------------------------------------ attention
+// One CTA per (panorama, head): N <= 64 tokens, head_dim 128.  Q,K,V staged in shared
+// memory (rows padded to 129 floats), scores + softmax + PV entirely on chip.
+constexpr int ATT_MAXN = 64, ATT_D = 128, ATT_LD = ATT_D + 1;
+
+__global__ void __launch_bounds__(128)
+attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, int N, int heads,
+                 float scale, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  float* sq = sm;
+  float* sk = sq + N * ATT_LD;
+  float* sv = sk + N * ATT_LD;
+  float* sp = sv + N * ATT_LD;        // [N][N+1]
+  int b = blockIdx.x / heads, hd = blockIdx.x % heads;
+  int dim = heads * ATT_D;
+  int tid = threadIdx.x;
+  for (int i = tid; i < N * ATT_D; i += 128) {
+    int r = i / ATT_D, d = i % ATT_D;
+    size_t row = (size_t)b * N + r;
+    sq[r * ATT_LD + d] = q[row * dim + hd * ATT_D + d];
+    sk[r * ATT_LD + d] = kv[row * 2 * dim + hd * ATT_D + d];
+    sv[r * ATT_LD + d] = kv[row * 2 * dim + dim + hd * ATT_D + d];
+  }
+  __syncthreads();
+  for (int i = tid; i < N * N; i += 128) {
+    int r = i / N, c = i % N;
+    float a = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < ATT_D; ++d) a += sq[r * ATT_LD + d] * sk[c * ATT_LD + d];
+    sp[r * (N + 1) + c] = a * scale;
+  }
+  __syncthreads();
+  // softmax: one warp per row
+  int lane = tid & 31, wid = tid >> 5;
+  for (int r = wid; r < N; r += 4) {
+    float m = -INFINITY;
+    for (int c = lane; c < N; c += 32) m = fmaxf(m, sp[r * (N + 1) + c]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int c = lane; c < N; c += 32) {
+      float e = expf(sp[r * (N + 1) + c] - m);
+      sp[r * (N + 1) + c] = e;
+      s += e;
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    float inv = 1.f / s;
+    for (int c = lane; c < N; c += 32) sp[r * (N + 1) + c] *= inv;
+  }
+  __syncthreads();
+  // out[r][d] = sum_c P[r][c] V[c][d]; thread = d
+  for (int r = 0; r < N; ++r) {
+    float a = 0.f;
+    for (int c = 0; c < N; ++c) a += sp[r * (N + 1) + c] * sv[c * ATT_LD + tid];
+    out[((size_t)b * N + r) * dim + hd * ATT_D + tid] = a;
+  }
+}
+
+// ---------------------------------------------------------------------- heads
+// pred / weight_pred 3x3 32->1 convs sharing one read of de_conv4_0
+// (spherical_model_iterative.py:371-374).  CTA = 16x16 pixels; the 18x18x32 halo tile
+// is stored channel-major (odd plane stride: conflict-free for both the transposing
+// store and the per-pixel reads).
+constexpr int HD_T = 16, HD_I = HD_T + 2, HD_PLANE = HD_I * HD_I + 1;
+
+__global__ void __launch_bounds__(256)
+heads_kernel(const float* __restrict__ x, int imgs, int h, int w, const float* __restrict__ wp,
+             float bp, const float* __restrict__ wc, float bc, int confidence,
+             float* __restrict__ pred_out, float* __restrict__ conf_out) {
+  __shared__ float tile[32 * HD_PLANE];
+  __shared__ float swp[288], swc[288];
+  int tiles_w = w / HD_T, tiles_h = h / HD_T;
+  int t = blockIdx.x;
+  int img = t / (tiles_w * tiles_h);
+  int r = t - img * tiles_w * tiles_h;
+  int y0 = (r / tiles_w) * HD_T - 1, x0 = (r % tiles_w) * HD_T - 1;
+  int tid = threadIdx.x;
+  for (int i = tid; i < 288; i += 256) {   // global (tap, c) -> smem [c][tap]
+    int tap = i / 32, c = i % 32;
+    swp[c * 9 + tap] = __ldg(&wp[i]);
+    swc[c * 9 + tap] = confidence ? __ldg(&wc[i]) : 0.f;
+  }
+  for (int i = tid; i < HD_I * HD_I * 32; i += 256) {
+    int c = i & 31, pix = i >> 5;
+    int yy = pix / HD_I, xx = pix - yy * HD_I;
+    int ih = y0 + yy, iw = x0 + xx;
+    float v = 0.f;
+    if (ih >= 0 && ih < h && iw >= 0 && iw < w) v = __ldg(&x[((size_t)(img * h + ih) * w + iw) * 32 + c]);
+    tile[c * HD_PLANE + pix] = v;
+  }
+  __syncthreads();
+  int py = tid / HD_T, px = tid % HD_T;
+  float ap = 0.f, ac = 0.f;
+  for (int c = 0; c < 32; ++c) {
+    const float* tp = tile + c * HD_PLANE + py * HD_I + px;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        float v = tp[ky * HD_I + kx];
+        ap += v * swp[c * 9 + ky * 3 + kx];
+        ac += v * swc[c * 9 + ky * 3 + kx];
+      }
+  }
+  size_t o = (size_t)(img * h + y0 + 1 + py) * w + x0 + 1 + px;
+  float pred = fmaxf(ap + bp, 0.f);
+  if (confidence) {
+    float cf = 1.f / (1.f + expf(-(ac + bc)));
+    pred_out[o] = pred * cf;
+    conf_out[o] = cf;
+  } else {
+    pred_out[o] = pred;
+  }
+}
+
+}  // namespace ofb
+
+using namespace ofb;
+
+extern "C" int ofb_stem_f32(const float* in, int n, int h, int w, const float* wgt, const float* scale,
+                            const float* shift, float* out, void* stream) {
+  OFB_CHECK(in && wgt && scale && shift && out, "stem: null pointer");
+  OFB_CHECK(h % (2 * STEM_TH) == 0 && w % (2 * STEM_TW) == 0, "stem: h,w must be multiples of 16,32 (got %d,%d)", h, w);
+  static bool attr = false;
+  if (!attr) {
+    OFB_CUDA(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM));
+    attr = true;
+  }
+  int blocks = n * (h / 2 / STEM_TH) * (w / 2 / STEM_TW);
+  stem_kernel<<<blocks, 128, STEM_SMEM, (cudaStream_t)stream>>>(in, n, h, w, wgt, scale, shift, out);
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ofb_maxpool3x3s2_f32(const float* in, int n, int h, int w, int c, float* out, void* stream) {
+  OFB_CHECK(in && out && c % 4 == 0 && h % 2 == 0 && w % 2 == 0, "maxpool: bad arguments");
+  size_t total = (size_t)n * (h / 2) * (w / 2) * (c / 4);
+  maxpool_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, n, h, w, c / 4, out);
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ofb_upsample2x_f32(const float* in, const float* img_bias, int n, int h, int w, int c,
+                                  float* out, void* stream) {
+  OFB_CHECK(in && out && c % 4 == 0, "upsample2x: bad arguments");
+  size_t total = (size_t)n * h * 2 * w * 2 * (c / 4);
+  upsample2x_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, img_bias, n, h, w, c / 4, out);
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ofb_point_embed_f32(const float* pts, int N, int cin, int p, const float* depth, int imgs,
+                                   const float* w1, const float* s1, const float* t1, const float* w2,
+                                   const float* s2, const float* t2, const float* base, float* out,
+                                   void* stream) {
+  OFB_CHECK(pts && w1 && s1 && t1 && w2 && s2 && t2 && out, "point_embed: null pointer");
+  OFB_CHECK(cin >= 1 && cin <= 5, "point_embed: cin must be <= 5 (got %d)", cin);
+  size_t total = (size_t)imgs * p * p * 16;
+  point_embed_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      pts, N, cin, p, depth, imgs, w1, s1, t1, w2, s2, t2, base, out);
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ofb_token_pack_f32(const float* down, const float* pos_emb, int imgs, int N, float* tokens,
+                                  void* stream) {
+  OFB_CHECK(down && pos_emb && tokens, "token_pack: null pointer");
+  token_pack_kernel<<<cdiv((long long)imgs * 512, 256), 256, 0, (cudaStream_t)stream>>>(down, pos_emb, imgs, N, tokens);
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ofb_layernorm_f32(const float* x, const float* gamma, const float* beta, int rows, int dim,
+                                 float eps, float* y, void* stream) {
+  OFB_CHECK(x && gamma && beta && y, "layernorm: null pointer");
+  OFB_CHECK(dim == 512, "layernorm: dim must be 512 (got %d)", dim);
+  layernorm_kernel<512><<<cdiv(rows, 4), 128, 0, (cudaStream_t)stream>>>(x, gamma, beta, rows, eps, y);
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ofb_attention_f32(const float* q, const float* kv, int B, int N, int heads, int head_dim,
+                                 float* out, void* stream) {
+  OFB_CHECK(q && kv && out, "attention: null pointer");
+  OFB_CHECK(head_dim == ATT_D && N <= ATT_MAXN && N > 0, "attention: head_dim must be 128 and N <= 64 (got %d, %d)", head_dim, N);
+  int smem = (3 * N * ATT_LD + N * (N + 1)) * 4;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    OFB_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  attention_kernel<<<B * heads, 128, smem, (cudaStream_t)stream>>>(q, kv, N, heads, 1.f / sqrtf((float)head_dim), out);
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ofb_heads_f32(const float* x, int imgs, int h, int w, const float* w_pred, float b_pred,
+                             const float* w_conf, float b_conf, int confidence, float* pred_out,
+                             float* conf_out, void* stream) {
+  OFB_CHECK(x && w_pred && pred_out && (!confidence || (w_conf && conf_out)), "heads: null pointer");
+  OFB_CHECK(h % HD_T == 0 && w % HD_T == 0, "heads: h,w must be multiples of 16");
+  int blocks = imgs * (h / HD_T) * (w / HD_T);
+  heads_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, imgs, h, w, w_pred, b_pred, w_conf, b_conf,
+                                                         confidence, pred_out, conf_out);
+  OFB_LAUNCH_CHECK();
+  return 0;
+}

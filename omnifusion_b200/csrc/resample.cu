@@ -1,0 +1,315 @@
+// Spherical resamplers: equi2pers gather, pers2equi CSR blend, confidence merge.
+// HBM-bound gather kernels: one thread per output element, tables read once per
+// thread and reused across the batch, outputs written coalesced.
+#include "common.cuh"
+
+namespace ofb {
+
+// ------------------------------------------------------------------ equi2pers
+// Bilinear taps of F.grid_sample(bilinear, border, align_corners=True)
+// (equi_pers/equi2pers_v3.py:111).  Written with explicit round-to-nearest
+// intrinsics so no FMA contraction can change the integer taps: the result must be
+// bit-identical to ATen's CPU kernel, which evaluates (g + 1) * ((size - 1) / 2),
+// clamps to [0, size-1] and floors.
+struct E2PTaps {
+  int x0, y0;
+  float wx, wy;
+};
+
+__device__ __forceinline__ E2PTaps e2p_taps(float gx, float gy, int He, int We) {
+  float ix = __fmul_rn(__fadd_rn(gx, 1.f), 0.5f * (float)(We - 1));
+  float iy = __fmul_rn(__fadd_rn(gy, 1.f), 0.5f * (float)(He - 1));
+  ix = fminf(fmaxf(ix, 0.f), (float)(We - 1));
+  iy = fminf(fmaxf(iy, 0.f), (float)(He - 1));
+  float fx = floorf(ix), fy = floorf(iy);
+  E2PTaps t;
+  t.x0 = (int)fx;
+  t.y0 = (int)fy;
+  t.wx = __fsub_rn(ix, fx);
+  t.wy = __fsub_rn(iy, fy);
+  return t;
+}
+
+__device__ __forceinline__ float e2p_sample(const float* __restrict__ plane, const E2PTaps& t,
+                                            int He, int We) {
+  const float* r0 = plane + (size_t)t.y0 * We + t.x0;
+  bool xin = t.x0 + 1 < We, yin = t.y0 + 1 < He;
+  float nw = __ldg(r0);
+  float ne = xin ? __ldg(r0 + 1) : 0.f;
+  float sw = yin ? __ldg(r0 + We) : 0.f;
+  float se = (xin && yin) ? __ldg(r0 + We + 1) : 0.f;
+  float ex = 1.f - t.wx, ey = 1.f - t.wy;
+  return nw * (ex * ey) + ne * (t.wx * ey) + sw * (ex * t.wy) + se * (t.wx * t.wy);
+}
+
+// REF layout: out[b][c][i][j][n].  One thread per (i,j,n), n fastest -> coalesced stores.
+__global__ void e2p_ref_kernel(const float* __restrict__ erp, const float2* __restrict__ grid,
+                               float* __restrict__ out, int B, int C, int He, int We, int N,
+                               int Ph, int Pw) {
+  int total = N * Ph * Pw;
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= total) return;
+  int n = s % N;
+  int ij = s / N;
+  float2 g = __ldg(&grid[(size_t)n * Ph * Pw + ij]);
+  E2PTaps t = e2p_taps(g.x, g.y, He, We);
+  size_t plane = (size_t)He * We;
+  for (int bc = 0; bc < B * C; ++bc)
+    out[(size_t)bc * total + s] = e2p_sample(erp + bc * plane, t, He, We);
+}
+
+// FOLDED layout: out[b*N+n][i][j][Cpad].  One thread per (n,i,j).
+template <int C>
+__global__ void e2p_folded_kernel(const float* __restrict__ erp, const float2* __restrict__ grid,
+                                  float* __restrict__ out, int B, int He, int We, int N, int Ph,
+                                  int Pw) {
+  int total = N * Ph * Pw;
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= total) return;
+  float2 g = __ldg(&grid[s]);
+  E2PTaps t = e2p_taps(g.x, g.y, He, We);
+  size_t plane = (size_t)He * We;
+  for (int b = 0; b < B; ++b) {
+    const float* img = erp + (size_t)b * C * plane;
+    if (C == 3) {
+      float4 v;
+      v.x = e2p_sample(img, t, He, We);
+      v.y = e2p_sample(img + plane, t, He, We);
+      v.z = e2p_sample(img + 2 * plane, t, He, We);
+      v.w = 0.f;
+      st4(out + ((size_t)b * total + s) * 4, v);
+    } else {
+      for (int c = 0; c < C; ++c)
+        out[((size_t)b * total + s) * C + c] = e2p_sample(img + c * plane, t, He, We);
+    }
+  }
+}
+
+__global__ void e2p_taps_kernel(const float2* __restrict__ grid, int total, int He, int We,
+                                int32_t* __restrict__ x0, int32_t* __restrict__ y0) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= total) return;
+  float2 g = grid[s];
+  E2PTaps t = e2p_taps(g.x, g.y, He, We);
+  x0[s] = t.x0;
+  y0[s] = t.y0;
+}
+
+// ------------------------------------------------------------------ pers2equi
+struct P2EStrides {
+  long long sb, sc, sy, sx, sn;
+};
+
+__device__ __forceinline__ void p2e_decode(uint32_t id, int& n, int& y0, int& x0, int& dy, int& dx) {
+  n = id >> 24;
+  y0 = (id >> 16) & 255;
+  x0 = (id >> 8) & 255;
+  dy = (id >> 1) & 1;
+  dx = id & 1;
+}
+
+// One thread per ERP pixel, PL (b,c) planes per thread in registers so a table row is
+// read once per PL planes.  Tap/weight order follows pers2equi_v3.py:174-177,194-196.
+template <int PL>
+__global__ void p2e_kernel(const float* __restrict__ pers, const int32_t* __restrict__ rowptr,
+                           const uint32_t* __restrict__ idx, const float4* __restrict__ w,
+                           float* __restrict__ out, int npix, int B, int C, P2EStrides st) {
+  int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  int plane0 = blockIdx.y * PL;
+  int planes = B * C;
+  const float* base[PL];
+#pragma unroll
+  for (int k = 0; k < PL; ++k) {
+    int q = min(plane0 + k, planes - 1);
+    base[k] = pers + (q / C) * st.sb + (q % C) * st.sc;
+  }
+  float acc[PL];
+#pragma unroll
+  for (int k = 0; k < PL; ++k) acc[k] = 0.f;
+  int beg = __ldg(&rowptr[pix]), end = __ldg(&rowptr[pix + 1]);
+  for (int e = beg; e < end; ++e) {
+    int n, y0, x0, dy, dx;
+    p2e_decode(__ldg(&idx[e]), n, y0, x0, dy, dx);
+    float4 ww = __ldg(&w[e]);
+    long long o00 = y0 * st.sy + x0 * st.sx + n * st.sn;
+    long long oy = dy * st.sy, ox = dx * st.sx;
+#pragma unroll
+    for (int k = 0; k < PL; ++k) {
+      const float* p = base[k] + o00;
+      float a = __ldg(p), b = __ldg(p + oy), c = __ldg(p + ox), d = __ldg(p + oy + ox);
+      acc[k] += a * ww.x + b * ww.y + c * ww.z + d * ww.w;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < PL; ++k)
+    if (plane0 + k < planes) out[(size_t)(plane0 + k) * npix + pix] = acc[k];
+}
+
+// Fused confidence merge (spherical_model_iterative.py:372-378): blends pred*w and w
+// with the same table walk and divides.
+template <int PL>
+__global__ void blend_conf_kernel(const float* __restrict__ pred, const float* __restrict__ conf,
+                                  const int32_t* __restrict__ rowptr,
+                                  const uint32_t* __restrict__ idx, const float4* __restrict__ w,
+                                  float* __restrict__ out, int npix, int B, int N, int Ph, int Pw) {
+  int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  int b0 = blockIdx.y * PL;
+  float accD[PL], accW[PL];
+#pragma unroll
+  for (int k = 0; k < PL; ++k) accD[k] = accW[k] = 0.f;
+  size_t img = (size_t)Ph * Pw;
+  int beg = __ldg(&rowptr[pix]), end = __ldg(&rowptr[pix + 1]);
+  for (int e = beg; e < end; ++e) {
+    int n, y0, x0, dy, dx;
+    p2e_decode(__ldg(&idx[e]), n, y0, x0, dy, dx);
+    float4 ww = __ldg(&w[e]);
+    size_t o00 = (size_t)n * img + y0 * Pw + x0;
+    int oy = dy * Pw, ox = dx;
+#pragma unroll
+    for (int k = 0; k < PL; ++k) {
+      int b = min(b0 + k, B - 1);
+      const float* p = pred + (size_t)b * N * img + o00;
+      const float* q = conf + (size_t)b * N * img + o00;
+      accD[k] += __ldg(p) * ww.x + __ldg(p + oy) * ww.y + __ldg(p + ox) * ww.z + __ldg(p + oy + ox) * ww.w;
+      accW[k] += __ldg(q) * ww.x + __ldg(q + oy) * ww.y + __ldg(q + ox) * ww.z + __ldg(q + oy + ox) * ww.w;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < PL; ++k)
+    if (b0 + k < B) {
+      float W = accW[k];
+      float zero = (W <= 1e-8f) ? 1.f : 0.f;
+      out[(size_t)(b0 + k) * npix + pix] = accD[k] / (W + 1e-8f * zero);
+    }
+}
+
+// ------------------------------------------------------------------- abs-rel
+__global__ void absrel_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                              const uint8_t* __restrict__ mask, size_t n, float scale,
+                              double* __restrict__ out) {
+  double s = 0.0, c = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    if (mask[i]) {
+      float g = gt[i];
+      s += (double)(fabsf(pred[i] * scale - g) / g);
+      c += 1.0;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  __shared__ double ss[32], sc[32];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { ss[wid] = s; sc[wid] = c; }
+  __syncthreads();
+  if (wid == 0) {
+    int nw = blockDim.x >> 5;
+    s = lane < nw ? ss[lane] : 0.0;
+    c = lane < nw ? sc[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if (lane == 0) { atomicAdd(&out[0], s); atomicAdd(&out[1], c); }
+  }
+}
+
+}  // namespace ofb
+
+using namespace ofb;
+
+extern "C" int ofb_equi2pers_f32(const float* erp, int B, int C, int He, int We, const float* grid,
+                                 int N, int Ph, int Pw, float* out, int layout, void* stream) {
+  OFB_CHECK(erp && grid && out, "equi2pers: null pointer");
+  OFB_CHECK(B > 0 && C > 0 && He > 1 && We > 1 && N > 0 && Ph > 0 && Pw > 0, "equi2pers: bad shape");
+  cudaStream_t s = (cudaStream_t)stream;
+  int total = N * Ph * Pw;
+  int thr = 256, blocks = cdiv(total, thr);
+  const float2* g = reinterpret_cast<const float2*>(grid);
+  if (layout == OFB_LAYOUT_REF) {
+    e2p_ref_kernel<<<blocks, thr, 0, s>>>(erp, g, out, B, C, He, We, N, Ph, Pw);
+  } else if (layout == OFB_LAYOUT_FOLDED) {
+    if (C == 3) e2p_folded_kernel<3><<<blocks, thr, 0, s>>>(erp, g, out, B, He, We, N, Ph, Pw);
+    else if (C == 1) e2p_folded_kernel<1><<<blocks, thr, 0, s>>>(erp, g, out, B, He, We, N, Ph, Pw);
+    else OFB_CHECK(false, "equi2pers: folded layout supports C in {1,3}, got %d", C);
+  } else {
+    OFB_CHECK(false, "equi2pers: unknown layout %d", layout);
+  }
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ofb_equi2pers_taps(const float* grid, int N, int Ph, int Pw, int He, int We,
+                                  int32_t* x0, int32_t* y0, void* stream) {
+  OFB_CHECK(grid && x0 && y0, "equi2pers_taps: null pointer");
+  int total = N * Ph * Pw;
+  e2p_taps_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2*>(grid), total, He, We, x0, y0);
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ofb_pers2equi_f32(const float* pers, int B, int C, int N, int Ph, int Pw, int layout,
+                                 const int32_t* rowptr, const uint32_t* idx, const float* w, int He,
+                                 int We, float* out, void* stream) {
+  OFB_CHECK(pers && rowptr && idx && w && out, "pers2equi: null pointer");
+  OFB_CHECK(B > 0 && C > 0 && N > 0 && N <= 256 && Ph <= 256 && Pw <= 256, "pers2equi: bad shape");
+  P2EStrides st;
+  if (layout == OFB_LAYOUT_REF) {
+    st.sn = 1; st.sx = N; st.sy = (long long)Pw * N; st.sc = (long long)Ph * Pw * N; st.sb = st.sc * C;
+  } else if (layout == OFB_LAYOUT_FOLDED) {
+    st.sc = 1; st.sx = C; st.sy = (long long)Pw * C; st.sn = (long long)Ph * Pw * C; st.sb = st.sn * N;
+  } else {
+    OFB_CHECK(false, "pers2equi: unknown layout %d", layout);
+  }
+  int npix = He * We, planes = B * C;
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  cudaStream_t s = (cudaStream_t)stream;
+  int thr = 128;
+  if (planes >= 8) {
+    dim3 g(cdiv(npix, thr), cdiv(planes, 8));
+    p2e_kernel<8><<<g, thr, 0, s>>>(pers, rowptr, idx, w4, out, npix, B, C, st);
+  } else if (planes >= 3) {
+    dim3 g(cdiv(npix, thr), cdiv(planes, 4));
+    p2e_kernel<4><<<g, thr, 0, s>>>(pers, rowptr, idx, w4, out, npix, B, C, st);
+  } else {
+    dim3 g(cdiv(npix, thr), planes);
+    p2e_kernel<1><<<g, thr, 0, s>>>(pers, rowptr, idx, w4, out, npix, B, C, st);
+  }
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ofb_blend_conf_f32(const float* pred_w, const float* conf, int B, int N, int Ph, int Pw,
+                                  const int32_t* rowptr, const uint32_t* idx, const float* w, int He,
+                                  int We, float* out, void* stream) {
+  OFB_CHECK(pred_w && conf && rowptr && idx && w && out, "blend_conf: null pointer");
+  int npix = He * We;
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  cudaStream_t s = (cudaStream_t)stream;
+  int thr = 128;
+  if (B >= 4) {
+    dim3 g(cdiv(npix, thr), cdiv(B, 4));
+    blend_conf_kernel<4><<<g, thr, 0, s>>>(pred_w, conf, rowptr, idx, w4, out, npix, B, N, Ph, Pw);
+  } else {
+    dim3 g(cdiv(npix, thr), B);
+    blend_conf_kernel<1><<<g, thr, 0, s>>>(pred_w, conf, rowptr, idx, w4, out, npix, B, N, Ph, Pw);
+  }
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ofb_absrel_partial(const float* pred, const float* gt, const uint8_t* mask, size_t n,
+                                  float scale, double* out, void* stream) {
+  OFB_CHECK(pred && gt && mask && out, "absrel: null pointer");
+  int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  absrel_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pred, gt, mask, n, scale, out);
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
