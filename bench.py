@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""Benchmark of the OmniFusion tangent-patch inference path (BASELINE.json metric:
+panoramas/sec, 512x1024 ERP, nrows=4, 2-iteration, confidence-blended).
+
+    python bench.py --gpus N --steps K --warmup W          # ours (one process per GPU via torchrun for N>1)
+    python bench.py --impl reference ...                   # the reference's CPU path (oracle port), host cores
+
+A "step" is one forward of one batch (default 8 panoramas per GPU = BASELINE configs[1]).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+NUM_PATCHES = {3: 10, 4: 18, 5: 26, 6: 46}
+GFLOP_PER_PATCH_ITER = 3.952          # SURVEY.md section 8d (2*MAC, convs + linears)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="panoramas per GPU per step")
+    ap.add_argument("--erp", default="512x1024")
+    ap.add_argument("--nrows", type=int, default=4)
+    ap.add_argument("--iters", type=int, default=2)
+    ap.add_argument("--confidence", type=int, default=1)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 CUDA-core conv, 2 tcgen05 conv")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-steps", type=int, default=2)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm": d["hbm_gbs"], "tensor": d["bf16_tflops_sustained"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm": 6650.0, "tensor": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi SM clocks and throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 8:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            time.sleep(0.15)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[1]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[4 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][2]), "reasons": reasons,
+                "samples": len(self.rows), "power_w_max": max(float(r[3]) for r in self.rows)}
+
+
+def oracle_timing(args, he, we, steps):
+    """The reference's CPU path (oracle port: torch-CPU fp32, all host threads) on a bounded sample:
+    B=1 panoramas of the same workload; returns (panoramas/s, cores, description)."""
+    from omnifusion_b200.checkpoint import synthetic_state_dict
+    from oracle import model as om
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synthetic_state_dict("iterative", NUM_PATCHES[args.nrows], 0)
+    rgb = torch.rand(1, 3, he, we, generator=torch.Generator().manual_seed(123))
+    om.forward_iterative(sd, rgb, args.iters, bool(args.confidence), nrows=args.nrows)     # builds the tap table
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        om.forward_iterative(sd, rgb, args.iters, bool(args.confidence), nrows=args.nrows)
+    dt = time.perf_counter() - t0
+    return steps / dt, cores, (f"{steps} forwards of B=1 ({he}x{we} ERP, nrows={args.nrows}, {args.iters}-iter, "
+                               f"confidence={args.confidence}) after 1 warm-up that builds the tap table; "
+                               f"torch-CPU fp32 oracle port, {cores} threads")
+
+
+def config_dict(args, he, we, world):
+    n = NUM_PATCHES[args.nrows]
+    return {"workload": f"batch={args.batch}/GPU, {he}x{we} ERP, fov=80, nrows={args.nrows} ({n} patches of 128x128), "
+                        f"{args.iters}-iter iterative model, confidence={args.confidence} (BASELINE configs[1])",
+            "batch_per_gpu": args.batch, "global_batch": args.batch * world, "erp": [he, we], "nrows": args.nrows,
+            "patches": n, "iters": args.iters, "confidence": bool(args.confidence),
+            "parallelism": f"dp{world} (panorama shards, no data-path collective)",
+            "l2": "activation working set per step (~0.2 GB/panorama) exceeds the 126 MB L2; 4 rotating input batches"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    he, we = (int(v) for v in args.erp.split("x"))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    t0 = time.perf_counter()
+    value, cores, sample = oracle_timing(args, he, we, max(1, args.steps))
+    line = {"impl": "reference", "metric": "panoramas/sec", "value": value, "unit": "panoramas/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": config_dict(args, he, we, world),
+            "cpu_baseline": {"value": value, "unit": "panoramas/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "panoramas/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+def parse_profile(text):
+    rows = []
+    for ln in text.strip().split("\n"):
+        f = ln.split()
+        if len(f) == 5:
+            rows.append({"name": f[0], "launches": int(f[1]), "ms": float(f[2]), "flops": float(f[3]), "bytes": float(f[4])})
+    return rows
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import ctypes as C
+    from omnifusion_b200 import _lib, parallel
+    from omnifusion_b200.checkpoint import synthetic_state_dict
+    from omnifusion_b200.model.spherical_model_iterative import spherical_fusion
+
+    rank, world, local = parallel.init_from_env("nccl")
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    he, we = (int(v) for v in args.erp.split("x"))
+    n_patch = NUM_PATCHES[args.nrows]
+    B, K, W, iters, conf = args.batch, args.steps, max(args.warmup, 3), args.iters, bool(args.confidence)
+
+    net = spherical_fusion(args.nrows, n_patch, (128, 128), (80, 80))
+    net.load_state_dict(synthetic_state_dict("iterative", n_patch, 0))
+    net = net.to(dev).eval()
+    net.set_option("engine", args.engine)
+
+    R = 4
+    gens = [torch.Generator().manual_seed(123 + 17 * rank + i) for i in range(R)]
+    host_in = [torch.rand(B, 3, he, we, generator=g).pin_memory() for g in gens]
+    dev_in = [h.to(dev) for h in host_in]
+    fwd = (lambda x: net(x, iter=iters, confidence=conf)) if args.no_graph else \
+          (lambda x: net.forward_graphed(x, iters, conf))
+
+    with torch.no_grad():
+        # launches per forward (counted on an eager forward; the graph replays the same launches)
+        net(dev_in[0], iter=iters, confidence=conf)
+        torch.cuda.synchronize()
+        _lib.lib().ofb_launch_count(1)
+        net(dev_in[0], iter=iters, confidence=conf)
+        torch.cuda.synchronize()
+        launches_per_step = int(_lib.lib().ofb_launch_count(1))
+
+        for i in range(W):
+            fwd(dev_in[i % R])
+        torch.cuda.synchronize()
+
+        # ---- device-resident throughput -------------------------------------------------
+        sampler = ClockSampler(local)
+        sampler.start()
+        parallel.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            fwd(dev_in[i % R])
+        e1.record()
+        torch.cuda.synchronize()
+        parallel.barrier()
+        ms = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
+        clocks = sampler.summary()
+
+        # ---- end to end: pinned host input -> H2D -> forward -> D2H of the final depth --------
+        host_out = torch.empty(B, 1, he, we).pin_memory()
+        stage = torch.empty(B, 3, he, we, device=dev)
+
+        def e2e_step(i):
+            stage.copy_(host_in[i % R], non_blocking=True)
+            out = fwd(stage)
+            host_out.copy_(out[-1], non_blocking=True)
+
+        for i in range(2):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        parallel.barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(K):
+            e2e_step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1000.0
+        parallel.barrier()
+        e2e_ms = parallel.max_over_ranks(max(e0.elapsed_time(e1), wall), dev)
+
+        # ---- per-kernel timing (CUDA events on the launch stream, eager launches) ------------
+        prof_rows = []
+        if rank == 0:
+            _lib.check(_lib.lib().ofb_profile_enable(net._handle, 1))
+            for i in range(2):
+                net(dev_in[i % R], iter=iters, confidence=conf)
+            buf = C.create_string_buffer(1 << 16)
+            n = _lib.check(_lib.lib().ofb_profile_report(net._handle, buf, len(buf)))
+            _lib.check(_lib.lib().ofb_profile_enable(net._handle, 0))
+            prof_rows = parse_profile(buf.raw[:n].decode())
+
+    if rank != 0:
+        return
+    pk = peaks()
+    total_ms = sum(r["ms"] for r in prof_rows) or 1.0
+    # group kernel classes: all tensor-bound convs of one engine count as one kernel family
+    conv = [r for r in prof_rows if r["name"].startswith("conv")]
+    dom = max(prof_rows, key=lambda r: r["ms"]) if prof_rows else None
+    conv_ms = sum(r["ms"] for r in conv)
+    conv_fl = sum(r["flops"] for r in conv)
+    roofline = None
+    if conv and conv_ms > 0:
+        achieved = conv_fl / (conv_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "conv engine (all conv3x3/1x1 launches of the forward)",
+                    "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"],
+                    "traffic": None, "peak_source": pk["source"] + ", dense bf16 sustained",
+                    "share_of_step": conv_ms / total_ms,
+                    "top_launch": {"name": dom["name"], "ms": dom["ms"] / max(dom["launches"], 1),
+                                   "tflops": dom["flops"] / (dom["ms"] * 1e-3) / 1e12 if dom["ms"] > 0 else None}}
+    top = sorted(prof_rows, key=lambda r: -r["ms"])[:12]
+    value = world * B * K / (ms * 1e-3)
+    e2e_value = world * B * K / (e2e_ms * 1e-3)
+    line = {"metric": "panoramas/sec", "value": value, "unit": "panoramas/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32", "data": "synthetic", "config": config_dict(args, he, we, world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "panoramas/s", "ms_per_step": e2e_ms / K,
+                    "h2d_bytes_per_step": B * 3 * he * we * 4, "d2h_bytes_per_step": B * he * we * 4},
+            "gpu_launches": launches_per_step * K,
+            "launches_per_step": launches_per_step,
+            "executed_gflop_per_step": sum(r["flops"] for r in prof_rows) / 2 / 1e9,
+            "canonical_gflop_per_step": GFLOP_PER_PATCH_ITER * n_patch * iters * B,
+            "roofline": roofline,
+            "kernel_breakdown": [{"name": r["name"], "launches": r["launches"] // 2, "ms_per_step": r["ms"] / 2,
+                                  "tflops": (r["flops"] / (r["ms"] * 1e-3) / 1e12) if r["ms"] > 0 else 0,
+                                  "gbs": (r["bytes"] / (r["ms"] * 1e-3) / 1e9) if r["ms"] > 0 else 0} for r in top],
+            "graph": not args.no_graph}
+    if not args.skip_cpu_baseline and world == 1:
+        v, cores, sample = oracle_timing(args, he, we, args.cpu_sample_steps)
+        line["cpu_baseline"] = {"value": v, "unit": "panoramas/s", "cores": cores, "kind": "port", "sample": sample}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
