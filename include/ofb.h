@@ -83,36 +83,56 @@ int ofb_blend_conf_f32(const float* pred_w, const float* conf, int B, int N, int
 enum { OFB_ACT_NONE = 0, OFB_ACT_RELU = 1, OFB_ACT_GELU = 2 };
 enum { OFB_ENGINE_AUTO = 0, OFB_ENGINE_SIMT = 1, OFB_ENGINE_TC = 2 };
 
+/* Activation storage formats.  OFB_FMT_F32: plain float32.  OFB_FMT_SPLIT16: "split-half
+ * planes" - value = float(hi) + float(lo), stored as one buffer of 2*numel halves, the hi
+ * plane followed by the lo plane (same 4 bytes/element as float32, ~22 mantissa bits).  It
+ * is what lets the tcgen05 engine reach fp32-level accuracy with three kind::f16 MMAs
+ * (hi*hi + lo*hi + hi*lo) instead of one lossy TF32/BF16 MMA. */
+enum { OFB_FMT_F32 = 0, OFB_FMT_SPLIT16 = 1 };
+
 /* One 2-D convolution over folded NHWC, replacing a Conv3d((k,k,1)) + BatchNorm3d
  * (+ residual) (+ ReLU) group of model/spherical_model_iterative.py:322-369 or an
  * nn.Linear of model/blocks.py (n = rows, h = w = 1, k = 1).
  *   y = act(conv(cat(in0,in1)) * scale + shift + residual)
- * in0 (n,h,w,c0), in1 (n,h,w,c1) or NULL; wgt (cout, k, k, c0+c1) ("OHWI");
- * scale/shift (cout) or NULL (= 1 / 0); residual (n,oh,ow,cout) or NULL. */
+ * in0 (n,h,w,c0), in1 (n,h,w,c1) or NULL; wgt (cout, k, k, c0+c1) ("OHWI") float32;
+ * scale/shift (cout) or NULL (= 1 / 0); residual (n,oh,ow,cout) or NULL.
+ * in_fmt applies to in0/in1, out_fmt to out/residual.  The tcgen05 engine needs
+ * in_fmt == out_fmt; with OFB_FMT_SPLIT16 it reads the weights from wgt_split (split-half
+ * planes of wgt * 2^e made by ofb_split_f16, wgt_unscale = 2^-e); with OFB_FMT_F32 it runs
+ * one kind::tf32 MMA on wgt (TF32 accuracy only - not used by the engine's default path). */
 typedef struct {
-  const float* in0; const float* in1; int c0, c1;
+  const void* in0; const void* in1; int c0, c1;
   int n, h, w;
   const float* wgt; int k, stride, pad, cout;
-  const float* scale; const float* shift; const float* residual;
+  const float* scale; const float* shift; const void* residual;
   int act;
-  float* out;
+  void* out;
   int engine;
+  int in_fmt, out_fmt;
+  const void* wgt_split; float wgt_unscale;
 } ofb_conv_desc;
 int ofb_conv_f32(const ofb_conv_desc* d, void* stream);
+
+/* float32 -> split-half planes of (src * mul), and back.  dst/src planes: 2*n halves. */
+int ofb_split_f16(const float* src, size_t n, float mul, void* dst_planes, void* stream);
+int ofb_merge_f16(const void* src_planes, size_t n, float* dst, void* stream);
+
+/* The network kernels below take OFB_FMT_* selectors for their activation tensors (void*);
+ * weights, biases, tables and the head outputs are always float32. */
 
 /* Stem: Conv3d(3->64, 7x7 s2 p3) + BN + ReLU, spherical_model_iterative.py:322.
  * in (n,h,w,4) (4th channel ignored), wgt (64,7,7,4) OHWI-padded, out (n,h/2,w/2,64). */
 int ofb_stem_f32(const float* in, int n, int h, int w, const float* wgt,
-                 const float* scale, const float* shift, float* out, void* stream);
+                 const float* scale, const float* shift, void* out, int out_fmt, void* stream);
 
 /* F.max_pool3d((3,3,1), s(2,2,1), p(1,1,0)), spherical_model_iterative.py:323. */
-int ofb_maxpool3x3s2_f32(const float* in, int n, int h, int w, int c, float* out, void* stream);
+int ofb_maxpool3x3s2_f32(const void* in, int n, int h, int w, int c, void* out, int fmt, void* stream);
 
 /* F.interpolate(bilinear, align_corners=False) x2, spherical_model_iterative.py:338-367.
  * If img_bias (n,c) is given it is added to every source pixel first (the token
  * broadcast-add of :334-335). in (n,h,w,c) -> out (n,2h,2w,c). */
-int ofb_upsample2x_f32(const float* in, const float* img_bias, int n, int h, int w, int c,
-                       float* out, void* stream);
+int ofb_upsample2x_f32(const void* in, const float* img_bias, int n, int h, int w, int c,
+                       void* out, int fmt, void* stream);
 
 /* Point embedding: mlp_points1/2, spherical_model_iterative.py:290-305,319-320,387-393.
  * pts (N,cin,p,p) NCHW (the xyz table, or [cx,cy,1,cx,cy] for the single-stage model);
@@ -121,29 +141,29 @@ int ofb_upsample2x_f32(const float* in, const float* img_bias, int n, int h, int
 int ofb_point_embed_f32(const float* pts, int N, int cin, int p, const float* depth, int imgs,
                         const float* w1, const float* s1, const float* t1,
                         const float* w2, const float* s2, const float* t2,
-                        const float* base, float* out, void* stream);
+                        const void* base, void* out, int fmt, void* stream);
 
 /* Token packing: spherical_model_iterative.py:330-331 + pos_emb add (:244).
  * down (imgs,4,4,32) -> tokens (imgs,512) with index c*16+i*4+j, + pos_emb[n]. */
-int ofb_token_pack_f32(const float* down, const float* pos_emb, int imgs, int N,
-                       float* tokens, void* stream);
+int ofb_token_pack_f32(const void* down, const float* pos_emb, int imgs, int N,
+                       void* tokens, int fmt, void* stream);
 
 /* nn.LayerNorm over the last dim (model/blocks.py:76,81; encoder_norm eps 1e-6). */
-int ofb_layernorm_f32(const float* x, const float* gamma, const float* beta, int rows, int dim,
-                      float eps, float* y, void* stream);
+int ofb_layernorm_f32(const void* x, const float* gamma, const float* beta, int rows, int dim,
+                      float eps, void* y, int in_fmt, int out_fmt, void* stream);
 
 /* Attention core, model/blocks.py:50-62: q (rows,512), kv (rows,1024) [k | v],
  * rows = B*N, heads of 128; softmax(q k^T / sqrt(128)) v -> out (rows,512). */
-int ofb_attention_f32(const float* q, const float* kv, int B, int N, int heads, int head_dim,
-                      float* out, void* stream);
+int ofb_attention_f32(const void* q, const void* kv, int B, int N, int heads, int head_dim,
+                      void* out, int fmt, void* stream);
 
 /* Heads: pred / weight_pred 3x3 convs + relu / sigmoid / product,
  * spherical_model_iterative.py:371-374.  x (imgs,h,w,32); w_pred,w_conf (3,3,32);
  * pred_out = relu(pred) * (confidence ? sigmoid(conf) : 1); conf_out = sigmoid(conf)
  * (written only when confidence != 0). */
-int ofb_heads_f32(const float* x, int imgs, int h, int w,
+int ofb_heads_f32(const void* x, int imgs, int h, int w,
                   const float* w_pred, float b_pred, const float* w_conf, float b_conf,
-                  int confidence, float* pred_out, float* conf_out, void* stream);
+                  int confidence, float* pred_out, float* conf_out, int in_fmt, void* stream);
 
 /* Abs-Rel partial sums, metrics.py:7-9: out[0] += sum(|p*scale-g|/g over mask), out[1] += count.
  * `out` must be zeroed by the caller. */

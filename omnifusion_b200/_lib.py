@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libofb.so")
 LAYOUT_REF, LAYOUT_FOLDED = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
+FMT_F32, FMT_SPLIT16 = 0, 1
 
 
 class OfbError(RuntimeError):
@@ -25,7 +26,8 @@ class ConvDesc(C.Structure):
                 ("n", C.c_int), ("h", C.c_int), ("w", C.c_int),
                 ("wgt", C.c_void_p), ("k", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("cout", C.c_int),
                 ("scale", C.c_void_p), ("shift", C.c_void_p), ("residual", C.c_void_p),
-                ("act", C.c_int), ("out", C.c_void_p), ("engine", C.c_int)]
+                ("act", C.c_int), ("out", C.c_void_p), ("engine", C.c_int),
+                ("in_fmt", C.c_int), ("out_fmt", C.c_int), ("wgt_split", C.c_void_p), ("wgt_unscale", C.c_float)]
 
 
 class Geometry(C.Structure):
@@ -48,14 +50,16 @@ _SIGNATURES = {
     "ofb_pers2equi_f32": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P]),
     "ofb_blend_conf_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P]),
     "ofb_conv_f32": (_I, [C.POINTER(ConvDesc), _P]),
-    "ofb_stem_f32": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P]),
-    "ofb_maxpool3x3s2_f32": (_I, [_P, _I, _I, _I, _I, _P, _P]),
-    "ofb_upsample2x_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
-    "ofb_point_embed_f32": (_I, [_P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "ofb_token_pack_f32": (_I, [_P, _P, _I, _I, _P, _P]),
-    "ofb_layernorm_f32": (_I, [_P, _P, _P, _I, _I, C.c_float, _P, _P]),
-    "ofb_attention_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
-    "ofb_heads_f32": (_I, [_P, _I, _I, _I, _P, C.c_float, _P, C.c_float, _I, _P, _P, _P]),
+    "ofb_split_f16": (_I, [_P, C.c_size_t, C.c_float, _P, _P]),
+    "ofb_merge_f16": (_I, [_P, C.c_size_t, _P, _P]),
+    "ofb_stem_f32": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
+    "ofb_maxpool3x3s2_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _P]),
+    "ofb_upsample2x_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P]),
+    "ofb_point_embed_f32": (_I, [_P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "ofb_token_pack_f32": (_I, [_P, _P, _I, _I, _P, _I, _P]),
+    "ofb_layernorm_f32": (_I, [_P, _P, _P, _I, _I, C.c_float, _P, _I, _I, _P]),
+    "ofb_attention_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P]),
+    "ofb_heads_f32": (_I, [_P, _I, _I, _I, _P, C.c_float, _P, C.c_float, _I, _P, _P, _I, _P]),
     "ofb_absrel_partial": (_I, [_P, _P, _P, C.c_size_t, C.c_float, _P, _P]),
     "ofb_create": (_I, [_I, C.POINTER(_P)]),
     "ofb_destroy": (_I, [_P]),

@@ -12,19 +12,19 @@
 namespace ofb {
 
 struct ConvArgs {
-  const float* in0; const float* in1; int c0, c1;
+  const void* in0; const void* in1; int c0, c1;
   int n, h, w, oh, ow;
   const float* wgt; int k, stride, pad, cout;
-  const float* scale; const float* shift; const float* residual;
+  const float* scale; const float* shift; const void* residual;
   int act;
-  float* out;
+  void* out;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
 }
 
-template <int BM, int BN, int TM, int TN>
+template <int BM, int BN, int TM, int TN, bool IN_SPLIT, bool OUT_SPLIT>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 conv_simt_kernel(ConvArgs a) {
   constexpr int BK = 16;
@@ -69,17 +69,17 @@ conv_simt_kernel(ConvArgs a) {
     int cq = step - tap * cchunks;
     int kh = tap / a.k, kw = tap - kh * a.k;
     int c = cq * BK;
-    const float* src = a.in0;
+    const void* src = a.in0;
     int cs = a.c0, coff = c;
     if (c >= a.c0) { src = a.in1; cs = a.c1; coff = c - a.c0; }
+    const size_t in_plane = (size_t)a.n * a.h * a.w * cs;
 #pragma unroll
     for (int i = 0; i < A_LD; ++i) {
       int f = tid + i * THREADS;
       int q = f & 3;
       int ih = a_ih0[i] + kh, iw = a_iw0[i] + kw;
       bool ok = a_ok[i] && ih >= 0 && ih < a.h && iw >= 0 && iw < a.w;
-      ra[i] = ok ? __ldg(reinterpret_cast<const float4*>(
-                       src + ((size_t)(a_img[i] * a.h + ih) * a.w + iw) * cs + coff + q * 4))
+      ra[i] = ok ? act_ld4<IN_SPLIT>(src, ((size_t)(a_img[i] * a.h + ih) * a.w + iw) * cs + coff + q * 4, in_plane)
                  : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
@@ -153,6 +153,7 @@ conv_simt_kernel(ConvArgs a) {
   }
 
   // epilogue: y = act(acc*scale + shift + residual)
+  const size_t out_plane = (size_t)M * a.cout;
   float sc[TN], sh[TN];
 #pragma unroll
   for (int j = 0; j < TN; ++j) {
@@ -173,7 +174,7 @@ conv_simt_kernel(ConvArgs a) {
       v.z = acc[i][j + 2] * sc[j + 2] + sh[j + 2];
       v.w = acc[i][j + 3] * sc[j + 3] + sh[j + 3];
       if (a.residual) {
-        float4 r = __ldg(reinterpret_cast<const float4*>(a.residual + o + j));
+        float4 r = act_ld4<OUT_SPLIT>(a.residual, o + j, out_plane);
         v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
       }
       if (a.act == OFB_ACT_RELU) {
@@ -181,17 +182,20 @@ conv_simt_kernel(ConvArgs a) {
       } else if (a.act == OFB_ACT_GELU) {
         v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
       }
-      st4(a.out + o + j, v);
+      act_st4<OUT_SPLIT>(a.out, o + j, out_plane, v);
     }
   }
 }
 
 template <int BM, int BN, int TM, int TN>
-static int launch(const ConvArgs& a, cudaStream_t s) {
+static int launch(const ConvArgs& a, int in_fmt, int out_fmt, cudaStream_t s) {
   constexpr int THREADS = (BM / TM) * (BN / TN);
   int M = a.n * a.oh * a.ow;
   dim3 grid(cdiv(M, BM), a.cout / BN);
-  conv_simt_kernel<BM, BN, TM, TN><<<grid, THREADS, 0, s>>>(a);
+  if (in_fmt == OFB_FMT_F32 && out_fmt == OFB_FMT_F32) conv_simt_kernel<BM, BN, TM, TN, false, false><<<grid, THREADS, 0, s>>>(a);
+  else if (in_fmt == OFB_FMT_SPLIT16 && out_fmt == OFB_FMT_SPLIT16) conv_simt_kernel<BM, BN, TM, TN, true, true><<<grid, THREADS, 0, s>>>(a);
+  else if (in_fmt == OFB_FMT_SPLIT16) conv_simt_kernel<BM, BN, TM, TN, true, false><<<grid, THREADS, 0, s>>>(a);
+  else conv_simt_kernel<BM, BN, TM, TN, false, true><<<grid, THREADS, 0, s>>>(a);
   OFB_LAUNCH_CHECK();
   return 0;
 }
@@ -208,11 +212,13 @@ int conv_simt(const ofb_conv_desc* d, cudaStream_t s) {
   OFB_CHECK(a.c0 % 16 == 0 && a.c1 % 16 == 0, "conv_simt: channel counts must be multiples of 16 (got %d,%d)", a.c0, a.c1);
   OFB_CHECK(a.cout % 32 == 0, "conv_simt: cout must be a multiple of 32 (got %d)", a.cout);
   long long M = (long long)a.n * a.oh * a.ow;
-  if (a.cout % 64 != 0) return launch<128, 32, 4, 4>(a, s);
+  OFB_CHECK(d->wgt, "conv_simt: float32 weights are required");
+  const int fi = d->in_fmt, fo = d->out_fmt;
+  if (a.cout % 64 != 0) return launch<128, 32, 4, 4>(a, fi, fo, s);
   // enough 128x64 tiles to fill the 148 SMs at least ~2x, else use 64x64 tiles
   long long tiles128 = ((M + 127) / 128) * (a.cout / 64);
-  if (tiles128 >= 296) return launch<128, 64, 8, 4>(a, s);
-  return launch<64, 64, 4, 4>(a, s);
+  if (tiles128 >= 296) return launch<128, 64, 8, 4>(a, fi, fo, s);
+  return launch<64, 64, 4, 4>(a, fi, fo, s);
 }
 
 }  // namespace ofb

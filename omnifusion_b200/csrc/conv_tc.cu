@@ -1,14 +1,493 @@
-// tcgen05 / TMEM / TMA implicit-GEMM convolution engine (sm_100a).
+// tcgen05 / TMEM / TMA implicit-GEMM convolution engine (sm_100a), stride 1, k in {1,3}.
+//
+// GEMM view: M = output pixels (CTA tile = 128 pixels = a TMA box of BNI images x BH rows x BW
+// columns), N = cout (CTA tile BN <= 128), K = taps x channels.  For every filter tap the
+// producer issues one 4-D TMA load of the *shifted* activation box (out-of-bounds rows/columns
+// are zero-filled by TMA = the conv padding) and one 2-D load of the matching K-slice of the
+// OHWI weights; both land in shared memory in the K-major 128B/64B-swizzled layout that
+// tcgen05.mma consumes directly.  One elected thread issues the MMAs, accumulating in TMEM;
+// four epilogue warps read TMEM back (tcgen05.ld), apply scale/shift/residual/activation and
+// store.  Pipeline: NST-stage smem ring with full/empty mbarriers; MMA completion is
+// signalled with tcgen05.commit.
+//
+// Two operand modes:
+//   TF32   : float32 tensors, one kind::tf32 MMA per K-step (TF32 accuracy).
+//   F16X3  : split-half planes (value = hi + lo, both fp16), three kind::f16 MMAs per K-step
+//            (hi*hi + lo*hi + hi*lo) accumulated in fp32 - ~22-bit operands, fp32-level result.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace ofb {
 
-bool conv_tc_supported(const ofb_conv_desc* d) { (void)d; return false; }
+enum { MODE_TF32 = 0, MODE_F16X3 = 1 };
+
+struct TcParams {
+  int n_img, H, W, c0, c1, cout, k, pad;
+  int BW, BH, BNI, tiles_x, tiles_y;
+  const float* scale; const float* shift; float wscale;
+  const void* residual; void* out;
+  int act;
+  long long plane;   // elements per plane of out / residual (split format)
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  int spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1 << 24)) __trap();   // a broken pipeline must fault, not hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <int MODE>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if (MODE == MODE_TF32) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
+      "%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
+// LBO (unused for swizzled K-major) = 1, SBO = bytes between 8-row groups >> 4, version = 1
+// (Blackwell), layout type 2 = SWIZZLE_128B / 4 = SWIZZLE_64B.
+template <int ROW_BYTES>
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8 * ROW_BYTES) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61;
+  return d;
+}
+
+__device__ __forceinline__ float act_fn(float v, int act) {
+  if (act == OFB_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == OFB_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+  return v;
+}
+
+template <int BN, int MODE, int ROW_BYTES>
+struct TcCfg {
+  static constexpr int PLANES = MODE == MODE_F16X3 ? 2 : 1;
+  static constexpr int A_BYTES = 128 * ROW_BYTES;
+  static constexpr int B_BYTES = BN * ROW_BYTES;
+  static constexpr int STAGE = (A_BYTES + B_BYTES) * PLANES;
+  static constexpr int NST_RAW = (196 * 1024) / STAGE;
+  static constexpr int NST = NST_RAW > 8 ? 8 : NST_RAW;
+  static constexpr int KC = ROW_BYTES / (MODE == MODE_F16X3 ? 2 : 4);   // channels per K-step
+  static constexpr int MMA_PER_TILE = ROW_BYTES / 32;                  // UMMA_K spans 32 bytes
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int SMEM = NST * STAGE + 1024 /*align*/ + 256 /*barriers*/ + BN * 8;
+};
+
+// tensor maps: a[src][plane] activations, b[plane] weights
+struct TcMaps {
+  CUtensorMap a[2][2];
+  CUtensorMap b[2];
+};
+
+template <int BN, int MODE, int ROW_BYTES>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+  using Cfg = TcCfg<BN, MODE, ROW_BYTES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t bars = base + Cfg::NST * Cfg::STAGE;       // full[NST], empty[NST], tmem_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + Cfg::NST * Cfg::STAGE + 8 * (2 * Cfg::NST + 1));
+  float* s_scale = reinterpret_cast<float*>(base_ptr + Cfg::NST * Cfg::STAGE + 256);
+  float* s_shift = s_scale + BN;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cin = p.c0 + p.c1;
+  const int cchunks = cin / Cfg::KC;
+  const int ksteps = p.k * p.k * cchunks;
+
+  // tile coordinates
+  const int tiles_per_group = p.tiles_x * p.tiles_y;
+  const int grp = blockIdx.x / tiles_per_group;
+  const int trem = blockIdx.x - grp * tiles_per_group;
+  const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
+  const int img0 = grp * p.BNI, y0 = ty * p.BH, x0 = tx * p.BW;
+  const int n0 = blockIdx.y * BN;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < Cfg::NST; ++i) {
+      mbar_init(bars + 8 * i, 1);
+      mbar_init(bars + 8 * (Cfg::NST + i), 1);
+    }
+    mbar_init(bars + 8 * (2 * Cfg::NST), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&maps.a[0][0]);
+    tma_prefetch_desc(&maps.b[0]);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < BN; i += 128) {
+      s_scale[i] = (p.scale ? __ldg(&p.scale[n0 + i]) : 1.f) * p.wscale;
+      s_shift[i] = p.shift ? __ldg(&p.shift[n0 + i]) : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int st = ks % Cfg::NST;
+        const uint32_t ph = (ks / Cfg::NST) & 1;
+        mbar_wait(bars + 8 * (Cfg::NST + st), ph ^ 1);
+        const int tap = ks / cchunks, cq = ks - tap * cchunks;
+        const int kh = tap / p.k, kw = tap - kh * p.k;
+        int c = cq * Cfg::KC;
+        int src = 0;
+        if (c >= p.c0) { src = 1; c -= p.c0; }
+        const uint32_t full = bars + 8 * st;
+        mbar_expect_tx(full, Cfg::STAGE);
+        const uint32_t sa = base + st * Cfg::STAGE;
+        const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
+#pragma unroll
+        for (int pl = 0; pl < Cfg::PLANES; ++pl) {
+          tma_load_4d(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, x0 + kw - p.pad, y0 + kh - p.pad, img0);
+          tma_load_2d(sb + pl * Cfg::B_BYTES, &maps.b[pl], full, tap * cin + cq * Cfg::KC, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (bit 4), a/b format
+      // (bits 7/10: 0 = F16, 2 = TF32), K-major A and B, N >> 3 at bit 17, M >> 4 at bit 24.
+      const uint32_t fmt = MODE == MODE_TF32 ? 2u : 0u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int st = ks % Cfg::NST;
+        const uint32_t ph = (ks / Cfg::NST) & 1;
+        mbar_wait(bars + 8 * st, ph);
+        tc_fence_after();
+        const uint32_t sa = base + st * Cfg::STAGE;
+        const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
+        const uint64_t a_hi = umma_desc<ROW_BYTES>(sa), b_hi = umma_desc<ROW_BYTES>(sb);
+        if (MODE == MODE_TF32) {
+#pragma unroll
+          for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk)
+            tc_mma<MODE>(tmem, a_hi + 2 * kk, b_hi + 2 * kk, idesc, (ks | kk) != 0);
+        } else {
+          const uint64_t a_lo = umma_desc<ROW_BYTES>(sa + Cfg::A_BYTES), b_lo = umma_desc<ROW_BYTES>(sb + Cfg::B_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk) {
+            tc_mma<MODE>(tmem, a_hi + 2 * kk, b_hi + 2 * kk, idesc, (ks | kk) != 0);
+            tc_mma<MODE>(tmem, a_lo + 2 * kk, b_hi + 2 * kk, idesc, 1);
+            tc_mma<MODE>(tmem, a_hi + 2 * kk, b_lo + 2 * kk, idesc, 1);
+          }
+        }
+        tc_commit(bars + 8 * (Cfg::NST + st));       // frees this smem stage when the MMAs retire
+      }
+      tc_commit(bars + 8 * (2 * Cfg::NST));          // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 <-> TMEM lane quarters) =====================
+    mbar_wait(bars + 8 * (2 * Cfg::NST), 0);
+    tc_fence_after();
+    const int q = warp & 3;                    // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int r = q * 32 + lane;               // accumulator row = pixel within the tile
+    const int xx = r % p.BW, yy = (r / p.BW) % p.BH, ni = r / (p.BW * p.BH);
+    const int img = img0 + ni;
+    const bool ok = img < p.n_img;
+    const size_t pix = ((size_t)(ok ? img : 0) * p.H + (y0 + yy)) * p.W + (x0 + xx);
+    const size_t off = pix * p.cout + n0;
+#pragma unroll 1
+    for (int cb = 0; cb < BN; cb += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + cb, v);
+      if (!ok) continue;
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * s_scale[cb + j] + s_shift[cb + j];
+      if (MODE == MODE_TF32) {
+        float* o = reinterpret_cast<float*>(p.out) + off + cb;
+        if (p.residual) {
+          const float* rs = reinterpret_cast<const float*>(p.residual) + off + cb;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 t = __ldg(reinterpret_cast<const float4*>(rs + j));
+            f[j] += t.x; f[j + 1] += t.y; f[j + 2] += t.z; f[j + 3] += t.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          st4(o + j, make_float4(act_fn(f[j], p.act), act_fn(f[j + 1], p.act), act_fn(f[j + 2], p.act),
+                                 act_fn(f[j + 3], p.act)));
+      } else {
+        __half* ohi = reinterpret_cast<__half*>(p.out) + off + cb;
+        __half* olo = ohi + p.plane;
+        if (p.residual) {
+          const __half* rhi = reinterpret_cast<const __half*>(p.residual) + off + cb;
+          const __half* rlo = rhi + p.plane;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 a = __ldg(reinterpret_cast<const uint4*>(rhi + j));
+            uint4 b = __ldg(reinterpret_cast<const uint4*>(rlo + j));
+            const __half2* ah = reinterpret_cast<const __half2*>(&a);
+            const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              float2 x = __half22float2(ah[t]), y = __half22float2(bh[t]);
+              f[j + 2 * t] += x.x + y.x;
+              f[j + 2 * t + 1] += x.y + y.y;
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 hi4, lo4;
+          __half2* hh = reinterpret_cast<__half2*>(&hi4);
+          __half2* ll = reinterpret_cast<__half2*>(&lo4);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            float a0 = act_fn(f[j + 2 * t], p.act), a1 = act_fn(f[j + 2 * t + 1], p.act);
+            __half2 h = __floats2half2_rn(a0, a1);
+            float2 hf = __half22float2(h);
+            hh[t] = h;
+            ll[t] = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+          }
+          *reinterpret_cast<uint4*>(ohi + j) = hi4;
+          *reinterpret_cast<uint4*>(olo + j) = lo4;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* m, bool half, int rank, void* addr, const cuuint64_t* dims, const cuuint32_t* box,
+                    int row_bytes) {
+  EncodeTiledFn fn = encode_fn();
+  OFB_CHECK(fn, "conv_tc: cuTensorMapEncodeTiled is not available from the driver");
+  const int es = half ? 2 : 4;
+  cuuint64_t strides[4];
+  cuuint64_t acc = es;
+  for (int i = 0; i < rank - 1; ++i) { acc *= dims[i]; strides[i] = acc; }
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, addr, dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  OFB_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+bool conv_tc_supported(const ofb_conv_desc* d) {
+  if (d->in_fmt != d->out_fmt) return false;
+  if (d->stride != 1) return false;
+  if (!((d->k == 3 && d->pad == 1) || (d->k == 1 && d->pad == 0))) return false;
+  if (d->in_fmt == OFB_FMT_SPLIT16 && !d->wgt_split) return false;
+  int c1 = d->in1 ? d->c1 : 0;
+  if (d->c0 % 32 || c1 % 32 || d->cout % 32) return false;
+  if (d->cout > 128 && d->cout % 128) return false;
+  if (!pow2(d->w) || !pow2(d->h) || d->w > 128) return false;
+  int bw = d->w, bh = d->h < 128 / bw ? d->h : 128 / bw;
+  if (d->h % bh) return false;
+  return true;
+}
+
+template <int BN, int MODE, int ROW_BYTES>
+static int launch_tc(const TcMaps& maps, const TcParams& p, dim3 grid, cudaStream_t s) {
+  using Cfg = TcCfg<BN, MODE, ROW_BYTES>;
+  static bool attr = false;
+  if (!attr) {
+    OFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MODE, ROW_BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr = true;
+  }
+  conv_tc_kernel<BN, MODE, ROW_BYTES><<<grid, 192, Cfg::SMEM, s>>>(maps, p);
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int MODE, int ROW_BYTES>
+static int launch_bn(int bn, const TcMaps& maps, const TcParams& p, dim3 grid, cudaStream_t s) {
+  if (bn == 128) return launch_tc<128, MODE, ROW_BYTES>(maps, p, grid, s);
+  if (bn == 64) return launch_tc<64, MODE, ROW_BYTES>(maps, p, grid, s);
+  return launch_tc<32, MODE, ROW_BYTES>(maps, p, grid, s);
+}
 
 int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
-  (void)d; (void)s;
-  set_error("conv_tc: not built");
-  return -1;
+  OFB_CHECK(conv_tc_supported(d), "conv_tc: unsupported shape");
+  const bool split = d->in_fmt == OFB_FMT_SPLIT16;
+  const int c1 = d->in1 ? d->c1 : 0, cin = d->c0 + c1;
+  const int es = split ? 2 : 4;
+  // channels per K-step: a 128-byte row when every source allows it, else a 64-byte row
+  int row_bytes = 128;
+  if ((d->c0 * es) % 128 || (c1 * es) % 128) row_bytes = 64;
+  const int kc = row_bytes / es;
+  OFB_CHECK(d->c0 % kc == 0 && c1 % kc == 0, "conv_tc: channel counts (%d,%d) not divisible by %d", d->c0, c1, kc);
+  TcParams p{};
+  p.n_img = d->n; p.H = d->h; p.W = d->w; p.c0 = d->c0; p.c1 = c1; p.cout = d->cout; p.k = d->k; p.pad = d->pad;
+  p.BW = d->w; p.BH = d->h < 128 / p.BW ? d->h : 128 / p.BW; p.BNI = 128 / (p.BW * p.BH);
+  p.tiles_x = d->w / p.BW; p.tiles_y = d->h / p.BH;
+  p.scale = d->scale; p.shift = d->shift; p.wscale = split ? d->wgt_unscale : 1.f;
+  p.residual = d->residual; p.out = d->out; p.act = d->act;
+  p.plane = (long long)d->n * d->h * d->w * d->cout;
+  const int bn = d->cout >= 128 ? 128 : d->cout;
+  const int groups = (d->n + p.BNI - 1) / p.BNI;
+  dim3 grid(groups * p.tiles_x * p.tiles_y, d->cout / bn);
+
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const int planes = split ? 2 : 1;
+  for (int src = 0; src < 2; ++src) {
+    const void* ptr = src == 0 ? d->in0 : d->in1;
+    int c = src == 0 ? d->c0 : c1;
+    if (!ptr || c == 0) { ptr = d->in0; c = d->c0; }      // unused map: keep it valid
+    cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
+    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BNI};
+    for (int pl = 0; pl < planes; ++pl) {
+      char* a = (char*)ptr + (size_t)pl * d->n * d->h * d->w * c * es;
+      if (make_map(&maps.a[src][pl], split, 4, a, dims, box, row_bytes)) return -1;
+    }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d->k * d->k * cin, (cuuint64_t)d->cout};
+    cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)bn};
+    for (int pl = 0; pl < planes; ++pl) {
+      char* a = split ? (char*)d->wgt_split + (size_t)pl * d->cout * d->k * d->k * cin * 2 : (char*)d->wgt;
+      if (make_map(&maps.b[pl], split, 2, a, dims, box, row_bytes)) return -1;
+    }
+  }
+  if (split) {
+    if (row_bytes == 128) return launch_bn<MODE_F16X3, 128>(bn, maps, p, grid, s);
+    return launch_bn<MODE_F16X3, 64>(bn, maps, p, grid, s);
+  }
+  if (row_bytes == 128) return launch_bn<MODE_TF32, 128>(bn, maps, p, grid, s);
+  return launch_bn<MODE_TF32, 64>(bn, maps, p, grid, s);
+}
+
+// ------------------------------------------------------------ split-half conversion
+__global__ void split_kernel(const float* __restrict__ src, size_t n, float mul, __half* __restrict__ hi,
+                             __half* __restrict__ lo) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = src[i] * mul;
+  __half h = __float2half_rn(v);
+  hi[i] = h;
+  lo[i] = __float2half_rn(v - __half2float(h));
+}
+__global__ void merge_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, size_t n,
+                             float* __restrict__ dst) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dst[i] = __half2float(hi[i]) + __half2float(lo[i]);
 }
 
 }  // namespace ofb
+
+using namespace ofb;
+
+extern "C" int ofb_split_f16(const float* src, size_t n, float mul, void* dst_planes, void* stream) {
+  OFB_CHECK(src && dst_planes && n > 0, "split_f16: bad arguments");
+  __half* hi = reinterpret_cast<__half*>(dst_planes);
+  split_kernel<<<cdiv((long long)n, 256), 256, 0, (cudaStream_t)stream>>>(src, n, mul, hi, hi + n);
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ofb_merge_f16(const void* src_planes, size_t n, float* dst, void* stream) {
+  OFB_CHECK(src_planes && dst && n > 0, "merge_f16: bad arguments");
+  const __half* hi = reinterpret_cast<const __half*>(src_planes);
+  merge_kernel<<<cdiv((long long)n, 256), 256, 0, (cudaStream_t)stream>>>(hi, hi + n, n, dst);
+  OFB_LAUNCH_CHECK();
+  return 0;
+}

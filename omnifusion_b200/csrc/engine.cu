@@ -32,18 +32,21 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s);
 bool conv_tc_supported(const ofb_conv_desc* d);
 
 int conv_dispatch(const ofb_conv_desc* d, cudaStream_t s) {
-  OFB_CHECK(d && d->in0 && d->wgt && d->out, "conv: null pointer");
+  OFB_CHECK(d && d->in0 && (d->wgt || d->wgt_split) && d->out, "conv: null pointer");
   OFB_CHECK(d->n > 0 && d->h > 0 && d->w > 0 && d->k > 0 && d->stride > 0, "conv: bad shape");
   if (d->engine == OFB_ENGINE_TC) {
     OFB_CHECK(conv_tc_supported(d), "conv: shape not supported by the tcgen05 engine");
     return conv_tc(d, s);
   }
-  if (d->engine == OFB_ENGINE_AUTO && conv_tc_supported(d)) return conv_tc(d, s);
+  // AUTO only picks the tensor-core engine where it is fp32-accurate (split-half operands);
+  // its single-pass TF32 mode on float32 tensors must be requested explicitly
+  if (d->engine == OFB_ENGINE_AUTO && d->in_fmt == OFB_FMT_SPLIT16 && conv_tc_supported(d)) return conv_tc(d, s);
   return conv_simt(d, s);
 }
 
 struct ConvW {
   float* w = nullptr; float* scale = nullptr; float* shift = nullptr;
+  void* ws = nullptr; float unscale = 1.f;     // split-half planes of w * 2^e, and 2^-e
   int cout = 0, cin = 0, k = 0;
 };
 struct Mlp { float *w1, *s1, *t1, *w2, *s2, *t2; int cin; };
@@ -51,7 +54,7 @@ struct Block {
   float *n1g, *n1b, *n2g, *n2b;
   ConvW q, kv, proj, fc1, fc2;
 };
-struct Act { float* p = nullptr; int n = 0, h = 0, w = 0, c = 0; };
+struct Act { float* p = nullptr; int n = 0, h = 0, w = 0, c = 0, fmt = 0; };
 
 }  // namespace ofb
 
@@ -73,6 +76,7 @@ struct ofb_handle {
   // workspace
   float* ws = nullptr; size_t ws_floats = 0; size_t ws_used = 0;
   int engine = OFB_ENGINE_AUTO, chunk = 0, dedup = 1;
+  int fmt = OFB_FMT_SPLIT16;       // activation storage inside the network
   std::map<std::string, Act> acts;
   // optional per-launch timing (ofb_profile_enable)
   bool profile = false;
@@ -121,7 +125,18 @@ static int pack_conv(ofb_handle* h, const TMap& m, const std::string& wname, Con
         for (int x = 0; x < kw; ++x)
           p[(((size_t)o * kh + y) * kw + x) * Ip + i] = t->data[(((size_t)o * I + i) * kh + y) * kw + x];
   cw->cout = O; cw->cin = Ip; cw->k = kh;
-  return dev_upload(h, p, &cw->w);
+  if (dev_upload(h, p, &cw->w)) return -1;
+  // split-half planes for the tcgen05 engine: scale by a power of two so max|w| lands in
+  // [2^13, 2^14) and both the hi and the lo plane stay in fp16's normal range
+  float mx = 0.f;
+  for (float v : p) mx = fmaxf(mx, fabsf(v));
+  int e = mx > 0.f ? 13 - (int)floorf(log2f(mx)) : 0;
+  cw->unscale = ldexpf(1.f, -e);
+  OFB_CUDA(cudaMalloc(&cw->ws, p.size() * 4));
+  h->owned.push_back(cw->ws);
+  if (ofb_split_f16(cw->w, p.size(), ldexpf(1.f, e), cw->ws, nullptr)) return -1;
+  OFB_CUDA(cudaStreamSynchronize(nullptr));
+  return 0;
 }
 
 static int pack_vec(ofb_handle* h, const TMap& m, const std::string& name, float** out, int expect = -1) {
@@ -327,6 +342,7 @@ static int run_conv(Ctx& c, const ConvW& w, const float* in0, int c0, const floa
   d.wgt = w.w; d.k = w.k; d.stride = stride; d.pad = pad; d.cout = w.cout;
   d.scale = w.scale; d.shift = w.shift; d.residual = residual; d.act = act; d.out = out;
   d.engine = c.h->engine;
+  d.in_fmt = d.out_fmt = c.h->fmt; d.wgt_split = w.ws; d.wgt_unscale = w.unscale;
   OFB_CHECK(w.w && w.cin == c0 + c1, "forward: conv weight/channel mismatch (%d vs %d+%d)", w.cin, c0, c1);
   double fl, by;
   conv_work(d, &fl, &by);
@@ -340,6 +356,7 @@ static int run_linear(Ctx& c, const ConvW& w, const float* in, const float* resi
   d.wgt = w.w; d.k = 1; d.stride = 1; d.pad = 0; d.cout = w.cout;
   d.scale = nullptr; d.shift = w.shift; d.residual = residual; d.act = act; d.out = out;
   d.engine = c.h->engine;
+  d.in_fmt = d.out_fmt = c.h->fmt; d.wgt_split = w.ws; d.wgt_unscale = w.unscale;
   double fl, by;
   conv_work(d, &fl, &by);
   char nm[64];
@@ -373,8 +390,8 @@ static int run_res_layer(Ctx& c, int l, const float* in, int cin, int hin, float
   return 0;
 }
 
-static void reg(ofb_handle* h, const char* name, float* p, int n, int hh, int ww, int cc) {
-  Act a; a.p = p; a.n = n; a.h = hh; a.w = ww; a.c = cc;
+static void reg(ofb_handle* h, const char* name, float* p, int n, int hh, int ww, int cc, int fmt = -1) {
+  Act a; a.p = p; a.n = n; a.h = hh; a.w = ww; a.c = cc; a.fmt = fmt < 0 ? h->fmt : fmt;
   h->acts[name] = a;
 }
 
@@ -387,6 +404,7 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
   if (ensure_workspace(h, imgs, P, &b)) return -1;
   Ctx c{h, s, imgs};
   void* vs = (void*)s;
+  const int F = h->fmt;
 
   for (int it = 0; it < iters; ++it) {
     bool reuse = it > 0 && h->dedup;
@@ -396,9 +414,9 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
       if (ofb_equi2pers_f32(rgb, Bc, 3, He, We, g.grid_hi, N, P, P, b.patches, OFB_LAYOUT_FOLDED, vs)) return -1; }
       const ConvW& st = h->conv["stem"];
       { Prof pr(h, s, "stem7x7", 0.0, 4.0*((double)imgs*P*P*4 + (double)imgs*(P/2)*(P/2)*64));
-      if (ofb_stem_f32(b.patches, imgs, P, P, st.w, st.scale, st.shift, b.conv1, vs)) return -1; }
+      if (ofb_stem_f32(b.patches, imgs, P, P, st.w, st.scale, st.shift, b.conv1, F, vs)) return -1; }
       { Prof pr(h, s, "maxpool", 0.0, 4.0*((double)imgs*(P/2)*(P/2)*64 + (double)imgs*p4*p4*64));
-      if (ofb_maxpool3x3s2_f32(b.conv1, imgs, P / 2, P / 2, 64, b.pool, vs)) return -1; }
+      if (ofb_maxpool3x3s2_f32(b.conv1, imgs, P / 2, P / 2, 64, b.pool, F, vs)) return -1; }
       if (run_res_layer(c, 0, b.pool, 64, p4, b.l1t, b.l1a, b.l1b, nullptr, b.layer1_pre)) return -1;
     }
     // point embedding added to layer1 (:319-320,325 / :385-393)
@@ -413,7 +431,7 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
     OFB_CHECK(mp.cin == g.pts_c, "forward: point table has %d channels, mlp expects %d", g.pts_c, mp.cin);
     { Prof pr(h, s, "point_embed", 0.0, 4.0*((double)imgs*p4*p4*128));
     if (ofb_point_embed_f32(g.pts, N, mp.cin, p4, depth, imgs, mp.w1, mp.s1, mp.t1, mp.w2, mp.s2, mp.t2,
-                            b.layer1_pre, b.layer1, vs)) return -1; }
+                            b.layer1_pre, b.layer1, F, vs)) return -1; }
     if (run_res_layer(c, 1, b.layer1, 64, p4, b.l2t, b.l2a, b.l2b, b.l2d, b.layer2)) return -1;
     if (run_res_layer(c, 2, b.layer2, 128, P / 8, b.l3t, b.l3a, b.l3b, b.l3d, b.layer3)) return -1;
     if (run_res_layer(c, 3, b.layer3, 256, P / 16, b.l4t, b.l4a, b.l4b, b.l4d, b.layer4)) return -1;
@@ -425,50 +443,50 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
     }
     OFB_CHECK(h->pos_patches == N, "forward: pos_emb has %d patches, geometry has %d", h->pos_patches, N);
     { Prof pr(h, s, "token_pack", 0.0, 4.0*((double)imgs*1024));
-    if (ofb_token_pack_f32(b.down, h->pos_emb, imgs, N, b.tok, vs)) return -1; }
+    if (ofb_token_pack_f32(b.down, h->pos_emb, imgs, N, b.tok, F, vs)) return -1; }
     float* x = b.tok;
     float* y = b.tok2;
     for (int i = 0; i < 6; ++i) {   // Transformer_Block, model/blocks.py:84-88
       Block& B = h->blk[i];
       { Prof pr(h, s, "layernorm", 0.0, 4.0*((double)imgs*1024));
-      if (ofb_layernorm_f32(x, B.n1g, B.n1b, imgs, 512, 1e-5f, b.ln, vs)) return -1; }
+      if (ofb_layernorm_f32(x, B.n1g, B.n1b, imgs, 512, 1e-5f, b.ln, F, F, vs)) return -1; }
       if (run_linear(c, B.q, b.ln, nullptr, OFB_ACT_NONE, b.q)) return -1;
       if (run_linear(c, B.kv, b.ln, nullptr, OFB_ACT_NONE, b.kv)) return -1;
       { Prof pr(h, s, "attention", 0.0, 4.0*((double)imgs*2048));
-      if (ofb_attention_f32(b.q, b.kv, Bc, N, 4, 128, b.att, vs)) return -1; }
+      if (ofb_attention_f32(b.q, b.kv, Bc, N, 4, 128, b.att, F, vs)) return -1; }
       if (run_linear(c, B.proj, b.att, x, OFB_ACT_NONE, y)) return -1;          // y = x + proj(att)
       { Prof pr(h, s, "layernorm", 0.0, 4.0*((double)imgs*1024));
-      if (ofb_layernorm_f32(y, B.n2g, B.n2b, imgs, 512, 1e-5f, b.ln, vs)) return -1; }
+      if (ofb_layernorm_f32(y, B.n2g, B.n2b, imgs, 512, 1e-5f, b.ln, F, F, vs)) return -1; }
       if (run_linear(c, B.fc1, b.ln, nullptr, OFB_ACT_GELU, b.fc1)) return -1;
       if (run_linear(c, B.fc2, b.fc1, y, OFB_ACT_NONE, x)) return -1;           // x = y + fc2(gelu(fc1))
     }
     { Prof pr(h, s, "layernorm", 0.0, 4.0*((double)imgs*1024));
-    if (ofb_layernorm_f32(x, h->enc_g, h->enc_b, imgs, 512, 1e-6f, b.enc, vs)) return -1; }
+    if (ofb_layernorm_f32(x, h->enc_g, h->enc_b, imgs, 512, 1e-6f, b.enc, F, OFB_FMT_F32, vs)) return -1; }
 
     // decoder (:337-369); the token broadcast-add (:334-335) is fused into the first upsample
     { Prof pr(h, s, "upsample2x_c512", 0.0, 4.0*5.0*(double)imgs*(P / 32)*(P / 32)*512);
-    if (ofb_upsample2x_f32(b.layer4, b.enc, imgs, P / 32, P / 32, 512, b.up0, vs)) return -1; }
+    if (ofb_upsample2x_f32(b.layer4, b.enc, imgs, P / 32, P / 32, 512, b.up0, F, vs)) return -1; }
     if (run_conv(c, h->conv["de_conv0_0"], b.up0, 512, nullptr, 0, P / 16, P / 16, 1, 1, nullptr, OFB_ACT_RELU, b.d00)) return -1;
     if (run_conv(c, h->conv["de_conv0_1"], b.d00, 256, b.layer3, 256, P / 16, P / 16, 1, 1, nullptr, OFB_ACT_RELU, b.d01)) return -1;
     { Prof pr(h, s, "upsample2x_c128", 0.0, 4.0*5.0*(double)imgs*(P / 16)*(P / 16)*128);
-    if (ofb_upsample2x_f32(b.d01, nullptr, imgs, P / 16, P / 16, 128, b.up1, vs)) return -1; }
+    if (ofb_upsample2x_f32(b.d01, nullptr, imgs, P / 16, P / 16, 128, b.up1, F, vs)) return -1; }
     if (run_conv(c, h->conv["de_conv1_0"], b.up1, 128, nullptr, 0, P / 8, P / 8, 1, 1, nullptr, OFB_ACT_RELU, b.d10)) return -1;
     if (run_conv(c, h->conv["de_conv1_1"], b.d10, 128, b.layer2, 128, P / 8, P / 8, 1, 1, nullptr, OFB_ACT_RELU, b.d11)) return -1;
     { Prof pr(h, s, "upsample2x_c64", 0.0, 4.0*5.0*(double)imgs*(P / 8)*(P / 8)*64);
-    if (ofb_upsample2x_f32(b.d11, nullptr, imgs, P / 8, P / 8, 64, b.up2, vs)) return -1; }
+    if (ofb_upsample2x_f32(b.d11, nullptr, imgs, P / 8, P / 8, 64, b.up2, F, vs)) return -1; }
     if (run_conv(c, h->conv["de_conv2_0"], b.up2, 64, nullptr, 0, p4, p4, 1, 1, nullptr, OFB_ACT_RELU, b.d20)) return -1;
     if (run_conv(c, h->conv["de_conv2_1"], b.d20, 64, b.layer1, 64, p4, p4, 1, 1, nullptr, OFB_ACT_RELU, b.d21)) return -1;
     { Prof pr(h, s, "upsample2x_c64", 0.0, 4.0*5.0*(double)imgs*(p4)*(p4)*64);
-    if (ofb_upsample2x_f32(b.d21, nullptr, imgs, p4, p4, 64, b.up3, vs)) return -1; }
+    if (ofb_upsample2x_f32(b.d21, nullptr, imgs, p4, p4, 64, b.up3, F, vs)) return -1; }
     if (run_conv(c, h->conv["de_conv3_0"], b.up3, 64, nullptr, 0, P / 2, P / 2, 1, 1, nullptr, OFB_ACT_RELU, b.d30)) return -1;
     if (run_conv(c, h->conv["de_conv3_1"], b.d30, 64, b.conv1, 64, P / 2, P / 2, 1, 1, nullptr, OFB_ACT_RELU, b.d31)) return -1;
     { Prof pr(h, s, "upsample2x_c32", 0.0, 4.0*5.0*(double)imgs*(P / 2)*(P / 2)*32);
-    if (ofb_upsample2x_f32(b.d31, nullptr, imgs, P / 2, P / 2, 32, b.up4, vs)) return -1; }
+    if (ofb_upsample2x_f32(b.d31, nullptr, imgs, P / 2, P / 2, 32, b.up4, F, vs)) return -1; }
     if (run_conv(c, h->conv["de_conv4_0"], b.up4, 32, nullptr, 0, P, P, 1, 1, nullptr, OFB_ACT_RELU, b.d40)) return -1;
 
     // heads + ERP merge (:371-380)
     { Prof pr(h, s, "heads", 0.0, 4.0*((double)imgs*P*P*34));
-    if (ofb_heads_f32(b.d40, imgs, P, P, h->pred_w, h->pred_b, h->conf_w, h->conf_b, confidence, b.pred, b.conf, vs)) return -1; }
+    if (ofb_heads_f32(b.d40, imgs, P, P, h->pred_w, h->pred_b, h->conf_w, h->conf_b, confidence, b.pred, b.conf, F, vs)) return -1; }
     float* out = outs[it] + out_off;
     if (confidence) {
       { Prof pr(h, s, "blend_conf", 0.0, 4.0*((double)imgs*P*P*2 + (double)Bc*He*We));
@@ -478,15 +496,15 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
       if (ofb_pers2equi_f32(b.pred, Bc, 1, N, P, P, OFB_LAYOUT_FOLDED, g.blend_rowptr, g.blend_idx, g.blend_w, He, We, out, vs)) return -1; }
     }
   }
-  reg(h, "patches", b.patches, imgs, P, P, 4); reg(h, "conv1", b.conv1, imgs, P / 2, P / 2, 64);
+  reg(h, "patches", b.patches, imgs, P, P, 4, 0); reg(h, "conv1", b.conv1, imgs, P / 2, P / 2, 64);
   reg(h, "pool", b.pool, imgs, p4, p4, 64); reg(h, "layer1_pre", b.layer1_pre, imgs, p4, p4, 64);
   reg(h, "layer1", b.layer1, imgs, p4, p4, 64); reg(h, "layer2", b.layer2, imgs, P / 8, P / 8, 128);
   reg(h, "layer3", b.layer3, imgs, P / 16, P / 16, 256); reg(h, "layer4", b.layer4, imgs, P / 32, P / 32, 512);
-  reg(h, "tokens", b.down, imgs, 4, 4, 32); reg(h, "encoded", b.enc, imgs, 1, 1, 512);
+  reg(h, "tokens", b.down, imgs, 4, 4, 32); reg(h, "encoded", b.enc, imgs, 1, 1, 512, 0);
   reg(h, "de_conv0_1", b.d01, imgs, P / 16, P / 16, 128); reg(h, "de_conv1_1", b.d11, imgs, P / 8, P / 8, 64);
   reg(h, "de_conv2_1", b.d21, imgs, p4, p4, 64); reg(h, "de_conv3_1", b.d31, imgs, P / 2, P / 2, 32);
-  reg(h, "de_conv4_0", b.d40, imgs, P, P, 32); reg(h, "pred_patch", b.pred, imgs, P, P, 1);
-  reg(h, "conf_patch", b.conf, imgs, P, P, 1);
+  reg(h, "de_conv4_0", b.d40, imgs, P, P, 32); reg(h, "pred_patch", b.pred, imgs, P, P, 1, 0);
+  reg(h, "conf_patch", b.conf, imgs, P, P, 1, 0);
   return 0;
 }
 
@@ -563,6 +581,10 @@ extern "C" int ofb_set_option(ofb_handle* h, const char* key, int value) {
   if (!strcmp(key, "engine")) h->engine = value;
   else if (!strcmp(key, "chunk")) h->chunk = value;
   else if (!strcmp(key, "dedup")) h->dedup = value;
+  else if (!strcmp(key, "format")) {
+    OFB_CHECK(value == OFB_FMT_F32 || value == OFB_FMT_SPLIT16, "set_option: format must be 0 (float32) or 1 (split-half)");
+    h->fmt = value;
+  }
   else OFB_CHECK(false, "set_option: unknown key '%s'", key);
   return 0;
 }
@@ -629,7 +651,11 @@ extern "C" int64_t ofb_get_activation(ofb_handle* h, const char* name, float* ds
   if (dims) { dims[0] = a.n; dims[1] = a.h; dims[2] = a.w; dims[3] = a.c; }
   if (dst) {
     OFB_CHECK(capacity >= n, "get_activation: capacity %lld < %lld", (long long)capacity, (long long)n);
-    OFB_CUDA(cudaMemcpyAsync(dst, a.p, n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    if (a.fmt == OFB_FMT_SPLIT16) {
+      if (ofb_merge_f16(a.p, (size_t)n, dst, stream)) return -1;
+    } else {
+      OFB_CUDA(cudaMemcpyAsync(dst, a.p, n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    }
   }
   return n;
 }

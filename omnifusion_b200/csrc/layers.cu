@@ -12,9 +12,10 @@ constexpr int STEM_TH = 8, STEM_TW = 16;
 constexpr int STEM_IH = STEM_TH * 2 + 5, STEM_IW = STEM_TW * 2 + 5;
 constexpr int STEM_SMEM = (49 * 4 * 64 + STEM_IH * STEM_IW * 4) * 4;
 
+template <bool OUT_SPLIT>
 __global__ void __launch_bounds__(128)
 stem_kernel(const float* __restrict__ in, int n, int h, int w, const float* __restrict__ wgt,
-            const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out) {
+            const float* __restrict__ scale, const float* __restrict__ shift, void* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];
   float* sw = smem;                               // [tap][c][64]
   float4* si = reinterpret_cast<float4*>(smem + 49 * 4 * 64);  // [IH][IW]
@@ -68,8 +69,9 @@ stem_kernel(const float* __restrict__ in, int n, int h, int w, const float* __re
       }
     }
   }
-  float* o0 = out + ((size_t)(img * oh_n + oh0 + pr) * ow_n + ow0 + pc) * 64 + half * 32;
-  float* o1 = o0 + (size_t)4 * ow_n * 64;
+  const size_t o0 = ((size_t)(img * oh_n + oh0 + pr) * ow_n + ow0 + pc) * 64 + half * 32;
+  const size_t o1 = o0 + (size_t)4 * ow_n * 64;
+  const size_t plane = (size_t)n * oh_n * ow_n * 64;
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     float4 s = __ldg(reinterpret_cast<const float4*>(scale + half * 32 + j));
@@ -79,14 +81,15 @@ stem_kernel(const float* __restrict__ in, int n, int h, int w, const float* __re
     v0.z = fmaxf(acc0[j + 2] * s.z + b.z, 0.f); v0.w = fmaxf(acc0[j + 3] * s.w + b.w, 0.f);
     v1.x = fmaxf(acc1[j] * s.x + b.x, 0.f); v1.y = fmaxf(acc1[j + 1] * s.y + b.y, 0.f);
     v1.z = fmaxf(acc1[j + 2] * s.z + b.z, 0.f); v1.w = fmaxf(acc1[j + 3] * s.w + b.w, 0.f);
-    st4(o0 + j, v0);
-    st4(o1 + j, v1);
+    act_st4<OUT_SPLIT>(out, o0 + j, plane, v0);
+    act_st4<OUT_SPLIT>(out, o1 + j, plane, v1);
   }
 }
 
 // -------------------------------------------------------------------- maxpool
-__global__ void maxpool_kernel(const float* __restrict__ in, int n, int h, int w, int c4,
-                               float* __restrict__ out) {
+template <bool SPLIT>
+__global__ void maxpool_kernel(const void* __restrict__ in, int n, int h, int w, int c4,
+                               void* __restrict__ out) {
   int oh_n = h / 2, ow_n = w / 2;
   size_t total = (size_t)n * oh_n * ow_n * c4;
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -97,7 +100,7 @@ __global__ void maxpool_kernel(const float* __restrict__ in, int n, int h, int w
   int oh = (int)(r % oh_n);
   int img = (int)(r / oh_n);
   float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-  const float4* src = reinterpret_cast<const float4*>(in);
+  const size_t in_plane = (size_t)n * h * w * c4 * 4;
 #pragma unroll
   for (int dy = -1; dy <= 1; ++dy) {
     int ih = oh * 2 + dy;
@@ -106,19 +109,20 @@ __global__ void maxpool_kernel(const float* __restrict__ in, int n, int h, int w
     for (int dx = -1; dx <= 1; ++dx) {
       int iw = ow * 2 + dx;
       if (iw < 0 || iw >= w) continue;
-      float4 v = __ldg(&src[((size_t)(img * h + ih) * w + iw) * c4 + c]);
+      float4 v = act_ld4<SPLIT>(in, (((size_t)(img * h + ih) * w + iw) * c4 + c) * 4, in_plane);
       m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
     }
   }
-  reinterpret_cast<float4*>(out)[i] = m;
+  act_st4<SPLIT>(out, i * 4, total * 4, m);
 }
 
 // ------------------------------------------------------------------- upsample
 // F.interpolate(scale 2, bilinear, align_corners=False): src = (dst+0.5)/2-0.5 clamped at 0,
 // i1 = min(i0+1, size-1), lambda in {0, .25, .75}.  Same expression tree as ATen's
 // upsample_bilinear2d: h0*(w0*a + w1*b) + h1*(w0*c + w1*d).
-__global__ void upsample2x_kernel(const float* __restrict__ in, const float* __restrict__ img_bias,
-                                  int n, int h, int w, int c4, float* __restrict__ out) {
+template <bool SPLIT>
+__global__ void upsample2x_kernel(const void* __restrict__ in, const float* __restrict__ img_bias,
+                                  int n, int h, int w, int c4, void* __restrict__ out) {
   int oh_n = h * 2, ow_n = w * 2;
   size_t total = (size_t)n * oh_n * ow_n * c4;
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -132,11 +136,12 @@ __global__ void upsample2x_kernel(const float* __restrict__ in, const float* __r
   int y0 = (int)sy, x0 = (int)sx;
   int y1 = y0 + (y0 < h - 1), x1 = x0 + (x0 < w - 1);
   float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
-  const float4* src = reinterpret_cast<const float4*>(in) + (size_t)img * h * w * c4 + c;
-  float4 a = __ldg(&src[((size_t)y0 * w + x0) * c4]);
-  float4 b = __ldg(&src[((size_t)y0 * w + x1) * c4]);
-  float4 cc = __ldg(&src[((size_t)y1 * w + x0) * c4]);
-  float4 d = __ldg(&src[((size_t)y1 * w + x1) * c4]);
+  const size_t in_plane = (size_t)n * h * w * c4 * 4;
+  const size_t ib = ((size_t)img * h * w * c4 + c) * 4;
+  float4 a = act_ld4<SPLIT>(in, ib + ((size_t)y0 * w + x0) * c4 * 4, in_plane);
+  float4 b = act_ld4<SPLIT>(in, ib + ((size_t)y0 * w + x1) * c4 * 4, in_plane);
+  float4 cc = act_ld4<SPLIT>(in, ib + ((size_t)y1 * w + x0) * c4 * 4, in_plane);
+  float4 d = act_ld4<SPLIT>(in, ib + ((size_t)y1 * w + x1) * c4 * 4, in_plane);
   if (img_bias) {
     float4 bb = __ldg(reinterpret_cast<const float4*>(img_bias) + (size_t)img * c4 + c);
     a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
@@ -149,18 +154,19 @@ __global__ void upsample2x_kernel(const float* __restrict__ in, const float* __r
   o.y = hy * (hx * a.y + lx * b.y) + ly * (hx * cc.y + lx * d.y);
   o.z = hy * (hx * a.z + lx * b.z) + ly * (hx * cc.z + lx * d.z);
   o.w = hy * (hx * a.w + lx * b.w) + ly * (hx * cc.w + lx * d.w);
-  reinterpret_cast<float4*>(out)[i] = o;
+  act_st4<SPLIT>(out, i * 4, total * 4, o);
 }
 
 // ---------------------------------------------------------------- point embed
 // 16 threads per pixel, 4 of the 64 output channels each; the 16-wide hidden layer is
 // recomputed per thread (48 FMA) - the kernel is bound by its 256 B/pixel store.
+template <bool SPLIT>
 __global__ void point_embed_kernel(const float* __restrict__ pts, int N, int cin, int p,
                                    const float* __restrict__ depth, int imgs,
                                    const float* __restrict__ w1, const float* __restrict__ s1,
                                    const float* __restrict__ t1, const float* __restrict__ w2,
                                    const float* __restrict__ s2, const float* __restrict__ t2,
-                                   const float* __restrict__ base, float* __restrict__ out) {
+                                   const void* __restrict__ base, void* __restrict__ out) {
   size_t total = (size_t)imgs * p * p * 16;
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -193,39 +199,43 @@ __global__ void point_embed_kernel(const float* __restrict__ pts, int N, int cin
   }
   size_t off = pix * 64 + g * 4;
   float4 v = make_float4(o[0], o[1], o[2], o[3]);
+  const size_t plane = (size_t)imgs * p * p * 64;
   if (base) {
-    float4 b = __ldg(reinterpret_cast<const float4*>(base + off));
+    float4 b = act_ld4<SPLIT>(base, off, plane);
     v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
   }
-  st4(out + off, v);
+  act_st4<SPLIT>(out, off, plane, v);
 }
 
 // ----------------------------------------------------------------- token pack
-__global__ void token_pack_kernel(const float* __restrict__ down, const float* __restrict__ pos,
-                                  int imgs, int N, float* __restrict__ tokens) {
+template <bool SPLIT>
+__global__ void token_pack_kernel(const void* __restrict__ down, const float* __restrict__ pos,
+                                  int imgs, int N, void* __restrict__ tokens) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= imgs * 512) return;
   int img = i >> 9, t = i & 511;
   int c = t >> 4, ij = t & 15;
-  tokens[i] = down[(size_t)img * 512 + ij * 32 + c] + __ldg(&pos[(img % N) * 512 + t]);
+  const size_t plane = (size_t)imgs * 512;
+  float v = act_ld1<SPLIT>(down, (size_t)img * 512 + ij * 32 + c, plane) + __ldg(&pos[(img % N) * 512 + t]);
+  act_st1<SPLIT>(tokens, i, plane, v);
 }
 
 // ------------------------------------------------------------------ layernorm
 // One warp per row; mean, then variance of the centred values (two passes in registers).
-template <int DIM>
-__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+template <int DIM, bool IN_SPLIT, bool OUT_SPLIT>
+__global__ void layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, int rows, float eps,
-                                 float* __restrict__ y) {
+                                 void* __restrict__ y) {
   constexpr int PER = DIM / 32;
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const float* xr = x + (size_t)row * DIM;
+  const size_t plane = (size_t)rows * DIM;
   float v[PER];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < PER; i += 4) {
-    float4 t = ld4(xr + (i / 4) * 128 + lane * 4);
+    float4 t = act_ld4<IN_SPLIT>(x, (size_t)row * DIM + (i / 4) * 128 + lane * 4, plane);
     v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
     s += t.x + t.y + t.z + t.w;
   }
@@ -249,7 +259,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
     o.y = (v[i + 1] - mean) * rstd * g.y + b.y;
     o.z = (v[i + 2] - mean) * rstd * g.z + b.z;
     o.w = (v[i + 3] - mean) * rstd * g.w + b.w;
-    st4(y + (size_t)row * DIM + col, o);
+    act_st4<OUT_SPLIT>(y, (size_t)row * DIM + col, plane, o);
   }
 }
 
@@ -258,9 +268,10 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 // memory (rows padded to 129 floats), scores + softmax + PV entirely on chip.
 constexpr int ATT_MAXN = 64, ATT_D = 128, ATT_LD = ATT_D + 1;
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(128)
-attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, int N, int heads,
-                 float scale, float* __restrict__ out) {
+attention_kernel(const void* __restrict__ q, const void* __restrict__ kv, int N, int heads,
+                 float scale, void* __restrict__ out, int rows) {
   extern __shared__ float sm[];
   float* sq = sm;
   float* sk = sq + N * ATT_LD;
@@ -272,9 +283,9 @@ attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, int 
   for (int i = tid; i < N * ATT_D; i += 128) {
     int r = i / ATT_D, d = i % ATT_D;
     size_t row = (size_t)b * N + r;
-    sq[r * ATT_LD + d] = q[row * dim + hd * ATT_D + d];
-    sk[r * ATT_LD + d] = kv[row * 2 * dim + hd * ATT_D + d];
-    sv[r * ATT_LD + d] = kv[row * 2 * dim + dim + hd * ATT_D + d];
+    sq[r * ATT_LD + d] = act_ld1<SPLIT>(q, row * dim + hd * ATT_D + d, (size_t)rows * dim);
+    sk[r * ATT_LD + d] = act_ld1<SPLIT>(kv, row * 2 * dim + hd * ATT_D + d, (size_t)rows * 2 * dim);
+    sv[r * ATT_LD + d] = act_ld1<SPLIT>(kv, row * 2 * dim + dim + hd * ATT_D + d, (size_t)rows * 2 * dim);
   }
   __syncthreads();
   for (int i = tid; i < N * N; i += 128) {
@@ -306,7 +317,7 @@ attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, int 
   for (int r = 0; r < N; ++r) {
     float a = 0.f;
     for (int c = 0; c < N; ++c) a += sp[r * (N + 1) + c] * sv[c * ATT_LD + tid];
-    out[((size_t)b * N + r) * dim + hd * ATT_D + tid] = a;
+    act_st1<SPLIT>(out, ((size_t)b * N + r) * dim + hd * ATT_D + tid, (size_t)rows * dim, a);
   }
 }
 
@@ -317,8 +328,9 @@ attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, int 
 // store and the per-pixel reads).
 constexpr int HD_T = 16, HD_I = HD_T + 2, HD_PLANE = HD_I * HD_I + 1;
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(256)
-heads_kernel(const float* __restrict__ x, int imgs, int h, int w, const float* __restrict__ wp,
+heads_kernel(const void* __restrict__ x, int imgs, int h, int w, const float* __restrict__ wp,
              float bp, const float* __restrict__ wc, float bc, int confidence,
              float* __restrict__ pred_out, float* __restrict__ conf_out) {
   __shared__ float tile[32 * HD_PLANE];
@@ -339,7 +351,8 @@ heads_kernel(const float* __restrict__ x, int imgs, int h, int w, const float* _
     int yy = pix / HD_I, xx = pix - yy * HD_I;
     int ih = y0 + yy, iw = x0 + xx;
     float v = 0.f;
-    if (ih >= 0 && ih < h && iw >= 0 && iw < w) v = __ldg(&x[((size_t)(img * h + ih) * w + iw) * 32 + c]);
+    if (ih >= 0 && ih < h && iw >= 0 && iw < w)
+      v = act_ld1<SPLIT>(x, ((size_t)(img * h + ih) * w + iw) * 32 + c, (size_t)imgs * h * w * 32);
     tile[c * HD_PLANE + pix] = v;
   }
   __syncthreads();
@@ -371,91 +384,107 @@ heads_kernel(const float* __restrict__ x, int imgs, int h, int w, const float* _
 
 using namespace ofb;
 
+#define OFB_FMT_OK(f) ((f) == OFB_FMT_F32 || (f) == OFB_FMT_SPLIT16)
+
 extern "C" int ofb_stem_f32(const float* in, int n, int h, int w, const float* wgt, const float* scale,
-                            const float* shift, float* out, void* stream) {
-  OFB_CHECK(in && wgt && scale && shift && out, "stem: null pointer");
+                            const float* shift, void* out, int out_fmt, void* stream) {
+  OFB_CHECK(in && wgt && scale && shift && out && OFB_FMT_OK(out_fmt), "stem: bad arguments");
   OFB_CHECK(h % (2 * STEM_TH) == 0 && w % (2 * STEM_TW) == 0, "stem: h,w must be multiples of 16,32 (got %d,%d)", h, w);
   static bool attr = false;
   if (!attr) {
-    OFB_CUDA(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM));
+    OFB_CUDA(cudaFuncSetAttribute(stem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM));
+    OFB_CUDA(cudaFuncSetAttribute(stem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM));
     attr = true;
   }
   int blocks = n * (h / 2 / STEM_TH) * (w / 2 / STEM_TW);
-  stem_kernel<<<blocks, 128, STEM_SMEM, (cudaStream_t)stream>>>(in, n, h, w, wgt, scale, shift, out);
+  if (out_fmt) stem_kernel<true><<<blocks, 128, STEM_SMEM, (cudaStream_t)stream>>>(in, n, h, w, wgt, scale, shift, out);
+  else stem_kernel<false><<<blocks, 128, STEM_SMEM, (cudaStream_t)stream>>>(in, n, h, w, wgt, scale, shift, out);
   OFB_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int ofb_maxpool3x3s2_f32(const float* in, int n, int h, int w, int c, float* out, void* stream) {
-  OFB_CHECK(in && out && c % 4 == 0 && h % 2 == 0 && w % 2 == 0, "maxpool: bad arguments");
+extern "C" int ofb_maxpool3x3s2_f32(const void* in, int n, int h, int w, int c, void* out, int fmt, void* stream) {
+  OFB_CHECK(in && out && c % 4 == 0 && h % 2 == 0 && w % 2 == 0 && OFB_FMT_OK(fmt), "maxpool: bad arguments");
   size_t total = (size_t)n * (h / 2) * (w / 2) * (c / 4);
-  maxpool_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, n, h, w, c / 4, out);
+  if (fmt) maxpool_kernel<true><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, n, h, w, c / 4, out);
+  else maxpool_kernel<false><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, n, h, w, c / 4, out);
   OFB_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int ofb_upsample2x_f32(const float* in, const float* img_bias, int n, int h, int w, int c,
-                                  float* out, void* stream) {
-  OFB_CHECK(in && out && c % 4 == 0, "upsample2x: bad arguments");
+extern "C" int ofb_upsample2x_f32(const void* in, const float* img_bias, int n, int h, int w, int c,
+                                  void* out, int fmt, void* stream) {
+  OFB_CHECK(in && out && c % 4 == 0 && OFB_FMT_OK(fmt), "upsample2x: bad arguments");
   size_t total = (size_t)n * h * 2 * w * 2 * (c / 4);
-  upsample2x_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, img_bias, n, h, w, c / 4, out);
+  if (fmt) upsample2x_kernel<true><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, img_bias, n, h, w, c / 4, out);
+  else upsample2x_kernel<false><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, img_bias, n, h, w, c / 4, out);
   OFB_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int ofb_point_embed_f32(const float* pts, int N, int cin, int p, const float* depth, int imgs,
                                    const float* w1, const float* s1, const float* t1, const float* w2,
-                                   const float* s2, const float* t2, const float* base, float* out,
+                                   const float* s2, const float* t2, const void* base, void* out, int fmt,
                                    void* stream) {
-  OFB_CHECK(pts && w1 && s1 && t1 && w2 && s2 && t2 && out, "point_embed: null pointer");
+  OFB_CHECK(pts && w1 && s1 && t1 && w2 && s2 && t2 && out && OFB_FMT_OK(fmt), "point_embed: bad arguments");
   OFB_CHECK(cin >= 1 && cin <= 5, "point_embed: cin must be <= 5 (got %d)", cin);
   size_t total = (size_t)imgs * p * p * 16;
-  point_embed_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      pts, N, cin, p, depth, imgs, w1, s1, t1, w2, s2, t2, base, out);
+  if (fmt) point_embed_kernel<true><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(pts, N, cin, p, depth, imgs, w1, s1, t1, w2, s2, t2, base, out);
+  else point_embed_kernel<false><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(pts, N, cin, p, depth, imgs, w1, s1, t1, w2, s2, t2, base, out);
   OFB_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int ofb_token_pack_f32(const float* down, const float* pos_emb, int imgs, int N, float* tokens,
+extern "C" int ofb_token_pack_f32(const void* down, const float* pos_emb, int imgs, int N, void* tokens, int fmt,
                                   void* stream) {
-  OFB_CHECK(down && pos_emb && tokens, "token_pack: null pointer");
-  token_pack_kernel<<<cdiv((long long)imgs * 512, 256), 256, 0, (cudaStream_t)stream>>>(down, pos_emb, imgs, N, tokens);
+  OFB_CHECK(down && pos_emb && tokens && OFB_FMT_OK(fmt), "token_pack: bad arguments");
+  int blocks = cdiv((long long)imgs * 512, 256);
+  if (fmt) token_pack_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(down, pos_emb, imgs, N, tokens);
+  else token_pack_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(down, pos_emb, imgs, N, tokens);
   OFB_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int ofb_layernorm_f32(const float* x, const float* gamma, const float* beta, int rows, int dim,
-                                 float eps, float* y, void* stream) {
-  OFB_CHECK(x && gamma && beta && y, "layernorm: null pointer");
+extern "C" int ofb_layernorm_f32(const void* x, const float* gamma, const float* beta, int rows, int dim,
+                                 float eps, void* y, int in_fmt, int out_fmt, void* stream) {
+  OFB_CHECK(x && gamma && beta && y && OFB_FMT_OK(in_fmt) && OFB_FMT_OK(out_fmt), "layernorm: bad arguments");
   OFB_CHECK(dim == 512, "layernorm: dim must be 512 (got %d)", dim);
-  layernorm_kernel<512><<<cdiv(rows, 4), 128, 0, (cudaStream_t)stream>>>(x, gamma, beta, rows, eps, y);
+  cudaStream_t s = (cudaStream_t)stream;
+  int blocks = cdiv(rows, 4);
+  if (!in_fmt && !out_fmt) layernorm_kernel<512, false, false><<<blocks, 128, 0, s>>>(x, gamma, beta, rows, eps, y);
+  else if (in_fmt && out_fmt) layernorm_kernel<512, true, true><<<blocks, 128, 0, s>>>(x, gamma, beta, rows, eps, y);
+  else if (in_fmt) layernorm_kernel<512, true, false><<<blocks, 128, 0, s>>>(x, gamma, beta, rows, eps, y);
+  else layernorm_kernel<512, false, true><<<blocks, 128, 0, s>>>(x, gamma, beta, rows, eps, y);
   OFB_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int ofb_attention_f32(const float* q, const float* kv, int B, int N, int heads, int head_dim,
-                                 float* out, void* stream) {
-  OFB_CHECK(q && kv && out, "attention: null pointer");
+extern "C" int ofb_attention_f32(const void* q, const void* kv, int B, int N, int heads, int head_dim,
+                                 void* out, int fmt, void* stream) {
+  OFB_CHECK(q && kv && out && OFB_FMT_OK(fmt), "attention: bad arguments");
   OFB_CHECK(head_dim == ATT_D && N <= ATT_MAXN && N > 0, "attention: head_dim must be 128 and N <= 64 (got %d, %d)", head_dim, N);
   int smem = (3 * N * ATT_LD + N * (N + 1)) * 4;
   static int attr_smem = 0;
   if (smem > attr_smem) {
-    OFB_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    OFB_CUDA(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    OFB_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
   }
-  attention_kernel<<<B * heads, 128, smem, (cudaStream_t)stream>>>(q, kv, N, heads, 1.f / sqrtf((float)head_dim), out);
+  float sc = 1.f / sqrtf((float)head_dim);
+  if (fmt) attention_kernel<true><<<B * heads, 128, smem, (cudaStream_t)stream>>>(q, kv, N, heads, sc, out, B * N);
+  else attention_kernel<false><<<B * heads, 128, smem, (cudaStream_t)stream>>>(q, kv, N, heads, sc, out, B * N);
   OFB_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int ofb_heads_f32(const float* x, int imgs, int h, int w, const float* w_pred, float b_pred,
+extern "C" int ofb_heads_f32(const void* x, int imgs, int h, int w, const float* w_pred, float b_pred,
                              const float* w_conf, float b_conf, int confidence, float* pred_out,
-                             float* conf_out, void* stream) {
-  OFB_CHECK(x && w_pred && pred_out && (!confidence || (w_conf && conf_out)), "heads: null pointer");
+                             float* conf_out, int in_fmt, void* stream) {
+  OFB_CHECK(x && w_pred && pred_out && (!confidence || (w_conf && conf_out)) && OFB_FMT_OK(in_fmt), "heads: bad arguments");
   OFB_CHECK(h % HD_T == 0 && w % HD_T == 0, "heads: h,w must be multiples of 16");
   int blocks = imgs * (h / HD_T) * (w / HD_T);
-  heads_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, imgs, h, w, w_pred, b_pred, w_conf, b_conf,
-                                                         confidence, pred_out, conf_out);
+  if (in_fmt) heads_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, imgs, h, w, w_pred, b_pred, w_conf, b_conf, confidence, pred_out, conf_out);
+  else heads_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, imgs, h, w, w_pred, b_pred, w_conf, b_conf, confidence, pred_out, conf_out);
   OFB_LAUNCH_CHECK();
   return 0;
 }

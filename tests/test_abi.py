@@ -36,7 +36,7 @@ def test_errors_are_reported_not_swallowed():
     assert L.ofb_equi2pers_f32(None, 1, 3, 8, 16, None, 18, 4, 4, None, 0, None) < 0
     assert b"null" in L.ofb_last_error()
     with pytest.raises(_lib.OfbError):
-        _lib.check(L.ofb_layernorm_f32(None, None, None, 1, 512, 1e-5, None, None))
+        _lib.check(L.ofb_layernorm_f32(None, None, None, 1, 512, 1e-5, None, 0, 0, None))
     with pytest.raises(_lib.OfbError):
         _lib.require_cuda(torch.zeros(1, 3, 8, 16), "x")          # no CPU fallback
 

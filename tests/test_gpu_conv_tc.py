@@ -1,0 +1,100 @@
+"""tcgen05 implicit-GEMM conv engine vs torch-CPU fp32 (and vs the CUDA-core engine).
+
+F16X3 mode (split-half planes, three kind::f16 MMAs) must be fp32-accurate; TF32 mode (one
+kind::tf32 MMA on float32 tensors) is only TF32-accurate and is tested at 3e-3."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from omnifusion_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def ops():
+    import ofb_ops
+    return ofb_ops
+
+
+def rand(*shape, seed=0, scale=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+TC_CASES = [
+    # n, hw, c0, c1, cout, k, residual, act
+    (2, 32, 64, 0, 64, 3, True, 1),       # layer1 block conv
+    (3, 16, 128, 0, 128, 3, True, 1),     # layer2
+    (5, 8, 256, 0, 256, 3, False, 1),     # layer3 (2 images per tile, ragged last group)
+    (19, 4, 512, 0, 512, 3, True, 1),     # layer4 (8 images per tile, ragged)
+    (3, 8, 256, 256, 128, 3, False, 1),   # de_conv0_1 (concat)
+    (2, 64, 64, 64, 32, 3, False, 1),     # de_conv3_1 (concat, cout 32)
+    (1, 128, 32, 0, 32, 3, False, 1),     # de_conv4_0 (cin 32: 64-byte rows in F16X3)
+    (2, 64, 64, 0, 64, 3, False, 1),      # de_conv3_0
+    (200, 1, 512, 0, 2048, 1, False, 2),  # fc1 + GELU as 1x1
+    (144, 1, 2048, 0, 512, 1, True, 0),   # fc2 + residual
+    (4, 4, 512, 0, 32, 1, False, 0),      # down1
+]
+
+
+def reference(case, seed=0):
+    n, hw, c0, c1, cout, k, use_res, act = case
+    x0 = rand(n, c0, hw, hw, seed=seed + 1)
+    x1 = rand(n, c1, hw, hw, seed=seed + 2) if c1 else None
+    w = rand(cout, c0 + c1, k, k, seed=seed + 3, scale=(1.0 / ((c0 + c1) * k * k)) ** 0.5)
+    scale = 0.5 + torch.rand(cout, generator=torch.Generator().manual_seed(seed + 4))
+    shift = rand(cout, seed=seed + 5, scale=0.1)
+    res = rand(n, cout, hw, hw, seed=seed + 6) if use_res else None
+    x = x0 if x1 is None else torch.cat([x0, x1], 1)
+    y = F.conv2d(x, w, None, 1, k // 2) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    if res is not None:
+        y = y + res
+    y = F.relu(y) if act == 1 else (F.gelu(y) if act == 2 else y)
+    return x0, x1, w, scale, shift, res, y
+
+
+def run(case, engine, fmt):
+    o = ops()
+    n, hw, c0, c1, cout, k, use_res, act = case
+    x0, x1, w, scale, shift, res, y = reference(case)
+    got = o.conv_fmt(o.nhwc(x0).to(DEV), o.ohwi(w).to(DEV), k, 1, k // 2,
+                     in1=o.nhwc(x1).to(DEV) if c1 else None, scale=scale.to(DEV), shift=shift.to(DEV),
+                     residual=o.nhwc(res).to(DEV) if use_res else None, act=act, engine=engine, in_fmt=fmt, out_fmt=fmt)
+    torch.cuda.synchronize()
+    return o.nchw(got.cpu()), y
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tc_f16x3_matches_fp32(case):
+    got, ref = run(case, _lib.ENGINE_TC, _lib.FMT_SPLIT16)
+    err = (got - ref).abs()
+    print(f"[parity] conv_tc f16x3 {case}: max_abs_err={err.max().item():.3e} ref_absmax={ref.abs().max().item():.3e}")
+    # tensor-core fp32 accumulation truncates (round-toward-zero) on every K-block add, so the error
+    # grows ~linearly with K (observed 1e-4 abs at K=4608) instead of ~sqrt(K) for FFMA
+    assert (err <= 1.5e-4 + 5e-5 * ref.abs()).all()
+
+
+@pytest.mark.parametrize("case", TC_CASES[:7])
+def test_conv_tc_tf32_matches_fp32_loosely(case):
+    got, ref = run(case, _lib.ENGINE_TC, _lib.FMT_F32)
+    err = (got - ref).abs()
+    print(f"[parity] conv_tc tf32 {case}: max_abs_err={err.max().item():.3e} ref_absmax={ref.abs().max().item():.3e}")
+    assert (err <= 1e-2 + 3e-3 * ref.abs()).all()
+
+
+@pytest.mark.parametrize("case", [TC_CASES[0], TC_CASES[4], TC_CASES[9]])
+def test_conv_simt_split_format_matches_fp32(case):
+    got, ref = run(case, _lib.ENGINE_SIMT, _lib.FMT_SPLIT16)
+    err = (got - ref).abs()
+    print(f"[parity] conv_simt split {case}: max_abs_err={err.max().item():.3e}")
+    assert (err <= 3e-5 + 3e-5 * ref.abs()).all()
+
+
+def test_split_merge_roundtrip_precision():
+    o = ops()
+    x = rand(1 << 16, seed=1, scale=10.0).to(DEV)
+    back = o.merge16(o.split16(x), x.shape)
+    err = (back - x).abs()
+    print(f"[parity] split16 roundtrip max abs err {err.max().item():.3e}")
+    # ~22 mantissa bits, and an absolute floor of half an fp16 subnormal step (2^-25) on the lo plane
+    assert (err <= 3.1e-8 + 2.5e-7 * x.abs()).all()
