@@ -24,12 +24,13 @@ namespace ofb {
 enum { MODE_TF32 = 0, MODE_F16X3 = 1 };
 
 struct TcParams {
-  int n_img, H, W, c0, c1, cout, k, pad;
+  int n_img, H, W, c0, c1, cout, k, pad, stride;   // H, W: output dims
   int BW, BH, BNI, tiles_x, tiles_y;
   const float* scale; const float* shift; float wscale;
   const void* residual; void* out;
   int act;
   long long plane;   // elements per plane of out / residual (split format)
+  int tiles_n, total_tiles;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -127,72 +128,89 @@ __device__ __forceinline__ float act_fn(float v, int act) {
   return v;
 }
 
-template <int BN, int MODE, int ROW_BYTES>
+// Per-configuration constants.  TMA_STORE: the epilogue stages 32-column chunks in shared
+// memory (swizzled) and writes them with cp.async.bulk.tensor stores (coalesced, asynchronous);
+// used for the narrow-N, HBM-bound layers.  Wide tiles store straight from registers.
+template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE>
 struct TcCfg {
   static constexpr int PLANES = MODE == MODE_F16X3 ? 2 : 1;
+  static constexpr int ES = MODE == MODE_F16X3 ? 2 : 4;
   static constexpr int A_BYTES = 128 * ROW_BYTES;
   static constexpr int B_BYTES = BN * ROW_BYTES;
   static constexpr int STAGE = (A_BYTES + B_BYTES) * PLANES;
-  static constexpr int NST_RAW = (196 * 1024) / STAGE;
+  static constexpr int OUT_ROW = 32 * ES;                                  // bytes per staged row (32 columns)
+  static constexpr int OUT_BUF = TMA_STORE ? PLANES * 128 * OUT_ROW : 0;   // one staging buffer
+  static constexpr int MISC = 1024 /*align*/ + 256 /*barriers*/ + BN * 8;
+  static constexpr int NST_RAW = (227 * 1024 - MISC - 2 * OUT_BUF) / STAGE;
   static constexpr int NST = NST_RAW > 8 ? 8 : NST_RAW;
-  static constexpr int KC = ROW_BYTES / (MODE == MODE_F16X3 ? 2 : 4);   // channels per K-step
-  static constexpr int MMA_PER_TILE = ROW_BYTES / 32;                  // UMMA_K spans 32 bytes
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-  static constexpr int SMEM = NST * STAGE + 1024 /*align*/ + 256 /*barriers*/ + BN * 8;
+  static constexpr int KC = ROW_BYTES / ES;                                // channels per K-step
+  static constexpr int MMA_PER_TILE = ROW_BYTES / 32;                      // UMMA_K spans 32 bytes
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;              // two accumulator buffers
+  static constexpr int SMEM = NST * STAGE + 2 * OUT_BUF + MISC;
+  static_assert(NST >= 2, "pipeline needs at least two stages");
 };
 
-// tensor maps: a[src][plane] activations, b[plane] weights
+// tensor maps: a[src][plane] activations, b[plane] weights, o[plane] output (TMA_STORE only)
 struct TcMaps {
   CUtensorMap a[2][2];
   CUtensorMap b[2];
+  CUtensorMap o[2];
 };
 
-template <int BN, int MODE, int ROW_BYTES>
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+// Persistent kernel: each CTA walks tiles t = blockIdx.x, +gridDim.x, ...; the smem ring and its
+// phases run continuously across tiles, and two TMEM accumulator buffers let the MMA warp start
+// tile i+1 while the epilogue warps drain tile i.
+template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
-  using Cfg = TcCfg<BN, MODE, ROW_BYTES>;
+  using Cfg = TcCfg<BN, MODE, ROW_BYTES, TMA_STORE>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw);
-  const uint32_t bars = base + Cfg::NST * Cfg::STAGE;       // full[NST], empty[NST], tmem_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + Cfg::NST * Cfg::STAGE + 8 * (2 * Cfg::NST + 1));
-  float* s_scale = reinterpret_cast<float*>(base_ptr + Cfg::NST * Cfg::STAGE + 256);
+  constexpr int RING = Cfg::NST * Cfg::STAGE;
+  const uint32_t stage_out = base + RING;                        // 2 staging buffers (TMA_STORE)
+  uint8_t* stage_out_ptr = base_ptr + RING;
+  constexpr int AFTER = RING + 2 * Cfg::OUT_BUF;
+  const uint32_t bars = base + AFTER;                            // full[NST], empty[NST], tfull[2], tempty[2]
+  const uint32_t bar_tfull = bars + 8 * (2 * Cfg::NST), bar_tempty = bar_tfull + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + AFTER + 8 * (2 * Cfg::NST + 4));
+  float* s_scale = reinterpret_cast<float*>(base_ptr + AFTER + 256);
   float* s_shift = s_scale + BN;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cin = p.c0 + p.c1;
   const int cchunks = cin / Cfg::KC;
   const int ksteps = p.k * p.k * cchunks;
-
-  // tile coordinates
   const int tiles_per_group = p.tiles_x * p.tiles_y;
-  const int grp = blockIdx.x / tiles_per_group;
-  const int trem = blockIdx.x - grp * tiles_per_group;
-  const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
-  const int img0 = grp * p.BNI, y0 = ty * p.BH, x0 = tx * p.BW;
-  const int n0 = blockIdx.y * BN;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < Cfg::NST; ++i) {
       mbar_init(bars + 8 * i, 1);
       mbar_init(bars + 8 * (Cfg::NST + i), 1);
     }
-    mbar_init(bars + 8 * (2 * Cfg::NST), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, 4);          // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&maps.a[0][0]);
     tma_prefetch_desc(&maps.b[0]);
+    if (TMA_STORE) tma_prefetch_desc(&maps.o[0]);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < BN; i += 128) {
-      s_scale[i] = (p.scale ? __ldg(&p.scale[n0 + i]) : 1.f) * p.wscale;
-      s_shift[i] = p.shift ? __ldg(&p.shift[n0 + i]) : 0.f;
-    }
   }
   tc_fence_before();
   __syncthreads();
@@ -202,23 +220,31 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const int st = ks % Cfg::NST;
-        const uint32_t ph = (ks / Cfg::NST) & 1;
-        mbar_wait(bars + 8 * (Cfg::NST + st), ph ^ 1);
-        const int tap = ks / cchunks, cq = ks - tap * cchunks;
-        const int kh = tap / p.k, kw = tap - kh * p.k;
-        int c = cq * Cfg::KC;
-        int src = 0;
-        if (c >= p.c0) { src = 1; c -= p.c0; }
-        const uint32_t full = bars + 8 * st;
-        mbar_expect_tx(full, Cfg::STAGE);
-        const uint32_t sa = base + st * Cfg::STAGE;
-        const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int nt = t % p.tiles_n, mt = t / p.tiles_n;
+        const int grp = mt / tiles_per_group, trem = mt - grp * tiles_per_group;
+        const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
+        const int img0 = grp * p.BNI, y0 = ty * p.BH, x0 = tx * p.BW, n0 = nt * BN;
+        for (int ks = 0; ks < ksteps; ++ks, ++it) {
+          const int st = it % Cfg::NST;
+          const uint32_t ph = (it / Cfg::NST) & 1;
+          mbar_wait(bars + 8 * (Cfg::NST + st), ph ^ 1);
+          const int tap = ks / cchunks, cq = ks - tap * cchunks;
+          const int kh = tap / p.k, kw = tap - kh * p.k;
+          int c = cq * Cfg::KC;
+          int src = 0;
+          if (c >= p.c0) { src = 1; c -= p.c0; }
+          const uint32_t full = bars + 8 * st;
+          mbar_expect_tx(full, Cfg::STAGE);
+          const uint32_t sa = base + st * Cfg::STAGE;
+          const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
 #pragma unroll
-        for (int pl = 0; pl < Cfg::PLANES; ++pl) {
-          tma_load_4d(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, x0 + kw - p.pad, y0 + kh - p.pad, img0);
-          tma_load_2d(sb + pl * Cfg::B_BYTES, &maps.b[pl], full, tap * cin + cq * Cfg::KC, n0);
+          for (int pl = 0; pl < Cfg::PLANES; ++pl) {
+            tma_load_4d(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, x0 * p.stride + kw - p.pad,
+                        y0 * p.stride + kh - p.pad, img0);
+            tma_load_2d(sb + pl * Cfg::B_BYTES, &maps.b[pl], full, tap * cin + cq * Cfg::KC, n0);
+          }
         }
       }
     }
@@ -229,102 +255,177 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       // (bits 7/10: 0 = F16, 2 = TF32), K-major A and B, N >> 3 at bit 17, M >> 4 at bit 24.
       const uint32_t fmt = MODE == MODE_TF32 ? 2u : 0u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const int st = ks % Cfg::NST;
-        const uint32_t ph = (ks / Cfg::NST) & 1;
-        mbar_wait(bars + 8 * st, ph);
+      uint32_t it = 0, i = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
+        const uint32_t buf = i & 1;
+        mbar_wait(bar_tempty + 8 * buf, ((i >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = base + st * Cfg::STAGE;
-        const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
-        const uint64_t a_hi = umma_desc<ROW_BYTES>(sa), b_hi = umma_desc<ROW_BYTES>(sb);
-        if (MODE == MODE_TF32) {
+        const uint32_t acc = tmem + buf * BN;
+        for (int ks = 0; ks < ksteps; ++ks, ++it) {
+          const int st = it % Cfg::NST;
+          const uint32_t ph = (it / Cfg::NST) & 1;
+          mbar_wait(bars + 8 * st, ph);
+          tc_fence_after();
+          const uint32_t sa = base + st * Cfg::STAGE;
+          const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
+          const uint64_t a_hi = umma_desc<ROW_BYTES>(sa), b_hi = umma_desc<ROW_BYTES>(sb);
+          if (MODE == MODE_TF32) {
 #pragma unroll
-          for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk)
-            tc_mma<MODE>(tmem, a_hi + 2 * kk, b_hi + 2 * kk, idesc, (ks | kk) != 0);
-        } else {
-          const uint64_t a_lo = umma_desc<ROW_BYTES>(sa + Cfg::A_BYTES), b_lo = umma_desc<ROW_BYTES>(sb + Cfg::B_BYTES);
+            for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk)
+              tc_mma<MODE>(acc, a_hi + 2 * kk, b_hi + 2 * kk, idesc, (ks | kk) != 0);
+          } else {
+            const uint64_t a_lo = umma_desc<ROW_BYTES>(sa + Cfg::A_BYTES), b_lo = umma_desc<ROW_BYTES>(sb + Cfg::B_BYTES);
 #pragma unroll
-          for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk) {
-            tc_mma<MODE>(tmem, a_hi + 2 * kk, b_hi + 2 * kk, idesc, (ks | kk) != 0);
-            tc_mma<MODE>(tmem, a_lo + 2 * kk, b_hi + 2 * kk, idesc, 1);
-            tc_mma<MODE>(tmem, a_hi + 2 * kk, b_lo + 2 * kk, idesc, 1);
+            for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk) {
+              tc_mma<MODE>(acc, a_hi + 2 * kk, b_hi + 2 * kk, idesc, (ks | kk) != 0);
+              tc_mma<MODE>(acc, a_lo + 2 * kk, b_hi + 2 * kk, idesc, 1);
+              tc_mma<MODE>(acc, a_hi + 2 * kk, b_lo + 2 * kk, idesc, 1);
+            }
           }
+          tc_commit(bars + 8 * (Cfg::NST + st));       // frees this smem stage when the MMAs retire
         }
-        tc_commit(bars + 8 * (Cfg::NST + st));       // frees this smem stage when the MMAs retire
+        tc_commit(bar_tfull + 8 * buf);                // accumulator complete
       }
-      tc_commit(bars + 8 * (2 * Cfg::NST));          // accumulator complete
     }
   } else {
     // ===================== epilogue (warps 2..5 <-> TMEM lane quarters) =====================
-    mbar_wait(bars + 8 * (2 * Cfg::NST), 0);
-    tc_fence_after();
     const int q = warp & 3;                    // a warp may only touch TMEM lanes [32*(warp%4), +32)
     const int r = q * 32 + lane;               // accumulator row = pixel within the tile
     const int xx = r % p.BW, yy = (r / p.BW) % p.BH, ni = r / (p.BW * p.BH);
-    const int img = img0 + ni;
-    const bool ok = img < p.n_img;
-    const size_t pix = ((size_t)(ok ? img : 0) * p.H + (y0 + yy)) * p.W + (x0 + xx);
-    const size_t off = pix * p.cout + n0;
-#pragma unroll 1
-    for (int cb = 0; cb < BN; cb += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + cb, v);
-      if (!ok) continue;
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * s_scale[cb + j] + s_shift[cb + j];
-      if (MODE == MODE_TF32) {
-        float* o = reinterpret_cast<float*>(p.out) + off + cb;
-        if (p.residual) {
-          const float* rs = reinterpret_cast<const float*>(p.residual) + off + cb;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 t = __ldg(reinterpret_cast<const float4*>(rs + j));
-            f[j] += t.x; f[j + 1] += t.y; f[j + 2] += t.z; f[j + 3] += t.w;
-          }
+    const int et = threadIdx.x - 64;           // 0..127
+    int last_n0 = -1;
+    uint32_t i = 0, chunk_ctr = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
+      const int nt = t % p.tiles_n, mt = t / p.tiles_n;
+      const int grp = mt / tiles_per_group, trem = mt - grp * tiles_per_group;
+      const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
+      const int img0 = grp * p.BNI, y0 = ty * p.BH, x0 = tx * p.BW, n0 = nt * BN;
+      if (n0 != last_n0) {
+        epi_bar();                               // nobody still reads the previous scale/shift
+        for (int j = et; j < BN; j += 128) {
+          s_scale[j] = (p.scale ? __ldg(&p.scale[n0 + j]) : 1.f) * p.wscale;
+          s_shift[j] = p.shift ? __ldg(&p.shift[n0 + j]) : 0.f;
         }
+        epi_bar();
+        last_n0 = n0;
+      }
+      const uint32_t buf = i & 1;
+      mbar_wait(bar_tfull + 8 * buf, (i >> 1) & 1);
+      tc_fence_after();
+      const int img = img0 + ni;
+      const bool ok = img < p.n_img;
+      const size_t pix = ((size_t)(ok ? img : 0) * p.H + (y0 + yy)) * p.W + (x0 + xx);
+      const size_t off = pix * p.cout + n0;
+#pragma unroll 1
+      for (int cb = 0; cb < BN; cb += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * BN + cb, v);
+        if (cb + 32 >= BN) {                     // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        }
+        float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          st4(o + j, make_float4(act_fn(f[j], p.act), act_fn(f[j + 1], p.act), act_fn(f[j + 2], p.act),
-                                 act_fn(f[j + 3], p.act)));
-      } else {
-        __half* ohi = reinterpret_cast<__half*>(p.out) + off + cb;
-        __half* olo = ohi + p.plane;
-        if (p.residual) {
-          const __half* rhi = reinterpret_cast<const __half*>(p.residual) + off + cb;
-          const __half* rlo = rhi + p.plane;
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * s_scale[cb + j] + s_shift[cb + j];
+        if (p.residual && ok) {
+          if (MODE == MODE_TF32) {
+            const float* rs = reinterpret_cast<const float*>(p.residual) + off + cb;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 a = __ldg(reinterpret_cast<const uint4*>(rhi + j));
-            uint4 b = __ldg(reinterpret_cast<const uint4*>(rlo + j));
-            const __half2* ah = reinterpret_cast<const __half2*>(&a);
-            const __half2* bh = reinterpret_cast<const __half2*>(&b);
+            for (int j = 0; j < 32; j += 4) {
+              float4 tt = __ldg(reinterpret_cast<const float4*>(rs + j));
+              f[j] += tt.x; f[j + 1] += tt.y; f[j + 2] += tt.z; f[j + 3] += tt.w;
+            }
+          } else {
+            const __half* rhi = reinterpret_cast<const __half*>(p.residual) + off + cb;
+            const __half* rlo = rhi + p.plane;
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              float2 x = __half22float2(ah[t]), y = __half22float2(bh[t]);
-              f[j + 2 * t] += x.x + y.x;
-              f[j + 2 * t + 1] += x.y + y.y;
+            for (int j = 0; j < 32; j += 8) {
+              uint4 a = __ldg(reinterpret_cast<const uint4*>(rhi + j));
+              uint4 b = __ldg(reinterpret_cast<const uint4*>(rlo + j));
+              const __half2* ah = reinterpret_cast<const __half2*>(&a);
+              const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+              for (int tt = 0; tt < 4; ++tt) {
+                float2 x = __half22float2(ah[tt]), y = __half22float2(bh[tt]);
+                f[j + 2 * tt] += x.x + y.x;
+                f[j + 2 * tt + 1] += x.y + y.y;
+              }
             }
           }
         }
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 hi4, lo4;
-          __half2* hh = reinterpret_cast<__half2*>(&hi4);
-          __half2* ll = reinterpret_cast<__half2*>(&lo4);
+        for (int j = 0; j < 32; ++j) f[j] = act_fn(f[j], p.act);
+
+        if (TMA_STORE) {
+          // stage the 128 x 32-column chunk (swizzled like the output tensor map expects) and let
+          // one thread write it with a bulk tensor store; two staging buffers alternate
+          const uint32_t sbuf = chunk_ctr & 1;
+          if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          epi_bar();                                         // staging buffer `sbuf` is free again
+          uint8_t* dst = stage_out_ptr + sbuf * Cfg::OUT_BUF;
+          if (MODE == MODE_TF32) {
+            // 128-byte rows, SWIZZLE_128B: 16-byte chunk index ^= row & 7
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            float a0 = act_fn(f[j + 2 * t], p.act), a1 = act_fn(f[j + 2 * t + 1], p.act);
-            __half2 h = __floats2half2_rn(a0, a1);
-            float2 hf = __half22float2(h);
-            hh[t] = h;
-            ll[t] = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + r * 128 + (((j >> 2) ^ (r & 7)) << 4)) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+            // 64-byte rows, SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 hi4, lo4;
+              __half2* hh = reinterpret_cast<__half2*>(&hi4);
+              __half2* ll = reinterpret_cast<__half2*>(&lo4);
+#pragma unroll
+              for (int tt = 0; tt < 4; ++tt) {
+                __half2 h = __floats2half2_rn(f[j + 2 * tt], f[j + 2 * tt + 1]);
+                float2 hf = __half22float2(h);
+                hh[tt] = h;
+                ll[tt] = __floats2half2_rn(f[j + 2 * tt] - hf.x, f[j + 2 * tt + 1] - hf.y);
+              }
+              const int sw = ((j >> 3) ^ ((r >> 1) & 3)) << 4;
+              *reinterpret_cast<uint4*>(dst + r * 64 + sw) = hi4;
+              *reinterpret_cast<uint4*>(dst + 128 * 64 + r * 64 + sw) = lo4;
+            }
           }
-          *reinterpret_cast<uint4*>(ohi + j) = hi4;
-          *reinterpret_cast<uint4*>(olo + j) = lo4;
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          epi_bar();
+          if (et == 0) {
+            const uint32_t src = stage_out + sbuf * Cfg::OUT_BUF;
+#pragma unroll
+            for (int pl = 0; pl < Cfg::PLANES; ++pl)
+              tma_store_4d(&maps.o[pl], src + pl * 128 * Cfg::OUT_ROW, n0 + cb, x0, y0, img0);   // OOB images are clipped
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          ++chunk_ctr;
+        } else if (ok) {
+          if (MODE == MODE_TF32) {
+            float* o = reinterpret_cast<float*>(p.out) + off + cb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) st4(o + j, make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]));
+          } else {
+            __half* ohi = reinterpret_cast<__half*>(p.out) + off + cb;
+            __half* olo = ohi + p.plane;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 hi4, lo4;
+              __half2* hh = reinterpret_cast<__half2*>(&hi4);
+              __half2* ll = reinterpret_cast<__half2*>(&lo4);
+#pragma unroll
+              for (int tt = 0; tt < 4; ++tt) {
+                __half2 h = __floats2half2_rn(f[j + 2 * tt], f[j + 2 * tt + 1]);
+                float2 hf = __half22float2(h);
+                hh[tt] = h;
+                ll[tt] = __floats2half2_rn(f[j + 2 * tt] - hf.x, f[j + 2 * tt + 1] - hf.y);
+              }
+              *reinterpret_cast<uint4*>(ohi + j) = hi4;
+              *reinterpret_cast<uint4*>(olo + j) = lo4;
+            }
+          }
         }
       }
     }
+    if (TMA_STORE && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -352,14 +453,16 @@ static EncodeTiledFn encode_fn() {
 }
 
 static int make_map(CUtensorMap* m, bool half, int rank, void* addr, const cuuint64_t* dims, const cuuint32_t* box,
-                    int row_bytes) {
+                    int row_bytes, int spatial_stride = 1) {
   EncodeTiledFn fn = encode_fn();
   OFB_CHECK(fn, "conv_tc: cuTensorMapEncodeTiled is not available from the driver");
   const int es = half ? 2 : 4;
   cuuint64_t strides[4];
   cuuint64_t acc = es;
   for (int i = 0; i < rank - 1; ++i) { acc *= dims[i]; strides[i] = acc; }
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  // a strided conv reads every `spatial_stride`-th pixel: TMA traversal strides on W and H
+  cuuint32_t estr[4] = {1, (cuuint32_t)spatial_stride, (cuuint32_t)spatial_stride, 1};
+  if (rank != 4) estr[1] = estr[2] = 1;
   CUresult r = fn(m, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, addr, dims,
                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -372,36 +475,50 @@ static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 bool conv_tc_supported(const ofb_conv_desc* d) {
   if (d->in_fmt != d->out_fmt) return false;
-  if (d->stride != 1) return false;
+  if (d->stride != 1 && d->stride != 2) return false;
   if (!((d->k == 3 && d->pad == 1) || (d->k == 1 && d->pad == 0))) return false;
+  if (d->stride == 2 && ((d->h | d->w) & 1)) return false;
   if (d->in_fmt == OFB_FMT_SPLIT16 && !d->wgt_split) return false;
   int c1 = d->in1 ? d->c1 : 0;
   if (d->c0 % 32 || c1 % 32 || d->cout % 32) return false;
   if (d->cout > 128 && d->cout % 128) return false;
-  if (!pow2(d->w) || !pow2(d->h) || d->w > 128) return false;
-  int bw = d->w, bh = d->h < 128 / bw ? d->h : 128 / bw;
-  if (d->h % bh) return false;
+  const int ow = d->w / d->stride, oh = d->h / d->stride;
+  if (!pow2(ow) || !pow2(oh) || ow > 128) return false;
+  int bw = ow, bh = oh < 128 / bw ? oh : 128 / bw;
+  if (oh % bh) return false;
   return true;
 }
 
-template <int BN, int MODE, int ROW_BYTES>
-static int launch_tc(const TcMaps& maps, const TcParams& p, dim3 grid, cudaStream_t s) {
-  using Cfg = TcCfg<BN, MODE, ROW_BYTES>;
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE>
+static int launch_tc(const TcMaps& maps, const TcParams& p, cudaStream_t s) {
+  using Cfg = TcCfg<BN, MODE, ROW_BYTES, TMA_STORE>;
   static bool attr = false;
   if (!attr) {
-    OFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MODE, ROW_BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    OFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MODE, ROW_BYTES, TMA_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr = true;
   }
-  conv_tc_kernel<BN, MODE, ROW_BYTES><<<grid, 192, Cfg::SMEM, s>>>(maps, p);
+  int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();      // persistent: one CTA per SM
+  conv_tc_kernel<BN, MODE, ROW_BYTES, TMA_STORE><<<grid, 192, Cfg::SMEM, s>>>(maps, p);
   OFB_LAUNCH_CHECK();
   return 0;
 }
 
 template <int MODE, int ROW_BYTES>
-static int launch_bn(int bn, const TcMaps& maps, const TcParams& p, dim3 grid, cudaStream_t s) {
-  if (bn == 128) return launch_tc<128, MODE, ROW_BYTES>(maps, p, grid, s);
-  if (bn == 64) return launch_tc<64, MODE, ROW_BYTES>(maps, p, grid, s);
-  return launch_tc<32, MODE, ROW_BYTES>(maps, p, grid, s);
+static int launch_bn(int bn, const TcMaps& maps, const TcParams& p, cudaStream_t s) {
+  if (bn == 128) return launch_tc<128, MODE, ROW_BYTES, false>(maps, p, s);
+  if (bn == 64) return launch_tc<64, MODE, ROW_BYTES, true>(maps, p, s);
+  return launch_tc<32, MODE, ROW_BYTES, true>(maps, p, s);
 }
 
 int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
@@ -415,15 +532,20 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
   const int kc = row_bytes / es;
   OFB_CHECK(d->c0 % kc == 0 && c1 % kc == 0, "conv_tc: channel counts (%d,%d) not divisible by %d", d->c0, c1, kc);
   TcParams p{};
-  p.n_img = d->n; p.H = d->h; p.W = d->w; p.c0 = d->c0; p.c1 = c1; p.cout = d->cout; p.k = d->k; p.pad = d->pad;
-  p.BW = d->w; p.BH = d->h < 128 / p.BW ? d->h : 128 / p.BW; p.BNI = 128 / (p.BW * p.BH);
-  p.tiles_x = d->w / p.BW; p.tiles_y = d->h / p.BH;
+  const int ow = d->w / d->stride, oh = d->h / d->stride;
+  p.n_img = d->n; p.H = oh; p.W = ow; p.c0 = d->c0; p.c1 = c1; p.cout = d->cout; p.k = d->k; p.pad = d->pad;
+  p.stride = d->stride;
+  p.BW = ow; p.BH = oh < 128 / p.BW ? oh : 128 / p.BW; p.BNI = 128 / (p.BW * p.BH);
+  p.tiles_x = ow / p.BW; p.tiles_y = oh / p.BH;
   p.scale = d->scale; p.shift = d->shift; p.wscale = split ? d->wgt_unscale : 1.f;
   p.residual = d->residual; p.out = d->out; p.act = d->act;
-  p.plane = (long long)d->n * d->h * d->w * d->cout;
-  const int bn = d->cout >= 128 ? 128 : d->cout;
+  p.plane = (long long)d->n * oh * ow * d->cout;
   const int groups = (d->n + p.BNI - 1) / p.BNI;
-  dim3 grid(groups * p.tiles_x * p.tiles_y, d->cout / bn);
+  // widest N tile that still yields about one CTA per SM (small problems: more, narrower tiles)
+  int bn = d->cout >= 128 ? 128 : d->cout;
+  while (bn > 32 && (long long)groups * p.tiles_x * p.tiles_y * (d->cout / bn) < num_sms()) bn >>= 1;
+  p.tiles_n = d->cout / bn;
+  p.total_tiles = groups * p.tiles_x * p.tiles_y * p.tiles_n;
 
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
@@ -433,10 +555,10 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
     int c = src == 0 ? d->c0 : c1;
     if (!ptr || c == 0) { ptr = d->in0; c = d->c0; }      // unused map: keep it valid
     cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
-    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BNI};
+    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(p.BW * d->stride), (cuuint32_t)(p.BH * d->stride), (cuuint32_t)p.BNI};
     for (int pl = 0; pl < planes; ++pl) {
       char* a = (char*)ptr + (size_t)pl * d->n * d->h * d->w * c * es;
-      if (make_map(&maps.a[src][pl], split, 4, a, dims, box, row_bytes)) return -1;
+      if (make_map(&maps.a[src][pl], split, 4, a, dims, box, row_bytes, d->stride)) return -1;
     }
   }
   {
@@ -447,12 +569,20 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
       if (make_map(&maps.b[pl], split, 2, a, dims, box, row_bytes)) return -1;
     }
   }
-  if (split) {
-    if (row_bytes == 128) return launch_bn<MODE_F16X3, 128>(bn, maps, p, grid, s);
-    return launch_bn<MODE_F16X3, 64>(bn, maps, p, grid, s);
+  if (bn < 128) {      // output tensor maps for the bulk-store epilogue: box = 32 columns x the pixel box
+    cuuint64_t dims[4] = {(cuuint64_t)d->cout, (cuuint64_t)ow, (cuuint64_t)oh, (cuuint64_t)d->n};
+    cuuint32_t box[4] = {32u, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BNI};
+    for (int pl = 0; pl < planes; ++pl) {
+      char* a = (char*)d->out + (size_t)pl * p.plane * es;
+      if (make_map(&maps.o[pl], split, 4, a, dims, box, 32 * es)) return -1;
+    }
   }
-  if (row_bytes == 128) return launch_bn<MODE_TF32, 128>(bn, maps, p, grid, s);
-  return launch_bn<MODE_TF32, 64>(bn, maps, p, grid, s);
+  if (split) {
+    if (row_bytes == 128) return launch_bn<MODE_F16X3, 128>(bn, maps, p, s);
+    return launch_bn<MODE_F16X3, 64>(bn, maps, p, s);
+  }
+  if (row_bytes == 128) return launch_bn<MODE_TF32, 128>(bn, maps, p, s);
+  return launch_bn<MODE_TF32, 64>(bn, maps, p, s);
 }
 
 // ------------------------------------------------------------ split-half conversion

@@ -158,47 +158,49 @@ __global__ void upsample2x_kernel(const void* __restrict__ in, const float* __re
 }
 
 // ---------------------------------------------------------------- point embed
-// 16 threads per pixel, 4 of the 64 output channels each; the 16-wide hidden layer is
-// recomputed per thread (48 FMA) - the kernel is bound by its 256 B/pixel store.
+// 16 threads per pixel: lane g of the group evaluates hidden unit g once, the group exchanges
+// the 16 hidden values by shuffle, then each lane produces 4 of the 64 output channels with the
+// second-layer weights staged k-major in shared memory.  Bound by its 256 B/pixel store.
 template <bool SPLIT>
-__global__ void point_embed_kernel(const float* __restrict__ pts, int N, int cin, int p,
+__global__ void __launch_bounds__(256)
+point_embed_kernel(const float* __restrict__ pts, int N, int cin, int p,
                                    const float* __restrict__ depth, int imgs,
                                    const float* __restrict__ w1, const float* __restrict__ s1,
                                    const float* __restrict__ t1, const float* __restrict__ w2,
                                    const float* __restrict__ s2, const float* __restrict__ t2,
                                    const void* __restrict__ base, void* __restrict__ out) {
+  __shared__ __align__(16) float w2s[16][64];
+  for (int i = threadIdx.x; i < 1024; i += 256) w2s[i & 15][i >> 4] = __ldg(&w2[i]);   // w2 is [co][k]
+  __syncthreads();
   size_t total = (size_t)imgs * p * p * 16;
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= total) return;
+  bool live = i < total;
+  if (!live) i = total - 1;
   int g = (int)(i & 15);
   size_t pix = i >> 4;
   int xy = (int)(pix % (p * p));
   int img = (int)(pix / (p * p));
   int n = img % N;
-  float in[5];
   float dsc = depth ? __ldg(&depth[pix]) : 1.f;
+  float a = 0.f;
   for (int c = 0; c < cin; ++c) {
     float v = __ldg(&pts[((size_t)n * cin + c) * p * p + xy]);
-    in[c] = (depth && c < 3) ? v * dsc : v;
+    if (depth && c < 3) v *= dsc;
+    a += v * __ldg(&w1[g * cin + c]);
   }
-  float hid[16];
+  float hid = fmaxf(a * __ldg(&s1[g]) + __ldg(&t1[g]), 0.f);
+  float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    float a = 0.f;
-    for (int c = 0; c < cin; ++c) a += in[c] * __ldg(&w1[k * cin + c]);
-    hid[k] = fmaxf(a * __ldg(&s1[k]) + __ldg(&t1[k]), 0.f);
+    float hk = __shfl_sync(0xffffffffu, hid, k, 16);
+    float4 w = *reinterpret_cast<const float4*>(&w2s[k][g * 4]);
+    o[0] += hk * w.x; o[1] += hk * w.y; o[2] += hk * w.z; o[3] += hk * w.w;
   }
-  float o[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    int co = g * 4 + j;
-    float a = 0.f;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) a += hid[k] * __ldg(&w2[co * 16 + k]);
-    o[j] = fmaxf(a * __ldg(&s2[co]) + __ldg(&t2[co]), 0.f);
-  }
+  if (!live) return;
+  float4 sc = __ldg(reinterpret_cast<const float4*>(s2 + g * 4)), sh = __ldg(reinterpret_cast<const float4*>(t2 + g * 4));
+  float4 v = make_float4(fmaxf(o[0] * sc.x + sh.x, 0.f), fmaxf(o[1] * sc.y + sh.y, 0.f),
+                         fmaxf(o[2] * sc.z + sh.z, 0.f), fmaxf(o[3] * sc.w + sh.w, 0.f));
   size_t off = pix * 64 + g * 4;
-  float4 v = make_float4(o[0], o[1], o[2], o[3]);
   const size_t plane = (size_t)imgs * p * p * 64;
   if (base) {
     float4 b = act_ld4<SPLIT>(base, off, plane);
@@ -346,14 +348,18 @@ heads_kernel(const void* __restrict__ x, int imgs, int h, int w, const float* __
     swp[c * 9 + tap] = __ldg(&wp[i]);
     swc[c * 9 + tap] = confidence ? __ldg(&wc[i]) : 0.f;
   }
-  for (int i = tid; i < HD_I * HD_I * 32; i += 256) {
-    int c = i & 31, pix = i >> 5;
+  const size_t xplane = (size_t)imgs * h * w * 32;
+  for (int i = tid; i < HD_I * HD_I * 8; i += 256) {     // 4 channels per load
+    int cq = i & 7, pix = i >> 3;
     int yy = pix / HD_I, xx = pix - yy * HD_I;
     int ih = y0 + yy, iw = x0 + xx;
-    float v = 0.f;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ih >= 0 && ih < h && iw >= 0 && iw < w)
-      v = act_ld1<SPLIT>(x, ((size_t)(img * h + ih) * w + iw) * 32 + c, (size_t)imgs * h * w * 32);
-    tile[c * HD_PLANE + pix] = v;
+      v = act_ld4<SPLIT>(x, ((size_t)(img * h + ih) * w + iw) * 32 + cq * 4, xplane);
+    tile[(cq * 4 + 0) * HD_PLANE + pix] = v.x;
+    tile[(cq * 4 + 1) * HD_PLANE + pix] = v.y;
+    tile[(cq * 4 + 2) * HD_PLANE + pix] = v.z;
+    tile[(cq * 4 + 3) * HD_PLANE + pix] = v.w;
   }
   __syncthreads();
   int py = tid / HD_T, px = tid % HD_T;

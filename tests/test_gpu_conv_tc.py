@@ -22,7 +22,7 @@ def rand(*shape, seed=0, scale=1.0):
 
 
 TC_CASES = [
-    # n, hw, c0, c1, cout, k, residual, act
+    # n, hw, c0, c1, cout, k, residual, act [, stride]
     (2, 32, 64, 0, 64, 3, True, 1),       # layer1 block conv
     (3, 16, 128, 0, 128, 3, True, 1),     # layer2
     (5, 8, 256, 0, 256, 3, False, 1),     # layer3 (2 images per tile, ragged last group)
@@ -34,19 +34,24 @@ TC_CASES = [
     (200, 1, 512, 0, 2048, 1, False, 2),  # fc1 + GELU as 1x1
     (144, 1, 2048, 0, 512, 1, True, 0),   # fc2 + residual
     (4, 4, 512, 0, 32, 1, False, 0),      # down1
+    (3, 32, 64, 0, 128, 3, False, 1, 2),  # layer2.0.conv1 (3x3 stride 2 via TMA traversal strides)
+    (3, 32, 64, 0, 128, 1, False, 0, 2),  # layer2.0.downsample (1x1 stride 2)
+    (5, 8, 256, 0, 512, 3, False, 1, 2),  # layer4.0.conv1
+    (5, 8, 256, 0, 512, 1, False, 0, 2),  # layer4.0.downsample
 ]
 
 
 def reference(case, seed=0):
-    n, hw, c0, c1, cout, k, use_res, act = case
+    n, hw, c0, c1, cout, k, use_res, act = case[:8]
+    stride = case[8] if len(case) > 8 else 1
     x0 = rand(n, c0, hw, hw, seed=seed + 1)
     x1 = rand(n, c1, hw, hw, seed=seed + 2) if c1 else None
     w = rand(cout, c0 + c1, k, k, seed=seed + 3, scale=(1.0 / ((c0 + c1) * k * k)) ** 0.5)
     scale = 0.5 + torch.rand(cout, generator=torch.Generator().manual_seed(seed + 4))
     shift = rand(cout, seed=seed + 5, scale=0.1)
-    res = rand(n, cout, hw, hw, seed=seed + 6) if use_res else None
+    res = rand(n, cout, hw // stride, hw // stride, seed=seed + 6) if use_res else None
     x = x0 if x1 is None else torch.cat([x0, x1], 1)
-    y = F.conv2d(x, w, None, 1, k // 2) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    y = F.conv2d(x, w, None, stride, k // 2) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
     if res is not None:
         y = y + res
     y = F.relu(y) if act == 1 else (F.gelu(y) if act == 2 else y)
@@ -55,9 +60,10 @@ def reference(case, seed=0):
 
 def run(case, engine, fmt):
     o = ops()
-    n, hw, c0, c1, cout, k, use_res, act = case
+    n, hw, c0, c1, cout, k, use_res, act = case[:8]
+    stride = case[8] if len(case) > 8 else 1
     x0, x1, w, scale, shift, res, y = reference(case)
-    got = o.conv_fmt(o.nhwc(x0).to(DEV), o.ohwi(w).to(DEV), k, 1, k // 2,
+    got = o.conv_fmt(o.nhwc(x0).to(DEV), o.ohwi(w).to(DEV), k, stride, k // 2,
                      in1=o.nhwc(x1).to(DEV) if c1 else None, scale=scale.to(DEV), shift=shift.to(DEV),
                      residual=o.nhwc(res).to(DEV) if use_res else None, act=act, engine=engine, in_fmt=fmt, out_fmt=fmt)
     torch.cuda.synchronize()
