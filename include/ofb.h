@@ -157,6 +157,10 @@ int ofb_layernorm_f32(const void* x, const float* gamma, const float* beta, int 
 int ofb_attention_f32(const void* q, const void* kv, int B, int N, int heads, int head_dim,
                       void* out, int fmt, void* stream);
 
+/* Same with q, k, v produced by one fused linear: qkv (rows,1536) = [q | k | v] per row. */
+int ofb_attention_qkv_f32(const void* qkv, int B, int N, int heads, int head_dim,
+                          void* out, int fmt, void* stream);
+
 /* Heads: pred / weight_pred 3x3 convs + relu / sigmoid / product,
  * spherical_model_iterative.py:371-374.  x (imgs,h,w,32); w_pred,w_conf (3,3,32);
  * pred_out = relu(pred) * (confidence ? sigmoid(conf) : 1); conf_out = sigmoid(conf)

@@ -73,6 +73,52 @@ __device__ __forceinline__ void act_st4(void* base, size_t idx, size_t plane, fl
 }
 
 
+// 8-channel variants (two float4 / two 16-byte half loads)
+struct float8 { float4 a, b; };
+template <bool SPLIT>
+__device__ __forceinline__ float8 act_ld8(const void* base, size_t idx, size_t plane) {
+  float8 r;
+  if (!SPLIT) {
+    const float* f = reinterpret_cast<const float*>(base) + idx;
+    r.a = __ldg(reinterpret_cast<const float4*>(f));
+    r.b = __ldg(reinterpret_cast<const float4*>(f + 4));
+    return r;
+  }
+  const __half* h = reinterpret_cast<const __half*>(base) + idx;
+  uint4 x = __ldg(reinterpret_cast<const uint4*>(h));
+  uint4 y = __ldg(reinterpret_cast<const uint4*>(h + plane));
+  const __half2* xh = reinterpret_cast<const __half2*>(&x);
+  const __half2* yh = reinterpret_cast<const __half2*>(&y);
+  float2 p0 = __half22float2(xh[0]), p1 = __half22float2(xh[1]), p2 = __half22float2(xh[2]), p3 = __half22float2(xh[3]);
+  float2 q0 = __half22float2(yh[0]), q1 = __half22float2(yh[1]), q2 = __half22float2(yh[2]), q3 = __half22float2(yh[3]);
+  r.a = make_float4(p0.x + q0.x, p0.y + q0.y, p1.x + q1.x, p1.y + q1.y);
+  r.b = make_float4(p2.x + q2.x, p2.y + q2.y, p3.x + q3.x, p3.y + q3.y);
+  return r;
+}
+template <bool SPLIT>
+__device__ __forceinline__ void act_st8(void* base, size_t idx, size_t plane, const float8& v) {
+  if (!SPLIT) {
+    float* f = reinterpret_cast<float*>(base) + idx;
+    st4(f, v.a);
+    st4(f + 4, v.b);
+    return;
+  }
+  __half* h = reinterpret_cast<__half*>(base) + idx;
+  const float in[8] = {v.a.x, v.a.y, v.a.z, v.a.w, v.b.x, v.b.y, v.b.z, v.b.w};
+  uint4 hi4, lo4;
+  __half2* hh = reinterpret_cast<__half2*>(&hi4);
+  __half2* ll = reinterpret_cast<__half2*>(&lo4);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    __half2 x = __floats2half2_rn(in[2 * t], in[2 * t + 1]);
+    float2 xf = __half22float2(x);
+    hh[t] = x;
+    ll[t] = __floats2half2_rn(in[2 * t] - xf.x, in[2 * t + 1] - xf.y);
+  }
+  *reinterpret_cast<uint4*>(h) = hi4;
+  *reinterpret_cast<uint4*>(h + plane) = lo4;
+}
+
 // scalar variants
 template <bool SPLIT>
 __device__ __forceinline__ float act_ld1(const void* base, size_t idx, size_t plane) {

@@ -541,9 +541,10 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
   p.residual = d->residual; p.out = d->out; p.act = d->act;
   p.plane = (long long)d->n * oh * ow * d->cout;
   const int groups = (d->n + p.BNI - 1) / p.BNI;
-  // widest N tile that still yields about one CTA per SM (small problems: more, narrower tiles)
+  // widest N tile unless that leaves most SMs without a tile
   int bn = d->cout >= 128 ? 128 : d->cout;
-  while (bn > 32 && (long long)groups * p.tiles_x * p.tiles_y * (d->cout / bn) < num_sms()) bn >>= 1;
+  // (only for really small problems such as the token linears: narrow tiles re-read the A tile more often)
+  while (bn > 32 && (long long)groups * p.tiles_x * p.tiles_y * (d->cout / bn) < num_sms() / 4) bn >>= 1;
   p.tiles_n = d->cout / bn;
   p.total_tiles = groups * p.tiles_x * p.tiles_y * p.tiles_n;
 

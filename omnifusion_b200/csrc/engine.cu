@@ -52,7 +52,7 @@ struct ConvW {
 struct Mlp { float *w1, *s1, *t1, *w2, *s2, *t2; int cin; };
 struct Block {
   float *n1g, *n1b, *n2g, *n2b;
-  ConvW q, kv, proj, fc1, fc2;
+  ConvW qkv, proj, fc1, fc2;     // qkv = rows of attn.q.weight followed by attn.kv.weight
 };
 struct Act { float* p = nullptr; int n = 0, h = 0, w = 0, c = 0, fmt = 0; };
 
@@ -224,8 +224,20 @@ static int load_all(ofb_handle* h, const TMap& m, bool single) {
     if (pack_vec(h, m, p + ".norm1.weight", &B.n1g, 512) || pack_vec(h, m, p + ".norm1.bias", &B.n1b, 512) ||
         pack_vec(h, m, p + ".norm2.weight", &B.n2g, 512) || pack_vec(h, m, p + ".norm2.bias", &B.n2b, 512))
       return -1;
-    if (linear(h, m, p + ".attn.q", false, &B.q) || linear(h, m, p + ".attn.kv", false, &B.kv) ||
-        linear(h, m, p + ".attn.proj", true, &B.proj) || linear(h, m, p + ".mlp.fc1", true, &B.fc1) ||
+    {  // q and kv projections share their input: one (1536,512) weight, one launch
+      const ofb_tensor_desc *tq = find(m, p + ".attn.q.weight"), *tkv = find(m, p + ".attn.kv.weight");
+      if (!tq || !tkv) return -1;
+      OFB_CHECK(numel(tq) == 512 * 512 && numel(tkv) == 1024 * 512, "load_weights: attention projection shapes");
+      std::vector<float> cat(1536 * 512);
+      memcpy(cat.data(), tq->data, 512 * 512 * sizeof(float));
+      memcpy(cat.data() + 512 * 512, tkv->data, 1024 * 512 * sizeof(float));
+      ofb_tensor_desc fused{};
+      std::string nm = p + ".attn.qkv.weight";
+      fused.name = nm.c_str(); fused.data = cat.data(); fused.ndim = 2; fused.shape[0] = 1536; fused.shape[1] = 512;
+      TMap one; one[nm] = &fused;
+      if (pack_conv(h, one, nm, &B.qkv)) return -1;
+    }
+    if (linear(h, m, p + ".attn.proj", true, &B.proj) || linear(h, m, p + ".mlp.fc1", true, &B.fc1) ||
         linear(h, m, p + ".mlp.fc2", true, &B.fc2))
       return -1;
   }
@@ -279,7 +291,7 @@ static size_t plan_buffers(ofb_handle* h, int imgs, int P, Buffers* b) {
   b->l3t = pl.take(s3); b->l3a = pl.take(s3); b->l3b = pl.take(s3); b->l3d = pl.take(s3); b->layer3 = pl.take(s3);
   b->l4t = pl.take(s4); b->l4a = pl.take(s4); b->l4b = pl.take(s4); b->l4d = pl.take(s4); b->layer4 = pl.take(s4);
   b->down = pl.take(I * 512); b->tok = pl.take(I * 512); b->ln = pl.take(I * 512); b->q = pl.take(I * 512);
-  b->kv = pl.take(I * 1024); b->att = pl.take(I * 512); b->tok2 = pl.take(I * 512); b->fc1 = pl.take(I * 2048);
+  b->kv = pl.take(I * 1536); b->att = pl.take(I * 512); b->tok2 = pl.take(I * 512); b->fc1 = pl.take(I * 2048);
   b->enc = pl.take(I * 512);
   b->up0 = pl.take(I * p16 * p16 * 512); b->d00 = pl.take(I * p16 * p16 * 256); b->d01 = pl.take(I * p16 * p16 * 128);
   b->up1 = pl.take(I * p8 * p8 * 128); b->d10 = pl.take(I * p8 * p8 * 128); b->d11 = pl.take(I * p8 * p8 * 64);
@@ -450,10 +462,9 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
       Block& B = h->blk[i];
       { Prof pr(h, s, "layernorm", 0.0, 4.0*((double)imgs*1024));
       if (ofb_layernorm_f32(x, B.n1g, B.n1b, imgs, 512, 1e-5f, b.ln, F, F, vs)) return -1; }
-      if (run_linear(c, B.q, b.ln, nullptr, OFB_ACT_NONE, b.q)) return -1;
-      if (run_linear(c, B.kv, b.ln, nullptr, OFB_ACT_NONE, b.kv)) return -1;
+      if (run_linear(c, B.qkv, b.ln, nullptr, OFB_ACT_NONE, b.kv)) return -1;     // (imgs,1536) = [q | k | v]
       { Prof pr(h, s, "attention", 0.0, 4.0*((double)imgs*2048));
-      if (ofb_attention_f32(b.q, b.kv, Bc, N, 4, 128, b.att, F, vs)) return -1; }
+      if (ofb_attention_qkv_f32(b.kv, Bc, N, 4, 128, b.att, F, vs)) return -1; }
       if (run_linear(c, B.proj, b.att, x, OFB_ACT_NONE, y)) return -1;          // y = x + proj(att)
       { Prof pr(h, s, "layernorm", 0.0, 4.0*((double)imgs*1024));
       if (ofb_layernorm_f32(y, B.n2g, B.n2b, imgs, 512, 1e-5f, b.ln, F, F, vs)) return -1; }

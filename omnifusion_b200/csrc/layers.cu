@@ -122,13 +122,13 @@ __global__ void maxpool_kernel(const void* __restrict__ in, int n, int h, int w,
 // upsample_bilinear2d: h0*(w0*a + w1*b) + h1*(w0*c + w1*d).
 template <bool SPLIT>
 __global__ void upsample2x_kernel(const void* __restrict__ in, const float* __restrict__ img_bias,
-                                  int n, int h, int w, int c4, void* __restrict__ out) {
+                                  int n, int h, int w, int c8, void* __restrict__ out) {
   int oh_n = h * 2, ow_n = w * 2;
-  size_t total = (size_t)n * oh_n * ow_n * c4;
+  size_t total = (size_t)n * oh_n * ow_n * c8;
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= total) return;
-  int c = (int)(i % c4);
-  size_t r = i / c4;
+  int c = (int)(i % c8);
+  size_t r = i / c8;
   int ow = (int)(r % ow_n); r /= ow_n;
   int oh = (int)(r % oh_n);
   int img = (int)(r / oh_n);
@@ -136,25 +136,26 @@ __global__ void upsample2x_kernel(const void* __restrict__ in, const float* __re
   int y0 = (int)sy, x0 = (int)sx;
   int y1 = y0 + (y0 < h - 1), x1 = x0 + (x0 < w - 1);
   float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
-  const size_t in_plane = (size_t)n * h * w * c4 * 4;
-  const size_t ib = ((size_t)img * h * w * c4 + c) * 4;
-  float4 a = act_ld4<SPLIT>(in, ib + ((size_t)y0 * w + x0) * c4 * 4, in_plane);
-  float4 b = act_ld4<SPLIT>(in, ib + ((size_t)y0 * w + x1) * c4 * 4, in_plane);
-  float4 cc = act_ld4<SPLIT>(in, ib + ((size_t)y1 * w + x0) * c4 * 4, in_plane);
-  float4 d = act_ld4<SPLIT>(in, ib + ((size_t)y1 * w + x1) * c4 * 4, in_plane);
+  const size_t in_plane = (size_t)n * h * w * c8 * 8;
+  const size_t ib = ((size_t)img * h * w * c8 + c) * 8;
+  float8 a = act_ld8<SPLIT>(in, ib + ((size_t)y0 * w + x0) * c8 * 8, in_plane);
+  float8 b = act_ld8<SPLIT>(in, ib + ((size_t)y0 * w + x1) * c8 * 8, in_plane);
+  float8 cc = act_ld8<SPLIT>(in, ib + ((size_t)y1 * w + x0) * c8 * 8, in_plane);
+  float8 d = act_ld8<SPLIT>(in, ib + ((size_t)y1 * w + x1) * c8 * 8, in_plane);
+  float8 bb;
+  bb.a = bb.b = make_float4(0.f, 0.f, 0.f, 0.f);
   if (img_bias) {
-    float4 bb = __ldg(reinterpret_cast<const float4*>(img_bias) + (size_t)img * c4 + c);
-    a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
-    b.x += bb.x; b.y += bb.y; b.z += bb.z; b.w += bb.w;
-    cc.x += bb.x; cc.y += bb.y; cc.z += bb.z; cc.w += bb.w;
-    d.x += bb.x; d.y += bb.y; d.z += bb.z; d.w += bb.w;
+    const float4* bp = reinterpret_cast<const float4*>(img_bias) + ((size_t)img * c8 + c) * 2;
+    bb.a = __ldg(bp);
+    bb.b = __ldg(bp + 1);
   }
-  float4 o;
-  o.x = hy * (hx * a.x + lx * b.x) + ly * (hx * cc.x + lx * d.x);
-  o.y = hy * (hx * a.y + lx * b.y) + ly * (hx * cc.y + lx * d.y);
-  o.z = hy * (hx * a.z + lx * b.z) + ly * (hx * cc.z + lx * d.z);
-  o.w = hy * (hx * a.w + lx * b.w) + ly * (hx * cc.w + lx * d.w);
-  act_st4<SPLIT>(out, i * 4, total * 4, o);
+  // same expression tree as ATen: h0*(w0*a + w1*b) + h1*(w0*c + w1*d), bias added to the sources first
+#define OFB_UP(f) (hy * (hx * (a.f + bb.f) + lx * (b.f + bb.f)) + ly * (hx * (cc.f + bb.f) + lx * (d.f + bb.f)))
+  float8 o;
+  o.a = make_float4(OFB_UP(a.x), OFB_UP(a.y), OFB_UP(a.z), OFB_UP(a.w));
+  o.b = make_float4(OFB_UP(b.x), OFB_UP(b.y), OFB_UP(b.z), OFB_UP(b.w));
+#undef OFB_UP
+  act_st8<SPLIT>(out, i * 8, total * 8, o);
 }
 
 // ---------------------------------------------------------------- point embed
@@ -272,8 +273,8 @@ constexpr int ATT_MAXN = 64, ATT_D = 128, ATT_LD = ATT_D + 1;
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(128)
-attention_kernel(const void* __restrict__ q, const void* __restrict__ kv, int N, int heads,
-                 float scale, void* __restrict__ out, int rows) {
+attention_kernel(const void* __restrict__ q, int q_ld, const void* __restrict__ kv, int kv_ld, int kv_col0,
+                 int N, int heads, float scale, void* __restrict__ out, int rows) {
   extern __shared__ float sm[];
   float* sq = sm;
   float* sk = sq + N * ATT_LD;
@@ -285,9 +286,9 @@ attention_kernel(const void* __restrict__ q, const void* __restrict__ kv, int N,
   for (int i = tid; i < N * ATT_D; i += 128) {
     int r = i / ATT_D, d = i % ATT_D;
     size_t row = (size_t)b * N + r;
-    sq[r * ATT_LD + d] = act_ld1<SPLIT>(q, row * dim + hd * ATT_D + d, (size_t)rows * dim);
-    sk[r * ATT_LD + d] = act_ld1<SPLIT>(kv, row * 2 * dim + hd * ATT_D + d, (size_t)rows * 2 * dim);
-    sv[r * ATT_LD + d] = act_ld1<SPLIT>(kv, row * 2 * dim + dim + hd * ATT_D + d, (size_t)rows * 2 * dim);
+    sq[r * ATT_LD + d] = act_ld1<SPLIT>(q, row * q_ld + hd * ATT_D + d, (size_t)rows * q_ld);
+    sk[r * ATT_LD + d] = act_ld1<SPLIT>(kv, row * kv_ld + kv_col0 + hd * ATT_D + d, (size_t)rows * kv_ld);
+    sv[r * ATT_LD + d] = act_ld1<SPLIT>(kv, row * kv_ld + kv_col0 + dim + hd * ATT_D + d, (size_t)rows * kv_ld);
   }
   __syncthreads();
   for (int i = tid; i < N * N; i += 128) {
@@ -325,28 +326,30 @@ attention_kernel(const void* __restrict__ q, const void* __restrict__ kv, int N,
 
 // ---------------------------------------------------------------------- heads
 // pred / weight_pred 3x3 32->1 convs sharing one read of de_conv4_0
-// (spherical_model_iterative.py:371-374).  CTA = 16x16 pixels; the 18x18x32 halo tile
-// is stored channel-major (odd plane stride: conflict-free for both the transposing
-// store and the per-pixel reads).
-constexpr int HD_T = 16, HD_I = HD_T + 2, HD_PLANE = HD_I * HD_I + 1;
+// (spherical_model_iterative.py:371-374).  CTA = 16x16 pixels; the 18x18x32 halo tile is kept
+// pixel-major with a 36-float pitch: 16-byte loads/stores are bank-conflict free both for the
+// cooperative fill and for the per-pixel reads (pitch 36 -> lane l starts at bank 4l).
+constexpr int HD_T = 16, HD_I = HD_T + 2, HD_PITCH = 36;
+constexpr int HD_SMEM = (HD_I * HD_I * HD_PITCH + 2 * 288) * 4;
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 heads_kernel(const void* __restrict__ x, int imgs, int h, int w, const float* __restrict__ wp,
              float bp, const float* __restrict__ wc, float bc, int confidence,
              float* __restrict__ pred_out, float* __restrict__ conf_out) {
-  __shared__ float tile[32 * HD_PLANE];
-  __shared__ float swp[288], swc[288];
+  extern __shared__ __align__(16) float hsm[];
+  float* tile = hsm;
+  float* swp = hsm + HD_I * HD_I * HD_PITCH;   // [tap][32]
+  float* swc = swp + 288;
   int tiles_w = w / HD_T, tiles_h = h / HD_T;
   int t = blockIdx.x;
   int img = t / (tiles_w * tiles_h);
   int r = t - img * tiles_w * tiles_h;
   int y0 = (r / tiles_w) * HD_T - 1, x0 = (r % tiles_w) * HD_T - 1;
   int tid = threadIdx.x;
-  for (int i = tid; i < 288; i += 256) {   // global (tap, c) -> smem [c][tap]
-    int tap = i / 32, c = i % 32;
-    swp[c * 9 + tap] = __ldg(&wp[i]);
-    swc[c * 9 + tap] = confidence ? __ldg(&wc[i]) : 0.f;
+  for (int i = tid; i < 288; i += 256) {
+    swp[i] = __ldg(&wp[i]);
+    swc[i] = confidence ? __ldg(&wc[i]) : 0.f;
   }
   const size_t xplane = (size_t)imgs * h * w * 32;
   for (int i = tid; i < HD_I * HD_I * 8; i += 256) {     // 4 channels per load
@@ -356,25 +359,27 @@ heads_kernel(const void* __restrict__ x, int imgs, int h, int w, const float* __
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ih >= 0 && ih < h && iw >= 0 && iw < w)
       v = act_ld4<SPLIT>(x, ((size_t)(img * h + ih) * w + iw) * 32 + cq * 4, xplane);
-    tile[(cq * 4 + 0) * HD_PLANE + pix] = v.x;
-    tile[(cq * 4 + 1) * HD_PLANE + pix] = v.y;
-    tile[(cq * 4 + 2) * HD_PLANE + pix] = v.z;
-    tile[(cq * 4 + 3) * HD_PLANE + pix] = v.w;
+    *reinterpret_cast<float4*>(tile + pix * HD_PITCH + cq * 4) = v;
   }
   __syncthreads();
   int py = tid / HD_T, px = tid % HD_T;
   float ap = 0.f, ac = 0.f;
-  for (int c = 0; c < 32; ++c) {
-    const float* tp = tile + c * HD_PLANE + py * HD_I + px;
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+  for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        float v = tp[ky * HD_I + kx];
-        ap += v * swp[c * 9 + ky * 3 + kx];
-        ac += v * swc[c * 9 + ky * 3 + kx];
+    for (int kx = 0; kx < 3; ++kx) {
+      const float* tp = tile + ((py + ky) * HD_I + px + kx) * HD_PITCH;
+      const float* w0 = swp + (ky * 3 + kx) * 32;
+      const float* w1 = swc + (ky * 3 + kx) * 32;
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        float4 v = *reinterpret_cast<const float4*>(tp + c);
+        float4 a = *reinterpret_cast<const float4*>(w0 + c);
+        float4 b = *reinterpret_cast<const float4*>(w1 + c);
+        ap += v.x * a.x + v.y * a.y + v.z * a.z + v.w * a.w;
+        ac += v.x * b.x + v.y * b.y + v.z * b.z + v.w * b.w;
       }
-  }
+    }
   size_t o = (size_t)(img * h + y0 + 1 + py) * w + x0 + 1 + px;
   float pred = fmaxf(ap + bp, 0.f);
   if (confidence) {
@@ -420,10 +425,10 @@ extern "C" int ofb_maxpool3x3s2_f32(const void* in, int n, int h, int w, int c, 
 
 extern "C" int ofb_upsample2x_f32(const void* in, const float* img_bias, int n, int h, int w, int c,
                                   void* out, int fmt, void* stream) {
-  OFB_CHECK(in && out && c % 4 == 0 && OFB_FMT_OK(fmt), "upsample2x: bad arguments");
-  size_t total = (size_t)n * h * 2 * w * 2 * (c / 4);
-  if (fmt) upsample2x_kernel<true><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, img_bias, n, h, w, c / 4, out);
-  else upsample2x_kernel<false><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, img_bias, n, h, w, c / 4, out);
+  OFB_CHECK(in && out && c % 8 == 0 && OFB_FMT_OK(fmt), "upsample2x: bad arguments");
+  size_t total = (size_t)n * h * 2 * w * 2 * (c / 8);
+  if (fmt) upsample2x_kernel<true><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, img_bias, n, h, w, c / 8, out);
+  else upsample2x_kernel<false><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, img_bias, n, h, w, c / 8, out);
   OFB_LAUNCH_CHECK();
   return 0;
 }
@@ -465,8 +470,8 @@ extern "C" int ofb_layernorm_f32(const void* x, const float* gamma, const float*
   return 0;
 }
 
-extern "C" int ofb_attention_f32(const void* q, const void* kv, int B, int N, int heads, int head_dim,
-                                 void* out, int fmt, void* stream) {
+static int attention_launch(const void* q, int q_ld, const void* kv, int kv_ld, int kv_col0, int B, int N, int heads,
+                            int head_dim, void* out, int fmt, void* stream) {
   OFB_CHECK(q && kv && out && OFB_FMT_OK(fmt), "attention: bad arguments");
   OFB_CHECK(head_dim == ATT_D && N <= ATT_MAXN && N > 0, "attention: head_dim must be 128 and N <= 64 (got %d, %d)", head_dim, N);
   int smem = (3 * N * ATT_LD + N * (N + 1)) * 4;
@@ -477,10 +482,21 @@ extern "C" int ofb_attention_f32(const void* q, const void* kv, int B, int N, in
     attr_smem = smem;
   }
   float sc = 1.f / sqrtf((float)head_dim);
-  if (fmt) attention_kernel<true><<<B * heads, 128, smem, (cudaStream_t)stream>>>(q, kv, N, heads, sc, out, B * N);
-  else attention_kernel<false><<<B * heads, 128, smem, (cudaStream_t)stream>>>(q, kv, N, heads, sc, out, B * N);
+  if (fmt) attention_kernel<true><<<B * heads, 128, smem, (cudaStream_t)stream>>>(q, q_ld, kv, kv_ld, kv_col0, N, heads, sc, out, B * N);
+  else attention_kernel<false><<<B * heads, 128, smem, (cudaStream_t)stream>>>(q, q_ld, kv, kv_ld, kv_col0, N, heads, sc, out, B * N);
   OFB_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int ofb_attention_f32(const void* q, const void* kv, int B, int N, int heads, int head_dim,
+                                 void* out, int fmt, void* stream) {
+  return attention_launch(q, heads * head_dim, kv, 2 * heads * head_dim, 0, B, N, heads, head_dim, out, fmt, stream);
+}
+
+extern "C" int ofb_attention_qkv_f32(const void* qkv, int B, int N, int heads, int head_dim, void* out, int fmt,
+                                     void* stream) {
+  int dim = heads * head_dim;
+  return attention_launch(qkv, 3 * dim, qkv, 3 * dim, dim, B, N, heads, head_dim, out, fmt, stream);
 }
 
 extern "C" int ofb_heads_f32(const void* x, int imgs, int h, int w, const float* w_pred, float b_pred,
@@ -489,8 +505,14 @@ extern "C" int ofb_heads_f32(const void* x, int imgs, int h, int w, const float*
   OFB_CHECK(x && w_pred && pred_out && (!confidence || (w_conf && conf_out)) && OFB_FMT_OK(in_fmt), "heads: bad arguments");
   OFB_CHECK(h % HD_T == 0 && w % HD_T == 0, "heads: h,w must be multiples of 16");
   int blocks = imgs * (h / HD_T) * (w / HD_T);
-  if (in_fmt) heads_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, imgs, h, w, w_pred, b_pred, w_conf, b_conf, confidence, pred_out, conf_out);
-  else heads_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, imgs, h, w, w_pred, b_pred, w_conf, b_conf, confidence, pred_out, conf_out);
+  static bool attr = false;
+  if (!attr) {
+    OFB_CUDA(cudaFuncSetAttribute(heads_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HD_SMEM));
+    OFB_CUDA(cudaFuncSetAttribute(heads_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HD_SMEM));
+    attr = true;
+  }
+  if (in_fmt) heads_kernel<true><<<blocks, 256, HD_SMEM, (cudaStream_t)stream>>>(x, imgs, h, w, w_pred, b_pred, w_conf, b_conf, confidence, pred_out, conf_out);
+  else heads_kernel<false><<<blocks, 256, HD_SMEM, (cudaStream_t)stream>>>(x, imgs, h, w, w_pred, b_pred, w_conf, b_conf, confidence, pred_out, conf_out);
   OFB_LAUNCH_CHECK();
   return 0;
 }
