@@ -121,7 +121,8 @@ int ofb_merge_f16(const void* src_planes, size_t n, float* dst, void* stream);
  * weights, biases, tables and the head outputs are always float32. */
 
 /* Stem: Conv3d(3->64, 7x7 s2 p3) + BN + ReLU, spherical_model_iterative.py:322.
- * in (n,h,w,4) (4th channel ignored), wgt (64,7,7,4) OHWI-padded, out (n,h/2,w/2,64). */
+ * in (n,h,w,4) (4th channel ignored), wgt (7,7,4,64) = [kh][kw][cin padded to 4][cout], 16-byte
+ * aligned (fetched with one bulk copy per CTA), out (n,h/2,w/2,64). */
 int ofb_stem_f32(const float* in, int n, int h, int w, const float* wgt,
                  const float* scale, const float* shift, void* out, int out_fmt, void* stream);
 

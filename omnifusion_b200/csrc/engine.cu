@@ -200,7 +200,17 @@ static const int kChan[4] = {64, 128, 256, 512};
 static int load_all(ofb_handle* h, const TMap& m, bool single) {
   // stem: (64,3,7,7,1) -> OHWI with the input channel padded to 4
   ConvW stem;
-  if (pack_conv(h, m, "conv1.weight", &stem, 4)) return -1;
+  {  // (64,3,7,7,1) -> [kh][kw][cin padded to 4][cout]: the layout the stem kernel bulk-copies to smem
+    const ofb_tensor_desc* t = find(m, "conv1.weight");
+    if (!t) return -1;
+    OFB_CHECK(numel(t) == 64 * 3 * 49, "load_weights: conv1.weight must be (64,3,7,7,1)");
+    std::vector<float> p(49 * 4 * 64, 0.f);
+    for (int o = 0; o < 64; ++o)
+      for (int i = 0; i < 3; ++i)
+        for (int k = 0; k < 49; ++k) p[(k * 4 + i) * 64 + o] = t->data[(o * 3 + i) * 49 + k];
+    stem.cout = 64; stem.cin = 4; stem.k = 7;
+    if (dev_upload(h, p, &stem.w)) return -1;
+  }
   if (pack_bn(h, m, "bn1", 64, 1e-5f, &stem.scale, &stem.shift)) return -1;
   h->conv["stem"] = stem;
   for (int l = 0; l < 4; ++l)

@@ -1,14 +1,16 @@
 // Bandwidth-bound network kernels over folded NHWC: stem conv, max-pool, 2x bilinear
 // upsample, point embedding, token packing, LayerNorm, attention core, depth/confidence heads.
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace ofb {
 
 // ----------------------------------------------------------------------- stem
 // Conv 7x7 s2 p3, 3(+1 pad)->64, BN, ReLU (spherical_model_iterative.py:322).
-// CTA: 8x16 output pixels x 64 couts; 128 threads, each 2 pixels (rows r, r+4) x 32 couts.
-// Input halo tile (21x37 float4) and the whole 50 KB filter live in shared memory.
-constexpr int STEM_TH = 8, STEM_TW = 16;
+// CTA: 16x16 output pixels x 64 couts; 128 threads, each 4 pixels (rows r, r+4, r+8, r+12) x 32
+// couts = 128 accumulators, so every weight read from shared memory feeds 4 FMAs per channel.
+// Input halo tile (37x37 float4) and the whole 50 KB filter live in shared memory.
+constexpr int STEM_TH = 16, STEM_TW = 16;
 constexpr int STEM_IH = STEM_TH * 2 + 5, STEM_IW = STEM_TW * 2 + 5;
 constexpr int STEM_SMEM = (49 * 4 * 64 + STEM_IH * STEM_IW * 4) * 4;
 
@@ -28,10 +30,15 @@ stem_kernel(const float* __restrict__ in, int n, int h, int w, const float* __re
   int oh0 = th * STEM_TH, ow0 = tw * STEM_TW;
   int ih0 = oh0 * 2 - 3, iw0 = ow0 * 2 - 3;
   const int tid = threadIdx.x;
-  // weights: global OHWI (64,7,7,4) -> smem [tap][c][co]
-  for (int i = tid; i < 64 * 49 * 4; i += 128) {
-    int co = i / (49 * 4), rem = i - co * 49 * 4;
-    sw[rem * 64 + co] = __ldg(&wgt[i]);
+  // weights (7,7,4,64) arrive with one 50 KB bulk copy issued by thread 0 (TMA engine), overlapping
+  // the cooperative halo-tile fill below
+  __shared__ __align__(8) uint64_t wbar;
+  const uint32_t bar = smem_u32(&wbar);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar, 49 * 4 * 64 * 4);
+    bulk_load(smem_u32(sw), wgt, 49 * 4 * 64 * 4, bar);
   }
   for (int i = tid; i < STEM_IH * STEM_IW; i += 128) {
     int y = i / STEM_IW, x = i - y * STEM_IW;
@@ -42,47 +49,49 @@ stem_kernel(const float* __restrict__ in, int n, int h, int w, const float* __re
     si[i] = v;
   }
   __syncthreads();
+  mbar_wait(bar, 0);
   int half = tid >> 6;                 // cout half: 32 couts
-  int p = tid & 63;                    // pixel pair id
+  int p = tid & 63;                    // pixel quad id
   int pr = p / STEM_TW, pc = p - pr * STEM_TW;   // pr in [0,4)
-  float acc0[32], acc1[32];
+  float acc[4][32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) acc0[j] = acc1[j] = 0.f;
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[q][j] = 0.f;
   for (int kh = 0; kh < 7; ++kh) {
     for (int kw = 0; kw < 7; ++kw) {
-      float4 x0 = si[(pr * 2 + kh) * STEM_IW + pc * 2 + kw];
-      float4 x1 = si[((pr + 4) * 2 + kh) * STEM_IW + pc * 2 + kw];
+      float4 x[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) x[q] = si[((pr + 4 * q) * 2 + kh) * STEM_IW + pc * 2 + kw];
       const float* wp = sw + (kh * 7 + kw) * 4 * 64 + half * 32;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         float4 w0 = *reinterpret_cast<const float4*>(wp + j);
         float4 w1 = *reinterpret_cast<const float4*>(wp + 64 + j);
         float4 w2 = *reinterpret_cast<const float4*>(wp + 128 + j);
-        acc0[j] += x0.x * w0.x + x0.y * w1.x + x0.z * w2.x;
-        acc0[j + 1] += x0.x * w0.y + x0.y * w1.y + x0.z * w2.y;
-        acc0[j + 2] += x0.x * w0.z + x0.y * w1.z + x0.z * w2.z;
-        acc0[j + 3] += x0.x * w0.w + x0.y * w1.w + x0.z * w2.w;
-        acc1[j] += x1.x * w0.x + x1.y * w1.x + x1.z * w2.x;
-        acc1[j + 1] += x1.x * w0.y + x1.y * w1.y + x1.z * w2.y;
-        acc1[j + 2] += x1.x * w0.z + x1.y * w1.z + x1.z * w2.z;
-        acc1[j + 3] += x1.x * w0.w + x1.y * w1.w + x1.z * w2.w;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          acc[q][j] += x[q].x * w0.x + x[q].y * w1.x + x[q].z * w2.x;
+          acc[q][j + 1] += x[q].x * w0.y + x[q].y * w1.y + x[q].z * w2.y;
+          acc[q][j + 2] += x[q].x * w0.z + x[q].y * w1.z + x[q].z * w2.z;
+          acc[q][j + 3] += x[q].x * w0.w + x[q].y * w1.w + x[q].z * w2.w;
+        }
       }
     }
   }
-  const size_t o0 = ((size_t)(img * oh_n + oh0 + pr) * ow_n + ow0 + pc) * 64 + half * 32;
-  const size_t o1 = o0 + (size_t)4 * ow_n * 64;
   const size_t plane = (size_t)n * oh_n * ow_n * 64;
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    float4 s = __ldg(reinterpret_cast<const float4*>(scale + half * 32 + j));
-    float4 b = __ldg(reinterpret_cast<const float4*>(shift + half * 32 + j));
-    float4 v0, v1;
-    v0.x = fmaxf(acc0[j] * s.x + b.x, 0.f); v0.y = fmaxf(acc0[j + 1] * s.y + b.y, 0.f);
-    v0.z = fmaxf(acc0[j + 2] * s.z + b.z, 0.f); v0.w = fmaxf(acc0[j + 3] * s.w + b.w, 0.f);
-    v1.x = fmaxf(acc1[j] * s.x + b.x, 0.f); v1.y = fmaxf(acc1[j + 1] * s.y + b.y, 0.f);
-    v1.z = fmaxf(acc1[j + 2] * s.z + b.z, 0.f); v1.w = fmaxf(acc1[j + 3] * s.w + b.w, 0.f);
-    act_st4<OUT_SPLIT>(out, o0 + j, plane, v0);
-    act_st4<OUT_SPLIT>(out, o1 + j, plane, v1);
+  for (int q = 0; q < 4; ++q) {
+    const size_t o = ((size_t)(img * oh_n + oh0 + pr + 4 * q) * ow_n + ow0 + pc) * 64 + half * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 sc = __ldg(reinterpret_cast<const float4*>(scale + half * 32 + j));
+      float4 b = __ldg(reinterpret_cast<const float4*>(shift + half * 32 + j));
+      float4 v;
+      v.x = fmaxf(acc[q][j] * sc.x + b.x, 0.f); v.y = fmaxf(acc[q][j + 1] * sc.y + b.y, 0.f);
+      v.z = fmaxf(acc[q][j + 2] * sc.z + b.z, 0.f); v.w = fmaxf(acc[q][j + 3] * sc.w + b.w, 0.f);
+      act_st4<OUT_SPLIT>(out, o + j, plane, v);
+    }
   }
 }
 
@@ -283,20 +292,47 @@ attention_kernel(const void* __restrict__ q, int q_ld, const void* __restrict__ 
   int b = blockIdx.x / heads, hd = blockIdx.x % heads;
   int dim = heads * ATT_D;
   int tid = threadIdx.x;
-  for (int i = tid; i < N * ATT_D; i += 128) {
-    int r = i / ATT_D, d = i % ATT_D;
-    size_t row = (size_t)b * N + r;
-    sq[r * ATT_LD + d] = act_ld1<SPLIT>(q, row * q_ld + hd * ATT_D + d, (size_t)rows * q_ld);
-    sk[r * ATT_LD + d] = act_ld1<SPLIT>(kv, row * kv_ld + kv_col0 + hd * ATT_D + d, (size_t)rows * kv_ld);
-    sv[r * ATT_LD + d] = act_ld1<SPLIT>(kv, row * kv_ld + kv_col0 + dim + hd * ATT_D + d, (size_t)rows * kv_ld);
+  // fill: 8 channels per load, four independent loads in flight per thread before the smem stores
+  {
+    const int chunks = N * 16 * 3;                 // (row, 8-channel chunk) x {q,k,v}
+    const size_t qplane = (size_t)rows * q_ld, kvplane = (size_t)rows * kv_ld;
+    for (int i0 = tid; i0 < chunks; i0 += 128 * 4) {
+      float8 v[4];
+      int dst[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        int i = i0 + u * 128;
+        dst[u] = -1;
+        if (i < chunks) {
+          int which = i / (N * 16), rem = i - which * (N * 16);
+          int r = rem >> 4, d = (rem & 15) * 8;
+          size_t row = (size_t)b * N + r;
+          if (which == 0) v[u] = act_ld8<SPLIT>(q, row * q_ld + hd * ATT_D + d, qplane);
+          else v[u] = act_ld8<SPLIT>(kv, row * kv_ld + kv_col0 + (which - 1) * dim + hd * ATT_D + d, kvplane);
+          dst[u] = which * N * ATT_LD + r * ATT_LD + d;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (dst[u] < 0) continue;
+        float* o = sm + dst[u];
+        o[0] = v[u].a.x; o[1] = v[u].a.y; o[2] = v[u].a.z; o[3] = v[u].a.w;
+        o[4] = v[u].b.x; o[5] = v[u].b.y; o[6] = v[u].b.z; o[7] = v[u].b.w;
+      }
+    }
   }
   __syncthreads();
   for (int i = tid; i < N * N; i += 128) {
     int r = i / N, c = i % N;
-    float a = 0.f;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 8
-    for (int d = 0; d < ATT_D; ++d) a += sq[r * ATT_LD + d] * sk[c * ATT_LD + d];
-    sp[r * (N + 1) + c] = a * scale;
+    for (int d = 0; d < ATT_D; d += 4) {
+      a0 += sq[r * ATT_LD + d] * sk[c * ATT_LD + d];
+      a1 += sq[r * ATT_LD + d + 1] * sk[c * ATT_LD + d + 1];
+      a2 += sq[r * ATT_LD + d + 2] * sk[c * ATT_LD + d + 2];
+      a3 += sq[r * ATT_LD + d + 3] * sk[c * ATT_LD + d + 3];
+    }
+    sp[r * (N + 1) + c] = ((a0 + a1) + (a2 + a3)) * scale;
   }
   __syncthreads();
   // softmax: one warp per row
@@ -317,10 +353,16 @@ attention_kernel(const void* __restrict__ q, int q_ld, const void* __restrict__ 
   }
   __syncthreads();
   // out[r][d] = sum_c P[r][c] V[c][d]; thread = d
-  for (int r = 0; r < N; ++r) {
-    float a = 0.f;
-    for (int c = 0; c < N; ++c) a += sp[r * (N + 1) + c] * sv[c * ATT_LD + tid];
-    act_st1<SPLIT>(out, ((size_t)b * N + r) * dim + hd * ATT_D + tid, (size_t)rows * dim, a);
+  for (int r0 = 0; r0 < N; r0 += 4) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < N; ++c) {
+      float vv = sv[c * ATT_LD + tid];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u] += sp[min(r0 + u, N - 1) * (N + 1) + c] * vv;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (r0 + u < N) act_st1<SPLIT>(out, ((size_t)b * N + r0 + u) * dim + hd * ATT_D + tid, (size_t)rows * dim, a[u]);
   }
 }
 
@@ -400,7 +442,7 @@ using namespace ofb;
 extern "C" int ofb_stem_f32(const float* in, int n, int h, int w, const float* wgt, const float* scale,
                             const float* shift, void* out, int out_fmt, void* stream) {
   OFB_CHECK(in && wgt && scale && shift && out && OFB_FMT_OK(out_fmt), "stem: bad arguments");
-  OFB_CHECK(h % (2 * STEM_TH) == 0 && w % (2 * STEM_TW) == 0, "stem: h,w must be multiples of 16,32 (got %d,%d)", h, w);
+  OFB_CHECK(h % (2 * STEM_TH) == 0 && w % (2 * STEM_TW) == 0, "stem: h,w must be multiples of 32 (got %d,%d)", h, w);
   static bool attr = false;
   if (!attr) {
     OFB_CUDA(cudaFuncSetAttribute(stem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM));

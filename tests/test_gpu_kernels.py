@@ -189,7 +189,8 @@ def test_stem_matches_torch_cpu():
     ref = F.relu(F.conv2d(x, wt, None, 2, 3) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
     x4 = torch.cat([x, torch.full((3, 1, 128, 128), 7.0)], 1)        # 4th channel must be ignored
     w4 = torch.cat([wt, torch.zeros(64, 1, 7, 7)], 1)
-    got = o.stem(o.nhwc(x4).to(DEV), o.ohwi(w4).to(DEV), scale.to(DEV), shift.to(DEV))
+    w_khwc_o = w4.permute(2, 3, 1, 0).contiguous()                   # (7,7,4,64)
+    got = o.stem(o.nhwc(x4).to(DEV), w_khwc_o.to(DEV), scale.to(DEV), shift.to(DEV))
     report("stem", o.nchw(got.cpu()), ref, atol=1e-5, rtol=1e-5)
 
 
