@@ -107,12 +107,17 @@ __device__ __forceinline__ float act_fn(float v, int act) {
 // Per-configuration constants.  TMA_STORE: the epilogue stages 32-column chunks in shared
 // memory (swizzled) and writes them with cp.async.bulk.tensor stores (coalesced, asynchronous);
 // used for the narrow-N, HBM-bound layers.  Wide tiles store straight from registers.
-template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE>
+// KHR ("kh reuse", 3x3 stride-1 convs whose tile lies inside one image): one stage holds the
+// activation box with a one-row halo above and below ((BH+2) x BW pixels, loaded once per kw) and
+// the weight slices of all three kh taps; the three kh MMAs read the same box at row offsets
+// 0, BW, 2*BW (multiples of 8 rows, so the swizzle phase is unchanged).  A-operand traffic from
+// L2 drops from 9*BH to 3*(BH+2) image rows per tile - the fix for the L2-bound narrow layers.
+template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR>
 struct TcCfg {
   static constexpr int PLANES = MODE == MODE_F16X3 ? 2 : 1;
   static constexpr int ES = MODE == MODE_F16X3 ? 2 : 4;
-  static constexpr int A_BYTES = 128 * ROW_BYTES;
-  static constexpr int B_BYTES = BN * ROW_BYTES;
+  static constexpr int A_BYTES = (KHR ? 192 : 128) * ROW_BYTES;           // capacity; KHR boxes are <= 192 rows
+  static constexpr int B_BYTES = (KHR ? 3 : 1) * BN * ROW_BYTES;
   static constexpr int STAGE = (A_BYTES + B_BYTES) * PLANES;
   static constexpr int OUT_ROW = 32 * ES;                                  // bytes per staged row (32 columns)
   static constexpr int OUT_BUF = TMA_STORE ? PLANES * 128 * OUT_ROW : 0;   // one staging buffer
@@ -145,10 +150,10 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
 // Persistent kernel: each CTA walks tiles t = blockIdx.x, +gridDim.x, ...; the smem ring and its
 // phases run continuously across tiles, and two TMEM accumulator buffers let the MMA warp start
 // tile i+1 while the epilogue warps drain tile i.
-template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE>
+template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
-  using Cfg = TcCfg<BN, MODE, ROW_BYTES, TMA_STORE>;
+  using Cfg = TcCfg<BN, MODE, ROW_BYTES, TMA_STORE, KHR>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023) & ~1023u;
@@ -166,7 +171,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cin = p.c0 + p.c1;
   const int cchunks = cin / Cfg::KC;
-  const int ksteps = p.k * p.k * cchunks;
+  const int ksteps = (KHR ? 3 : p.k * p.k) * cchunks;
   const int tiles_per_group = p.tiles_x * p.tiles_y;
 
   if (warp == 0 && lane == 0) {
@@ -212,14 +217,24 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           int src = 0;
           if (c >= p.c0) { src = 1; c -= p.c0; }
           const uint32_t full = bars + 8 * st;
-          mbar_expect_tx(full, Cfg::STAGE);
           const uint32_t sa = base + st * Cfg::STAGE;
           const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
+          if (KHR) {
+            // here `tap` is kw; the box carries rows y0-1 .. y0+BH, the weights all three kh
+            mbar_expect_tx(full, (uint32_t)(Cfg::PLANES * ((p.BH + 2) * p.BW * ROW_BYTES + Cfg::B_BYTES)));
 #pragma unroll
-          for (int pl = 0; pl < Cfg::PLANES; ++pl) {
-            tma_load_4d(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, x0 * p.stride + kw - p.pad,
-                        y0 * p.stride + kh - p.pad, img0);
-            tma_load_2d(sb + pl * Cfg::B_BYTES, &maps.b[pl], full, tap * cin + cq * Cfg::KC, n0);
+            for (int pl = 0; pl < Cfg::PLANES; ++pl) {
+              tma_load_4d(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, x0 + tap - 1, y0 - 1, img0);
+              tma_load_4d(sb + pl * Cfg::B_BYTES, &maps.b[pl], full, cq * Cfg::KC, n0, 0, tap);
+            }
+          } else {
+            mbar_expect_tx(full, Cfg::STAGE);
+#pragma unroll
+            for (int pl = 0; pl < Cfg::PLANES; ++pl) {
+              tma_load_4d(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, x0 * p.stride + kw - p.pad,
+                          y0 * p.stride + kh - p.pad, img0);
+              tma_load_2d(sb + pl * Cfg::B_BYTES, &maps.b[pl], full, tap * cin + cq * Cfg::KC, n0);
+            }
           }
         }
       }
@@ -244,18 +259,24 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           tc_fence_after();
           const uint32_t sa = base + st * Cfg::STAGE;
           const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
-          const uint64_t a_hi = umma_desc<ROW_BYTES>(sa), b_hi = umma_desc<ROW_BYTES>(sb);
-          if (MODE == MODE_TF32) {
 #pragma unroll
-            for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk)
-              tc_mma<MODE>(acc, a_hi + 2 * kk, b_hi + 2 * kk, idesc, (ks | kk) != 0);
-          } else {
-            const uint64_t a_lo = umma_desc<ROW_BYTES>(sa + Cfg::A_BYTES), b_lo = umma_desc<ROW_BYTES>(sb + Cfg::B_BYTES);
+          for (int kh = 0; kh < (KHR ? 3 : 1); ++kh) {
+            // KHR: tap kh reads the halo box kh image rows further down, and its own weight slice
+            const uint32_t ao = KHR ? (uint32_t)(kh * p.BW * ROW_BYTES) : 0u, bo = (uint32_t)(kh * BN * ROW_BYTES);
+            const uint64_t a_hi = umma_desc<ROW_BYTES>(sa + ao), b_hi = umma_desc<ROW_BYTES>(sb + bo);
+            if (MODE == MODE_TF32) {
 #pragma unroll
-            for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk) {
-              tc_mma<MODE>(acc, a_hi + 2 * kk, b_hi + 2 * kk, idesc, (ks | kk) != 0);
-              tc_mma<MODE>(acc, a_lo + 2 * kk, b_hi + 2 * kk, idesc, 1);
-              tc_mma<MODE>(acc, a_hi + 2 * kk, b_lo + 2 * kk, idesc, 1);
+              for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk)
+                tc_mma<MODE>(acc, a_hi + 2 * kk, b_hi + 2 * kk, idesc, (ks | kh | kk) != 0);
+            } else {
+              const uint64_t a_lo = umma_desc<ROW_BYTES>(sa + Cfg::A_BYTES + ao);
+              const uint64_t b_lo = umma_desc<ROW_BYTES>(sb + Cfg::B_BYTES + bo);
+#pragma unroll
+              for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk) {
+                tc_mma<MODE>(acc, a_hi + 2 * kk, b_hi + 2 * kk, idesc, (ks | kh | kk) != 0);
+                tc_mma<MODE>(acc, a_lo + 2 * kk, b_hi + 2 * kk, idesc, 1);
+                tc_mma<MODE>(acc, a_hi + 2 * kk, b_lo + 2 * kk, idesc, 1);
+              }
             }
           }
           tc_commit(bars + 8 * (Cfg::NST + st));       // frees this smem stage when the MMAs retire
@@ -429,13 +450,13 @@ static EncodeTiledFn encode_fn() {
 }
 
 static int make_map(CUtensorMap* m, bool half, int rank, void* addr, const cuuint64_t* dims, const cuuint32_t* box,
-                    int row_bytes, int spatial_stride = 1) {
+                    int row_bytes, int spatial_stride = 1, const cuuint64_t* byte_strides = nullptr) {
   EncodeTiledFn fn = encode_fn();
   OFB_CHECK(fn, "conv_tc: cuTensorMapEncodeTiled is not available from the driver");
   const int es = half ? 2 : 4;
   cuuint64_t strides[4];
   cuuint64_t acc = es;
-  for (int i = 0; i < rank - 1; ++i) { acc *= dims[i]; strides[i] = acc; }
+  for (int i = 0; i < rank - 1; ++i) { acc *= dims[i]; strides[i] = byte_strides ? byte_strides[i] : acc; }
   // a strided conv reads every `spatial_stride`-th pixel: TMA traversal strides on W and H
   cuuint32_t estr[4] = {1, (cuuint32_t)spatial_stride, (cuuint32_t)spatial_stride, 1};
   if (rank != 4) estr[1] = estr[2] = 1;
@@ -476,25 +497,29 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE>
+template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR>
 static int launch_tc(const TcMaps& maps, const TcParams& p, cudaStream_t s) {
-  using Cfg = TcCfg<BN, MODE, ROW_BYTES, TMA_STORE>;
+  using Cfg = TcCfg<BN, MODE, ROW_BYTES, TMA_STORE, KHR>;
   static bool attr = false;
   if (!attr) {
-    OFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MODE, ROW_BYTES, TMA_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    OFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MODE, ROW_BYTES, TMA_STORE, KHR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr = true;
   }
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();      // persistent: one CTA per SM
-  conv_tc_kernel<BN, MODE, ROW_BYTES, TMA_STORE><<<grid, 192, Cfg::SMEM, s>>>(maps, p);
+  conv_tc_kernel<BN, MODE, ROW_BYTES, TMA_STORE, KHR><<<grid, 192, Cfg::SMEM, s>>>(maps, p);
   OFB_LAUNCH_CHECK();
   return 0;
 }
 
 template <int MODE, int ROW_BYTES>
-static int launch_bn(int bn, const TcMaps& maps, const TcParams& p, cudaStream_t s) {
-  if (bn == 128) return launch_tc<128, MODE, ROW_BYTES, false>(maps, p, s);
-  if (bn == 64) return launch_tc<64, MODE, ROW_BYTES, true>(maps, p, s);
-  return launch_tc<32, MODE, ROW_BYTES, true>(maps, p, s);
+static int launch_bn(int bn, bool khr, const TcMaps& maps, const TcParams& p, cudaStream_t s) {
+  if (bn == 128) return launch_tc<128, MODE, ROW_BYTES, false, false>(maps, p, s);
+  if (MODE == MODE_F16X3 && khr) {
+    if (bn == 64) return launch_tc<64, MODE_F16X3, ROW_BYTES, true, true>(maps, p, s);
+    return launch_tc<32, MODE_F16X3, ROW_BYTES, true, true>(maps, p, s);
+  }
+  if (bn == 64) return launch_tc<64, MODE, ROW_BYTES, true, false>(maps, p, s);
+  return launch_tc<32, MODE, ROW_BYTES, true, false>(maps, p, s);
 }
 
 int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
@@ -521,8 +546,18 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
   int bn = d->cout >= 128 ? 128 : d->cout;
   // (only for really small problems such as the token linears: narrow tiles re-read the A tile more often)
   while (bn > 32 && (long long)groups * p.tiles_x * p.tiles_y * (d->cout / bn) < num_sms() / 4) bn >>= 1;
+  // kh-reuse tiling for the narrow (L2-bound) 3x3 layers: 32x4 / 16x8 pixel tiles inside one image
+  // (decided from the layer shape only, never from the batch size, so results stay batch-invariant:
+  // kh-reuse accumulates the taps in a different order)
+  const bool khr = split && d->k == 3 && d->stride == 1 && d->cout <= 64 && ow >= 16 && oh >= 8;
+  int groups_k = groups;
+  if (khr) {
+    p.BW = ow < 32 ? ow : 32; p.BH = 128 / p.BW; p.BNI = 1;
+    p.tiles_x = ow / p.BW; p.tiles_y = oh / p.BH;
+    groups_k = d->n;
+  }
   p.tiles_n = d->cout / bn;
-  p.total_tiles = groups * p.tiles_x * p.tiles_y * p.tiles_n;
+  p.total_tiles = groups_k * p.tiles_x * p.tiles_y * p.tiles_n;
 
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
@@ -532,13 +567,22 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
     int c = src == 0 ? d->c0 : c1;
     if (!ptr || c == 0) { ptr = d->in0; c = d->c0; }      // unused map: keep it valid
     cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
-    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(p.BW * d->stride), (cuuint32_t)(p.BH * d->stride), (cuuint32_t)p.BNI};
+    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(p.BW * d->stride), (cuuint32_t)((khr ? p.BH + 2 : p.BH) * d->stride), (cuuint32_t)p.BNI};
     for (int pl = 0; pl < planes; ++pl) {
       char* a = (char*)ptr + (size_t)pl * d->n * d->h * d->w * c * es;
       if (make_map(&maps.a[src][pl], split, 4, a, dims, box, row_bytes, d->stride)) return -1;
     }
   }
-  {
+  if (khr) {
+    // weights (cout, kh, kw, cin) seen as dims {cin, cout, kh, kw}: one box = {kc, bn, all 3 kh, one kw}
+    cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)d->cout, 3, 3};
+    cuuint64_t bstr[3] = {(cuuint64_t)9 * cin * es, (cuuint64_t)3 * cin * es, (cuuint64_t)cin * es};
+    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)bn, 3u, 1u};
+    for (int pl = 0; pl < planes; ++pl) {
+      char* a = (char*)d->wgt_split + (size_t)pl * d->cout * 9 * cin * 2;
+      if (make_map(&maps.b[pl], split, 4, a, dims, box, row_bytes, 1, bstr)) return -1;
+    }
+  } else {
     cuuint64_t dims[2] = {(cuuint64_t)d->k * d->k * cin, (cuuint64_t)d->cout};
     cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)bn};
     for (int pl = 0; pl < planes; ++pl) {
@@ -555,11 +599,11 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
     }
   }
   if (split) {
-    if (row_bytes == 128) return launch_bn<MODE_F16X3, 128>(bn, maps, p, s);
-    return launch_bn<MODE_F16X3, 64>(bn, maps, p, s);
+    if (row_bytes == 128) return launch_bn<MODE_F16X3, 128>(bn, khr, maps, p, s);
+    return launch_bn<MODE_F16X3, 64>(bn, khr, maps, p, s);
   }
-  if (row_bytes == 128) return launch_bn<MODE_TF32, 128>(bn, maps, p, s);
-  return launch_bn<MODE_TF32, 64>(bn, maps, p, s);
+  if (row_bytes == 128) return launch_bn<MODE_TF32, 128>(bn, false, maps, p, s);
+  return launch_bn<MODE_TF32, 64>(bn, false, maps, p, s);
 }
 
 // ------------------------------------------------------------ split-half conversion

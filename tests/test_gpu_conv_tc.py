@@ -38,6 +38,8 @@ TC_CASES = [
     (3, 32, 64, 0, 128, 1, False, 0, 2),  # layer2.0.downsample (1x1 stride 2)
     (5, 8, 256, 0, 512, 3, False, 1, 2),  # layer4.0.conv1
     (5, 8, 256, 0, 512, 1, False, 0, 2),  # layer4.0.downsample
+    (3, 16, 128, 128, 64, 3, False, 1),   # de_conv1_1 (kh-reuse tiling, 16x8 pixel tiles)
+    (2, 32, 64, 64, 64, 3, True, 1),      # de_conv2_1-like with residual (kh-reuse, 32x4 tiles)
 ]
 
 
