@@ -40,13 +40,21 @@ stem_kernel(const float* __restrict__ in, int n, int h, int w, const float* __re
     mbar_expect_tx(bar, 49 * 4 * 64 * 4);
     bulk_load(smem_u32(sw), wgt, 49 * 4 * 64 * 4, bar);
   }
-  for (int i = tid; i < STEM_IH * STEM_IW; i += 128) {
-    int y = i / STEM_IW, x = i - y * STEM_IW;
-    int ih = ih0 + y, iw = iw0 + x;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ih >= 0 && ih < h && iw >= 0 && iw < w)
-      v = __ldg(reinterpret_cast<const float4*>(in + ((size_t)(img * h + ih) * w + iw) * 4));
-    si[i] = v;
+  {  // halo tile: all of a thread's loads are issued before the first shared-memory store
+    constexpr int PER = (STEM_IH * STEM_IW + 127) / 128;
+    float4 v[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      int i = tid + u * 128;
+      int y = i / STEM_IW, x = i - y * STEM_IW;
+      int ih = ih0 + y, iw = iw0 + x;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < STEM_IH * STEM_IW && ih >= 0 && ih < h && iw >= 0 && iw < w)
+        v[u] = __ldg(reinterpret_cast<const float4*>(in + ((size_t)(img * h + ih) * w + iw) * 4));
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u)
+      if (tid + u * 128 < STEM_IH * STEM_IW) si[tid + u * 128] = v[u];
   }
   __syncthreads();
   mbar_wait(bar, 0);
@@ -372,7 +380,11 @@ attention_kernel(const void* __restrict__ q, int q_ld, const void* __restrict__ 
 // pixel-major with a 36-float pitch: 16-byte loads/stores are bank-conflict free both for the
 // cooperative fill and for the per-pixel reads (pitch 36 -> lane l starts at bank 4l).
 constexpr int HD_T = 16, HD_I = HD_T + 2, HD_PITCH = 36;
-constexpr int HD_SMEM = (HD_I * HD_I * HD_PITCH + 2 * 288) * 4;
+constexpr int HD_SMEM = HD_I * HD_I * HD_PITCH * 4;
+// Both 3x3x32 filters live in constant memory: every lane of a warp needs the same weight at
+// the same time, so the FFMAs take it as a constant-bank operand and no shared-memory bandwidth
+// is spent on weights (the kernel was shared-memory bound with the filters in smem).
+__constant__ float c_heads_w[2][288];   // [pred | conf][tap][32]
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(256)
@@ -381,27 +393,31 @@ heads_kernel(const void* __restrict__ x, int imgs, int h, int w, const float* __
              float* __restrict__ pred_out, float* __restrict__ conf_out) {
   extern __shared__ __align__(16) float hsm[];
   float* tile = hsm;
-  float* swp = hsm + HD_I * HD_I * HD_PITCH;   // [tap][32]
-  float* swc = swp + 288;
   int tiles_w = w / HD_T, tiles_h = h / HD_T;
   int t = blockIdx.x;
   int img = t / (tiles_w * tiles_h);
   int r = t - img * tiles_w * tiles_h;
   int y0 = (r / tiles_w) * HD_T - 1, x0 = (r % tiles_w) * HD_T - 1;
   int tid = threadIdx.x;
-  for (int i = tid; i < 288; i += 256) {
-    swp[i] = __ldg(&wp[i]);
-    swc[i] = confidence ? __ldg(&wc[i]) : 0.f;
-  }
   const size_t xplane = (size_t)imgs * h * w * 32;
-  for (int i = tid; i < HD_I * HD_I * 8; i += 256) {     // 4 channels per load
-    int cq = i & 7, pix = i >> 3;
-    int yy = pix / HD_I, xx = pix - yy * HD_I;
-    int ih = y0 + yy, iw = x0 + xx;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ih >= 0 && ih < h && iw >= 0 && iw < w)
-      v = act_ld4<SPLIT>(x, ((size_t)(img * h + ih) * w + iw) * 32 + cq * 4, xplane);
-    *reinterpret_cast<float4*>(tile + pix * HD_PITCH + cq * 4) = v;
+  {  // halo tile, 4 channels per load; all loads in flight before the first shared-memory store
+    constexpr int TOTAL = HD_I * HD_I * 8, PER = (TOTAL + 255) / 256;
+    float4 v[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      int i = tid + u * 256;
+      int cq = i & 7, pix = i >> 3;
+      int yy = pix / HD_I, xx = pix - yy * HD_I;
+      int ih = y0 + yy, iw = x0 + xx;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < TOTAL && ih >= 0 && ih < h && iw >= 0 && iw < w)
+        v[u] = act_ld4<SPLIT>(x, ((size_t)(img * h + ih) * w + iw) * 32 + cq * 4, xplane);
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      int i = tid + u * 256;
+      if (i < TOTAL) *reinterpret_cast<float4*>(tile + (i >> 3) * HD_PITCH + (i & 7) * 4) = v[u];
+    }
   }
   __syncthreads();
   int py = tid / HD_T, px = tid % HD_T;
@@ -411,15 +427,14 @@ heads_kernel(const void* __restrict__ x, int imgs, int h, int w, const float* __
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
       const float* tp = tile + ((py + ky) * HD_I + px + kx) * HD_PITCH;
-      const float* w0 = swp + (ky * 3 + kx) * 32;
-      const float* w1 = swc + (ky * 3 + kx) * 32;
+      const int wo = (ky * 3 + kx) * 32;
 #pragma unroll
       for (int c = 0; c < 32; c += 4) {
         float4 v = *reinterpret_cast<const float4*>(tp + c);
-        float4 a = *reinterpret_cast<const float4*>(w0 + c);
-        float4 b = *reinterpret_cast<const float4*>(w1 + c);
-        ap += v.x * a.x + v.y * a.y + v.z * a.z + v.w * a.w;
-        ac += v.x * b.x + v.y * b.y + v.z * b.z + v.w * b.w;
+        ap += v.x * c_heads_w[0][wo + c] + v.y * c_heads_w[0][wo + c + 1] + v.z * c_heads_w[0][wo + c + 2] +
+              v.w * c_heads_w[0][wo + c + 3];
+        ac += v.x * c_heads_w[1][wo + c] + v.y * c_heads_w[1][wo + c + 1] + v.z * c_heads_w[1][wo + c + 2] +
+              v.w * c_heads_w[1][wo + c + 3];
       }
     }
   size_t o = (size_t)(img * h + y0 + 1 + py) * w + x0 + 1 + px;
@@ -547,6 +562,10 @@ extern "C" int ofb_heads_f32(const void* x, int imgs, int h, int w, const float*
   OFB_CHECK(x && w_pred && pred_out && (!confidence || (w_conf && conf_out)) && OFB_FMT_OK(in_fmt), "heads: bad arguments");
   OFB_CHECK(h % HD_T == 0 && w % HD_T == 0, "heads: h,w must be multiples of 16");
   int blocks = imgs * (h / HD_T) * (w / HD_T);
+  // filters -> constant memory (stream-ordered device-to-device copies, 2.3 KB)
+  OFB_CUDA(cudaMemcpyToSymbolAsync(c_heads_w, w_pred, 288 * sizeof(float), 0, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  if (confidence)
+    OFB_CUDA(cudaMemcpyToSymbolAsync(c_heads_w, w_conf, 288 * sizeof(float), 288 * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   static bool attr = false;
   if (!attr) {
     OFB_CUDA(cudaFuncSetAttribute(heads_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HD_SMEM));
