@@ -42,8 +42,11 @@ int ofb_set_device(int device);
 /* Layout selector for patch tensors. */
 enum {
   OFB_LAYOUT_REF = 0,    /* reference layout (B,C,Ph,Pw,N), N innermost            */
-  OFB_LAYOUT_FOLDED = 1  /* folded NHWC (B*N,Ph,Pw,Cpad), Cpad = C rounded up to 4
+  OFB_LAYOUT_FOLDED = 1, /* folded NHWC (B*N,Ph,Pw,Cpad), Cpad = C rounded up to 4
                             when C == 3, else C                                      */
+  OFB_LAYOUT_STEM16 = 2  /* equi2pers only, C == 3: split-half planes of (B*N,Ph,Pw+8,4), rows
+                            padded by 4 pixels on each side (pad left untouched: the caller
+                            zeroes the buffer once) - the input format of ofb_stem_tc_f16  */
 };
 
 /* equi2pers sampling: equi_pers/equi2pers_v3.py:106-113 (F.grid_sample bilinear /
@@ -125,6 +128,14 @@ int ofb_merge_f16(const void* src_planes, size_t n, float* dst, void* stream);
  * aligned (fetched with one bulk copy per CTA), out (n,h/2,w/2,64). */
 int ofb_stem_f32(const float* in, int n, int h, int w, const float* wgt,
                  const float* scale, const float* shift, void* out, int out_fmt, void* stream);
+
+/* The same stem on the tcgen05 engine.  patches: split-half planes of (n,h,w+8,4) - 4 channels per
+ * pixel (4th = 0), every row padded with 4 zero pixels left and right (written by
+ * ofb_equi2pers_f32 with OFB_LAYOUT_STEM16; the pad must be zero).  wgt_split: split-half planes
+ * of (64,7,8,4) = [cout][kh][kw' = kw+1 (kw' = 0 is zero)][cin padded to 4] times 2^e made by
+ * ofb_split_f16, wgt_unscale = 2^-e.  out: split-half (n,h/2,w/2,64). */
+int ofb_stem_tc_f16(const void* patches, int n, int h, int w, const void* wgt_split, float wgt_unscale,
+                    const float* scale, const float* shift, void* out, void* stream);
 
 /* F.max_pool3d((3,3,1), s(2,2,1), p(1,1,0)), spherical_model_iterative.py:323. */
 int ofb_maxpool3x3s2_f32(const void* in, int n, int h, int w, int c, void* out, int fmt, void* stream);

@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libofb.so")
 
-LAYOUT_REF, LAYOUT_FOLDED = 0, 1
+LAYOUT_REF, LAYOUT_FOLDED, LAYOUT_STEM16 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
 FMT_F32, FMT_SPLIT16 = 0, 1
@@ -53,6 +53,7 @@ _SIGNATURES = {
     "ofb_split_f16": (_I, [_P, C.c_size_t, C.c_float, _P, _P]),
     "ofb_merge_f16": (_I, [_P, C.c_size_t, _P, _P]),
     "ofb_stem_f32": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
+    "ofb_stem_tc_f16": (_I, [_P, _I, _I, _I, _P, C.c_float, _P, _P, _P, _P]),
     "ofb_maxpool3x3s2_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _P]),
     "ofb_upsample2x_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "ofb_point_embed_f32": (_I, [_P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),

@@ -26,6 +26,8 @@ enum { MODE_TF32 = 0, MODE_F16X3 = 1 };
 
 struct TcParams {
   int n_img, H, W, c0, c1, cout, k, pad, stride;   // H, W: output dims
+  // tap -> TMA coordinates: x = x0*sx + kw - padx, y = y0*sy + kh - pady with kh = tap / kdiv, kw = tap % kdiv
+  int taps, kdiv, sx, sy, padx, pady;
   int BW, BH, BNI, tiles_x, tiles_y;
   const float* scale; const float* shift; float wscale;
   const void* residual; void* out;
@@ -171,7 +173,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cin = p.c0 + p.c1;
   const int cchunks = cin / Cfg::KC;
-  const int ksteps = (KHR ? 3 : p.k * p.k) * cchunks;
+  const int ksteps = (KHR ? 3 : p.taps) * cchunks;
   const int tiles_per_group = p.tiles_x * p.tiles_y;
 
   if (warp == 0 && lane == 0) {
@@ -212,7 +214,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           const uint32_t ph = (it / Cfg::NST) & 1;
           mbar_wait(bars + 8 * (Cfg::NST + st), ph ^ 1);
           const int tap = ks / cchunks, cq = ks - tap * cchunks;
-          const int kh = tap / p.k, kw = tap - kh * p.k;
+          const int kh = tap / p.kdiv, kw = tap - kh * p.kdiv;
           int c = cq * Cfg::KC;
           int src = 0;
           if (c >= p.c0) { src = 1; c -= p.c0; }
@@ -231,8 +233,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             mbar_expect_tx(full, Cfg::STAGE);
 #pragma unroll
             for (int pl = 0; pl < Cfg::PLANES; ++pl) {
-              tma_load_4d(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, x0 * p.stride + kw - p.pad,
-                          y0 * p.stride + kh - p.pad, img0);
+              tma_load_4d(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, x0 * p.sx + kw - p.padx,
+                          y0 * p.sy + kh - p.pady, img0);
               tma_load_2d(sb + pl * Cfg::B_BYTES, &maps.b[pl], full, tap * cin + cq * Cfg::KC, n0);
             }
           }
@@ -450,7 +452,8 @@ static EncodeTiledFn encode_fn() {
 }
 
 static int make_map(CUtensorMap* m, bool half, int rank, void* addr, const cuuint64_t* dims, const cuuint32_t* box,
-                    int row_bytes, int spatial_stride = 1, const cuuint64_t* byte_strides = nullptr) {
+                    int row_bytes, int spatial_stride = 1, const cuuint64_t* byte_strides = nullptr,
+                    const cuuint32_t* elem_strides = nullptr) {
   EncodeTiledFn fn = encode_fn();
   OFB_CHECK(fn, "conv_tc: cuTensorMapEncodeTiled is not available from the driver");
   const int es = half ? 2 : 4;
@@ -460,6 +463,7 @@ static int make_map(CUtensorMap* m, bool half, int rank, void* addr, const cuuin
   // a strided conv reads every `spatial_stride`-th pixel: TMA traversal strides on W and H
   cuuint32_t estr[4] = {1, (cuuint32_t)spatial_stride, (cuuint32_t)spatial_stride, 1};
   if (rank != 4) estr[1] = estr[2] = 1;
+  if (elem_strides) for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
   CUresult r = fn(m, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, addr, dims,
                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -536,6 +540,7 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
   const int ow = d->w / d->stride, oh = d->h / d->stride;
   p.n_img = d->n; p.H = oh; p.W = ow; p.c0 = d->c0; p.c1 = c1; p.cout = d->cout; p.k = d->k; p.pad = d->pad;
   p.stride = d->stride;
+  p.taps = d->k * d->k; p.kdiv = d->k; p.sx = p.sy = d->stride; p.padx = p.pady = d->pad;
   p.BW = ow; p.BH = oh < 128 / p.BW ? oh : 128 / p.BW; p.BNI = 128 / (p.BW * p.BH);
   p.tiles_x = ow / p.BW; p.tiles_y = oh / p.BH;
   p.scale = d->scale; p.shift = d->shift; p.wscale = split ? d->wgt_unscale : 1.f;
@@ -604,6 +609,49 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
   }
   if (row_bytes == 128) return launch_bn<MODE_TF32, 128>(bn, false, maps, p, s);
   return launch_bn<MODE_TF32, 64>(bn, false, maps, p, s);
+}
+
+// ------------------------------------------------------------------ stem on tensor cores
+// Conv 7x7 s2 p3 3->64 as an implicit GEMM with K = 7 (kh) x 32: the input patches are stored
+// split-half, 4 channels per pixel, each row padded by 4 zero pixels on both sides.  For output
+// pixel (oy,ox) and tap row kh the 8 input pixels 2ox-4 .. 2ox+3 of row 2oy-3+kh are 32
+// contiguous halves, so the A operand is a tensor map whose innermost dimension is that 64-byte
+// window and whose second dimension (the window index ox) has a 16-byte stride: overlapping
+// windows read straight out of the image by TMA, no im2col buffer.  kw = -4 carries a zero weight.
+int stem_tc(const void* patches, int n, int h, int w, const void* wgt_split, float wgt_unscale, const float* scale,
+            const float* shift, void* out, cudaStream_t s) {
+  OFB_CHECK(patches && wgt_split && scale && shift && out, "stem_tc: null pointer");
+  OFB_CHECK(h % 4 == 0 && w % 2 == 0 && w / 2 <= 128 && pow2(w / 2) && pow2(h / 2) && 128 % (w / 2) == 0,
+            "stem_tc: unsupported patch size %dx%d", h, w);
+  const int ow = w / 2, oh = h / 2, pitch = w + 8;           // pixels per padded row
+  TcParams p{};
+  p.n_img = n; p.H = oh; p.W = ow; p.c0 = 32; p.c1 = 0; p.cout = 64; p.k = 7; p.pad = 3; p.stride = 2;
+  p.taps = 7; p.kdiv = 1; p.sx = 1; p.sy = 2; p.padx = 0; p.pady = 3;
+  p.BW = ow; p.BH = 128 / ow; p.BNI = 1;
+  OFB_CHECK(oh % p.BH == 0, "stem_tc: unsupported patch size %dx%d", h, w);
+  p.tiles_x = 1; p.tiles_y = oh / p.BH;
+  p.scale = scale; p.shift = shift; p.wscale = wgt_unscale; p.residual = nullptr; p.out = out; p.act = OFB_ACT_RELU;
+  p.plane = (long long)n * oh * ow * 64;
+  p.tiles_n = 1; p.total_tiles = n * p.tiles_y;
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const size_t in_plane = (size_t)n * h * pitch * 4;         // halves per plane
+  for (int pl = 0; pl < 2; ++pl) {
+    cuuint64_t dims[4] = {32, (cuuint64_t)ow, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t bstr[3] = {16, (cuuint64_t)pitch * 8, (cuuint64_t)h * pitch * 8};
+    cuuint32_t box[4] = {32u, (cuuint32_t)ow, (cuuint32_t)(2 * p.BH), 1u};
+    cuuint32_t estr[4] = {1, 1, 2, 1};
+    char* a = (char*)patches + pl * in_plane * 2;
+    if (make_map(&maps.a[0][pl], true, 4, a, dims, box, 64, 1, bstr, estr)) return -1;
+    maps.a[1][pl] = maps.a[0][pl];
+    cuuint64_t bd[2] = {7 * 32, 64};
+    cuuint32_t bb[2] = {32u, 64u};
+    if (make_map(&maps.b[pl], true, 2, (char*)wgt_split + (size_t)pl * 64 * 7 * 32 * 2, bd, bb, 64)) return -1;
+    cuuint64_t od[4] = {64, (cuuint64_t)ow, (cuuint64_t)oh, (cuuint64_t)n};
+    cuuint32_t ob[4] = {32u, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1u};
+    if (make_map(&maps.o[pl], true, 4, (char*)out + (size_t)pl * p.plane * 2, od, ob, 64)) return -1;
+  }
+  return launch_tc<64, MODE_F16X3, 64, true, false>(maps, p, s);
 }
 
 // ------------------------------------------------------------ split-half conversion

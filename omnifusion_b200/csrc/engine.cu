@@ -28,6 +28,8 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches += n; }
 
 int conv_simt(const ofb_conv_desc* d, cudaStream_t s);
+int stem_tc(const void* patches, int n, int h, int w, const void* wgt_split, float wgt_unscale, const float* scale,
+            const float* shift, void* out, cudaStream_t s);
 int conv_tc(const ofb_conv_desc* d, cudaStream_t s);
 bool conv_tc_supported(const ofb_conv_desc* d);
 
@@ -77,6 +79,8 @@ struct ofb_handle {
   float* ws = nullptr; size_t ws_floats = 0; size_t ws_used = 0;
   int engine = OFB_ENGINE_AUTO, chunk = 0, dedup = 1;
   int fmt = OFB_FMT_SPLIT16;       // activation storage inside the network
+  bool patches_zeroed = false;      // row pads of the stem-layout patch buffer are zero
+  int patches_imgs = 0;
   std::map<std::string, Act> acts;
   // optional per-launch timing (ofb_profile_enable)
   bool profile = false;
@@ -210,6 +214,25 @@ static int load_all(ofb_handle* h, const TMap& m, bool single) {
         for (int k = 0; k < 49; ++k) p[(k * 4 + i) * 64 + o] = t->data[(o * 3 + i) * 49 + k];
     stem.cout = 64; stem.cin = 4; stem.k = 7;
     if (dev_upload(h, p, &stem.w)) return -1;
+    // tensor-core stem: [cout][kh][kw' = kw + 1][cin padded to 4], kw' = 0 zero (ofb_stem_tc_f16)
+    std::vector<float> q(64 * 7 * 8 * 4, 0.f);
+    float mx = 0.f;
+    for (int o = 0; o < 64; ++o)
+      for (int i = 0; i < 3; ++i)
+        for (int kh = 0; kh < 7; ++kh)
+          for (int kw = 0; kw < 7; ++kw) {
+            float v = t->data[((o * 3 + i) * 7 + kh) * 7 + kw];
+            q[((o * 7 + kh) * 8 + kw + 1) * 4 + i] = v;
+            mx = fmaxf(mx, fabsf(v));
+          }
+    int ex = mx > 0.f ? 13 - (int)floorf(log2f(mx)) : 0;
+    stem.unscale = ldexpf(1.f, -ex);
+    float* tmp = nullptr;
+    if (dev_upload(h, q, &tmp)) return -1;
+    OFB_CUDA(cudaMalloc(&stem.ws, q.size() * 4));
+    h->owned.push_back(stem.ws);
+    if (ofb_split_f16(tmp, q.size(), ldexpf(1.f, ex), stem.ws, nullptr)) return -1;
+    OFB_CUDA(cudaStreamSynchronize(nullptr));
   }
   if (pack_bn(h, m, "bn1", 64, 1e-5f, &stem.scale, &stem.shift)) return -1;
   h->conv["stem"] = stem;
@@ -292,7 +315,7 @@ static size_t plan_buffers(ofb_handle* h, int imgs, int P, Buffers* b) {
   Plan pl{h};
   size_t I = (size_t)imgs;
   int p2 = P / 2, p4 = P / 4, p8 = P / 8, p16 = P / 16, p32 = P / 32;
-  b->patches = pl.take(I * P * P * 4);
+  b->patches = pl.take(I * P * (P + 8) * 4);       // room for the row-padded stem layout
   b->conv1 = pl.take(I * p2 * p2 * 64);
   b->pool = pl.take(I * p4 * p4 * 64);
   size_t s1 = I * p4 * p4 * 64, s2 = I * p8 * p8 * 128, s3 = I * p16 * p16 * 256, s4 = I * p32 * p32 * 512;
@@ -323,6 +346,7 @@ static int ensure_workspace(ofb_handle* h, int imgs, int P, Buffers* b) {
     h->ws = nullptr; h->ws_floats = 0;
     OFB_CUDA(cudaMalloc(&h->ws, need * sizeof(float)));
     h->ws_floats = need;
+    h->patches_zeroed = false;
   }
   plan_buffers(h, imgs, P, b);
   return 0;
@@ -432,11 +456,22 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
     bool reuse = it > 0 && h->dedup;
     if (!reuse) {
       // equi2pers(rgb, P) -> patches; stem; pool; layer1 (spherical_model_iterative.py:315,322-324)
-      { Prof pr(h, s, "e2p_rgb", 0.0, 4.0*((double)Bc*3*He*We + (double)imgs*P*P*4));
-      if (ofb_equi2pers_f32(rgb, Bc, 3, He, We, g.grid_hi, N, P, P, b.patches, OFB_LAYOUT_FOLDED, vs)) return -1; }
       const ConvW& st = h->conv["stem"];
-      { Prof pr(h, s, "stem7x7", 0.0, 4.0*((double)imgs*P*P*4 + (double)imgs*(P/2)*(P/2)*64));
-      if (ofb_stem_f32(b.patches, imgs, P, P, st.w, st.scale, st.shift, b.conv1, F, vs)) return -1; }
+      const bool stem_tc_path = F == OFB_FMT_SPLIT16 && h->engine != OFB_ENGINE_SIMT;
+      if (stem_tc_path && (!h->patches_zeroed || h->patches_imgs != imgs)) {
+        // the stem layout's row pads must read as zero; the interior is rewritten by every forward
+        OFB_CUDA(cudaMemsetAsync(b.patches, 0, (size_t)imgs * P * (P + 8) * 4 * sizeof(float), s));
+        h->patches_zeroed = true; h->patches_imgs = imgs;
+      }
+      { Prof pr(h, s, "e2p_rgb", 0.0, 4.0*((double)Bc*3*He*We + (double)imgs*P*P*4));
+      if (ofb_equi2pers_f32(rgb, Bc, 3, He, We, g.grid_hi, N, P, P, b.patches,
+                            stem_tc_path ? OFB_LAYOUT_STEM16 : OFB_LAYOUT_FOLDED, vs)) return -1; }
+      { Prof pr(h, s, "stem7x7", 2.0*imgs*(P/2)*(P/2)*64*147.0, 4.0*((double)imgs*P*P*4 + (double)imgs*(P/2)*(P/2)*64));
+      if (stem_tc_path) {
+        if (ofb_stem_tc_f16(b.patches, imgs, P, P, st.ws, st.unscale, st.scale, st.shift, b.conv1, vs)) return -1;
+      } else {
+        if (ofb_stem_f32(b.patches, imgs, P, P, st.w, st.scale, st.shift, b.conv1, F, vs)) return -1;
+      } }
       { Prof pr(h, s, "maxpool", 0.0, 4.0*((double)imgs*(P/2)*(P/2)*64 + (double)imgs*p4*p4*64));
       if (ofb_maxpool3x3s2_f32(b.conv1, imgs, P / 2, P / 2, 64, b.pool, F, vs)) return -1; }
       if (run_res_layer(c, 0, b.pool, 64, p4, b.l1t, b.l1a, b.l1b, nullptr, b.layer1_pre)) return -1;
@@ -545,6 +580,11 @@ extern "C" int ofb_set_device(int device) {
   return 0;
 }
 
+extern "C" int ofb_stem_tc_f16(const void* patches, int n, int h, int w, const void* wgt_split, float wgt_unscale,
+                               const float* scale, const float* shift, void* out, void* stream) {
+  return stem_tc(patches, n, h, w, wgt_split, wgt_unscale, scale, shift, out, (cudaStream_t)stream);
+}
+
 extern "C" int ofb_conv_f32(const ofb_conv_desc* d, void* stream) { return conv_dispatch(d, (cudaStream_t)stream); }
 
 extern "C" int ofb_create(int device, ofb_handle** out) {
@@ -599,6 +639,7 @@ extern "C" int ofb_load_weights(ofb_handle* h, const ofb_tensor_desc* tensors, i
 
 extern "C" int ofb_set_option(ofb_handle* h, const char* key, int value) {
   OFB_CHECK(h && key, "set_option: null pointer");
+  h->patches_zeroed = false;
   if (!strcmp(key, "engine")) h->engine = value;
   else if (!strcmp(key, "chunk")) h->chunk = value;
   else if (!strcmp(key, "dedup")) h->dedup = value;

@@ -85,6 +85,30 @@ __global__ void e2p_folded_kernel(const float* __restrict__ erp, const float2* _
   }
 }
 
+// STEM16 layout: split-half planes of (B*N, Ph, Pw+8, 4); the 4-pixel row pads are never written.
+__global__ void e2p_stem16_kernel(const float* __restrict__ erp, const float2* __restrict__ grid,
+                                  __half* __restrict__ out, int B, int He, int We, int N, int Ph, int Pw) {
+  int total = N * Ph * Pw;
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= total) return;
+  float2 g = __ldg(&grid[s]);
+  E2PTaps t = e2p_taps(g.x, g.y, He, We);
+  size_t plane = (size_t)He * We;
+  int j = s % Pw, ni = s / Pw;                       // ni = n*Ph + i
+  const int pitch = Pw + 8;
+  const size_t out_plane = (size_t)B * N * Ph * pitch * 4;
+  for (int b = 0; b < B; ++b) {
+    const float* img = erp + (size_t)b * 3 * plane;
+    float4 v;
+    v.x = e2p_sample(img, t, He, We);
+    v.y = e2p_sample(img + plane, t, He, We);
+    v.z = e2p_sample(img + 2 * plane, t, He, We);
+    v.w = 0.f;
+    size_t o = (((size_t)b * N * Ph + ni) * pitch + 4 + j) * 4;
+    act_st4<true>(out, o, out_plane, v);
+  }
+}
+
 __global__ void e2p_taps_kernel(const float2* __restrict__ grid, int total, int He, int We,
                                 int32_t* __restrict__ x0, int32_t* __restrict__ y0) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -236,6 +260,9 @@ extern "C" int ofb_equi2pers_f32(const float* erp, int B, int C, int He, int We,
     if (C == 3) e2p_folded_kernel<3><<<blocks, thr, 0, s>>>(erp, g, out, B, He, We, N, Ph, Pw);
     else if (C == 1) e2p_folded_kernel<1><<<blocks, thr, 0, s>>>(erp, g, out, B, He, We, N, Ph, Pw);
     else OFB_CHECK(false, "equi2pers: folded layout supports C in {1,3}, got %d", C);
+  } else if (layout == OFB_LAYOUT_STEM16) {
+    OFB_CHECK(C == 3, "equi2pers: the stem layout needs C == 3, got %d", C);
+    e2p_stem16_kernel<<<blocks, thr, 0, s>>>(erp, g, reinterpret_cast<__half*>(out), B, He, We, N, Ph, Pw);
   } else {
     OFB_CHECK(false, "equi2pers: unknown layout %d", layout);
   }

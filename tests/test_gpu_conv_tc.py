@@ -106,3 +106,35 @@ def test_split_merge_roundtrip_precision():
     print(f"[parity] split16 roundtrip max abs err {err.max().item():.3e}")
     # ~22 mantissa bits, and an absolute floor of half an fp16 subnormal step (2^-25) on the lo plane
     assert (err <= 3.1e-8 + 2.5e-7 * x.abs()).all()
+
+
+def test_stem_on_tensor_cores_matches_fp32():
+    """7x7 s2 stem as an implicit GEMM over overlapping 64-byte TMA windows (ofb_stem_tc_f16)."""
+    import ctypes as C
+    o = ops()
+    n = 3
+    x = torch.rand(n, 3, 128, 128, generator=torch.Generator().manual_seed(1))
+    w = rand(64, 3, 7, 7, seed=2, scale=0.1)
+    scale = 0.5 + torch.rand(64, generator=torch.Generator().manual_seed(3))
+    shift = rand(64, seed=4, scale=0.1)
+    ref = F.relu(F.conv2d(x, w, None, 2, 3) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    # patches: (n,128,128+8,4) with zero row pads and a zero 4th channel, split-half planes
+    xp = torch.zeros(n, 128, 136, 4)
+    xp[:, :, 4:132, :3] = x.permute(0, 2, 3, 1)
+    planes = o.split16(xp.to(DEV))
+    # weights: (64,7,8,4) with kw' = kw + 1
+    wq = torch.zeros(64, 7, 8, 4)
+    wq[:, :, 1:, :3] = w.permute(0, 2, 3, 1)
+    mul = o.weight_scale(wq)
+    wplanes = o.split16(wq.to(DEV), mul)
+    out = torch.empty(2 * n * 64 * 64 * 64, dtype=torch.float16, device=DEV)
+    d_scale, d_shift = scale.to(DEV), shift.to(DEV)          # keep the device copies alive across the call
+    _lib.use_device(torch.device(DEV))
+    _lib.check(_lib.lib().ofb_stem_tc_f16(_lib.ptr(planes), n, 128, 128, _lib.ptr(wplanes), 1.0 / mul,
+                                           _lib.ptr(d_scale), _lib.ptr(d_shift), _lib.ptr(out),
+                                           _lib.stream_of(torch.device(DEV))))
+    torch.cuda.synchronize()
+    got = o.nchw(o.merge16(out, (n, 64, 64, 64)).cpu())
+    err = (got - ref).abs()
+    print(f"[parity] stem_tc: max_abs_err={err.max().item():.3e} ref_absmax={ref.abs().max().item():.3e}")
+    assert (err <= 3e-5 + 3e-5 * ref.abs()).all()
