@@ -186,6 +186,12 @@ int ofb_heads_f32(const void* x, int imgs, int h, int w,
 int ofb_absrel_partial(const float* pred, const float* gt, const uint8_t* mask, size_t n,
                        float scale, double* out, void* stream);
 
+/* All seven evaluation metrics of metrics.py:7-26 as partial sums (test.py:151-177): out[9] +=
+ * [sum |p-g|/g, sum (p-g)^2/g, sum (p-g)^2, sum (ln p - ln g)^2, n_log, n(delta<1.25),
+ *  n(delta<1.25^2), n(delta<1.25^3), n] over mask, with p = pred*scale.  `out` zeroed by the caller. */
+int ofb_depth_metrics_partial(const float* pred, const float* gt, const uint8_t* mask, size_t n,
+                              float scale, double* out, void* stream);
+
 /* ------------------------------------------------------------------- engine */
 
 int ofb_create(int device, ofb_handle** out);

@@ -114,22 +114,33 @@ __device__ __forceinline__ float act_fn(float v, int act) {
 // the weight slices of all three kh taps; the three kh MMAs read the same box at row offsets
 // 0, BW, 2*BW (multiples of 8 rows, so the swizzle phase is unchanged).  A-operand traffic from
 // L2 drops from 9*BH to 3*(BH+2) image rows per tile - the fix for the L2-bound narrow layers.
-template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR>
+// BRES (KHR layers whose whole filter is a few KB, i.e. 32->32): the weights are loaded once per CTA
+// into a resident region and the ring stages carry activations only - the layer is bound by the TMA
+// request rate on its 64-byte rows, and a third of those requests were weight re-loads.
+template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR, bool BRES = false>
 struct TcCfg {
   static constexpr int PLANES = MODE == MODE_F16X3 ? 2 : 1;
   static constexpr int ES = MODE == MODE_F16X3 ? 2 : 4;
   static constexpr int A_BYTES = (KHR ? 192 : 128) * ROW_BYTES;           // capacity; KHR boxes are <= 192 rows
   static constexpr int B_BYTES = (KHR ? 3 : 1) * BN * ROW_BYTES;
-  static constexpr int STAGE = (A_BYTES + B_BYTES) * PLANES;
+  static constexpr int STAGE = (A_BYTES + (BRES ? 0 : B_BYTES)) * PLANES;
+  static constexpr int RES = BRES ? 3 * PLANES * B_BYTES : 0;               // resident weights (all 3 kw)
   static constexpr int OUT_ROW = 32 * ES;                                  // bytes per staged row (32 columns)
   static constexpr int OUT_BUF = TMA_STORE ? PLANES * 128 * OUT_ROW : 0;   // one staging buffer
   static constexpr int MISC = 1024 /*align*/ + 256 /*barriers*/ + BN * 8;
-  static constexpr int NST_RAW = (227 * 1024 - MISC - 2 * OUT_BUF) / STAGE;
+  static constexpr int NST_RAW = (227 * 1024 - MISC - 2 * OUT_BUF - RES) / STAGE;
   static constexpr int NST = NST_RAW > 8 ? 8 : NST_RAW;
   static constexpr int KC = ROW_BYTES / ES;                                // channels per K-step
   static constexpr int MMA_PER_TILE = ROW_BYTES / 32;                      // UMMA_K spans 32 bytes
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;              // two accumulator buffers
-  static constexpr int SMEM = NST * STAGE + 2 * OUT_BUF + MISC;
+  // Every MMA re-reads its 128 x 32 B slice of A from shared memory, which is what bounds the narrow
+  // tiles.  So hi*Whi and hi*Wlo are issued as ONE MMA against the stacked weight tile [Whi; Wlo]
+  // (the lo tile directly follows the hi tile in shared memory; N = 2*BN, two column blocks of the
+  // accumulator that the epilogue adds) and only lo*Whi needs a second MMA: A is read twice per
+  // K-slice instead of three times, and 2 instead of 3 MMAs are issued.
+  static constexpr bool STACK = MODE == MODE_F16X3;
+  static constexpr int ACC_COLS = STACK ? 2 * BN : BN;                     // accumulator columns per buffer
+  static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;  // two accumulator buffers
+  static constexpr int SMEM = NST * STAGE + 2 * OUT_BUF + RES + MISC;
   static_assert(NST >= 2, "pipeline needs at least two stages");
 };
 
@@ -152,10 +163,10 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
 // Persistent kernel: each CTA walks tiles t = blockIdx.x, +gridDim.x, ...; the smem ring and its
 // phases run continuously across tiles, and two TMEM accumulator buffers let the MMA warp start
 // tile i+1 while the epilogue warps drain tile i.
-template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR>
+template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR, bool BRES = false>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
-  using Cfg = TcCfg<BN, MODE, ROW_BYTES, TMA_STORE, KHR>;
+  using Cfg = TcCfg<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023) & ~1023u;
@@ -163,10 +174,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   constexpr int RING = Cfg::NST * Cfg::STAGE;
   const uint32_t stage_out = base + RING;                        // 2 staging buffers (TMA_STORE)
   uint8_t* stage_out_ptr = base_ptr + RING;
-  constexpr int AFTER = RING + 2 * Cfg::OUT_BUF;
-  const uint32_t bars = base + AFTER;                            // full[NST], empty[NST], tfull[2], tempty[2]
-  const uint32_t bar_tfull = bars + 8 * (2 * Cfg::NST), bar_tempty = bar_tfull + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + AFTER + 8 * (2 * Cfg::NST + 4));
+  const uint32_t res_b = base + RING + 2 * Cfg::OUT_BUF;         // resident weights (BRES)
+  constexpr int AFTER = RING + 2 * Cfg::OUT_BUF + Cfg::RES;
+  const uint32_t bars = base + AFTER;                            // full[NST], empty[NST], tfull[2], tempty[2], res
+  const uint32_t bar_tfull = bars + 8 * (2 * Cfg::NST), bar_tempty = bar_tfull + 16, bar_res = bar_tempty + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + AFTER + 8 * (2 * Cfg::NST + 5));
   float* s_scale = reinterpret_cast<float*>(base_ptr + AFTER + 256);
   float* s_shift = s_scale + BN;
 
@@ -185,6 +197,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       mbar_init(bar_tfull + 8 * i, 1);
       mbar_init(bar_tempty + 8 * i, 4);          // one arrival per epilogue warp
     }
+    mbar_init(bar_res, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&maps.a[0][0]);
     tma_prefetch_desc(&maps.b[0]);
@@ -199,11 +212,21 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
+  // prefetch) may overlap the tail of the previous kernel in the stream; no global memory is
+  // touched before this point.  Let the next kernel start its own prologue as early as possible.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0;
+      if (BRES) {      // the whole filter (3 kw x all kh x cin x cout, both planes) once per CTA
+        mbar_expect_tx(bar_res, Cfg::RES);
+        for (int kw = 0; kw < 3; ++kw)
+          tma_load_4d(res_b + kw * Cfg::PLANES * Cfg::B_BYTES, &maps.b[0], bar_res, 0, 0, 0, kw);
+      }
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const int nt = t % p.tiles_n, mt = t / p.tiles_n;
         const int grp = mt / tiles_per_group, trem = mt - grp * tiles_per_group;
@@ -223,12 +246,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
           if (KHR) {
             // here `tap` is kw; the box carries rows y0-1 .. y0+BH, the weights all three kh
-            mbar_expect_tx(full, (uint32_t)(Cfg::PLANES * ((p.BH + 2) * p.BW * ROW_BYTES + Cfg::B_BYTES)));
+            mbar_expect_tx(full, (uint32_t)(Cfg::PLANES * ((p.BH + 2) * p.BW * ROW_BYTES + (BRES ? 0 : Cfg::B_BYTES))));
 #pragma unroll
-            for (int pl = 0; pl < Cfg::PLANES; ++pl) {
+            for (int pl = 0; pl < Cfg::PLANES; ++pl)
               tma_load_4d(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, x0 + tap - 1, y0 - 1, img0);
-              tma_load_4d(sb + pl * Cfg::B_BYTES, &maps.b[pl], full, cq * Cfg::KC, n0, 0, tap);
-            }
+            // one box = {kc, stacked [Whi; Wlo] rows, all 3 kh, this kw}
+            if (!BRES) tma_load_4d(sb, &maps.b[0], full, cq * Cfg::KC, 0, 0, tap);
           } else {
             mbar_expect_tx(full, Cfg::STAGE);
 #pragma unroll
@@ -249,35 +272,50 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       const uint32_t fmt = MODE == MODE_TF32 ? 2u : 0u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
       uint32_t it = 0, i = 0;
+      if (BRES) mbar_wait(bar_res, 0);
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
         const uint32_t buf = i & 1;
         mbar_wait(bar_tempty + 8 * buf, ((i >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t acc = tmem + buf * BN;
+        const uint32_t acc = tmem + buf * Cfg::ACC_COLS;
         for (int ks = 0; ks < ksteps; ++ks, ++it) {
           const int st = it % Cfg::NST;
           const uint32_t ph = (it / Cfg::NST) & 1;
           mbar_wait(bars + 8 * st, ph);
           tc_fence_after();
           const uint32_t sa = base + st * Cfg::STAGE;
-          const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
+          // BRES: one K-step per kw (cin == KC), its weights sit in the resident region
+          const uint32_t sb = BRES ? res_b + (uint32_t)(ks * Cfg::PLANES * Cfg::B_BYTES) : sa + Cfg::PLANES * Cfg::A_BYTES;
+          const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * BN) >> 3) << 17);   // N = 2*BN
+          if (KHR) {
 #pragma unroll
-          for (int kh = 0; kh < (KHR ? 3 : 1); ++kh) {
-            // KHR: tap kh reads the halo box kh image rows further down, and its own weight slice
-            const uint32_t ao = KHR ? (uint32_t)(kh * p.BW * ROW_BYTES) : 0u, bo = (uint32_t)(kh * BN * ROW_BYTES);
+            for (int kh = 0; kh < 3; ++kh) {
+              // tap kh reads the halo box kh image rows further down; weights: [kh][Whi rows; Wlo rows]
+              const uint32_t ao = (uint32_t)(kh * p.BW * ROW_BYTES), bo = (uint32_t)(kh * 2 * BN * ROW_BYTES);
+              const uint64_t a_hi = umma_desc<ROW_BYTES>(sa + ao), a_lo = umma_desc<ROW_BYTES>(sa + Cfg::A_BYTES + ao);
+              const uint64_t b_st = umma_desc<ROW_BYTES>(sb + bo);
+#pragma unroll
+              for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk) {
+                tc_mma<MODE>(acc, a_hi + 2 * kk, b_st + 2 * kk, idesc2, (ks | kh | kk) != 0);   // hi*Whi | hi*Wlo
+                tc_mma<MODE>(acc, a_lo + 2 * kk, b_st + 2 * kk, idesc, 1);                     // + lo*Whi
+              }
+            }
+          } else
+#pragma unroll
+          for (int kh = 0; kh < 1; ++kh) {
+            const uint32_t ao = 0u, bo = 0u;
             const uint64_t a_hi = umma_desc<ROW_BYTES>(sa + ao), b_hi = umma_desc<ROW_BYTES>(sb + bo);
             if (MODE == MODE_TF32) {
 #pragma unroll
               for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk)
                 tc_mma<MODE>(acc, a_hi + 2 * kk, b_hi + 2 * kk, idesc, (ks | kh | kk) != 0);
             } else {
+              // sb holds [Whi rows][Wlo rows] back to back = the stacked operand
               const uint64_t a_lo = umma_desc<ROW_BYTES>(sa + Cfg::A_BYTES + ao);
-              const uint64_t b_lo = umma_desc<ROW_BYTES>(sb + Cfg::B_BYTES + bo);
 #pragma unroll
               for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk) {
-                tc_mma<MODE>(acc, a_hi + 2 * kk, b_hi + 2 * kk, idesc, (ks | kh | kk) != 0);
-                tc_mma<MODE>(acc, a_lo + 2 * kk, b_hi + 2 * kk, idesc, 1);
-                tc_mma<MODE>(acc, a_hi + 2 * kk, b_lo + 2 * kk, idesc, 1);
+                tc_mma<MODE>(acc, a_hi + 2 * kk, b_hi + 2 * kk, idesc2, (ks | kh | kk) != 0);   // hi*Whi | hi*Wlo
+                tc_mma<MODE>(acc, a_lo + 2 * kk, b_hi + 2 * kk, idesc, 1);                     // + lo*Whi
               }
             }
           }
@@ -318,7 +356,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 #pragma unroll 1
       for (int cb = 0; cb < BN; cb += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * BN + cb, v);
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * Cfg::ACC_COLS + cb, v);
+        if (Cfg::STACK) {                        // second column block (hi*Wlo) of the stacked accumulator
+          uint32_t v2[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * Cfg::ACC_COLS + BN + cb, v2);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        }
         if (cb + 32 >= BN) {                     // accumulator fully read: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -490,6 +534,11 @@ bool conv_tc_supported(const ofb_conv_desc* d) {
   return true;
 }
 
+static bool g_pdl = true;      // programmatic dependent launch for the tensor-core kernels
+static bool g_store128 = true;  // bulk-tensor-store epilogue also for the 128-wide tiles
+void conv_tc_set_pdl(bool on) { g_pdl = on; }
+void conv_tc_set_store128(bool on) { g_store128 = on; }
+
 static int num_sms() {
   static int n = 0;
   if (!n) {
@@ -501,25 +550,36 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR>
+template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR, bool BRES = false>
 static int launch_tc(const TcMaps& maps, const TcParams& p, cudaStream_t s) {
-  using Cfg = TcCfg<BN, MODE, ROW_BYTES, TMA_STORE, KHR>;
+  using Cfg = TcCfg<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES>;
   static bool attr = false;
   if (!attr) {
-    OFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MODE, ROW_BYTES, TMA_STORE, KHR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    OFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr = true;
   }
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();      // persistent: one CTA per SM
-  conv_tc_kernel<BN, MODE, ROW_BYTES, TMA_STORE, KHR><<<grid, 192, Cfg::SMEM, s>>>(maps, p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;
+  cudaLaunchAttribute attr_pdl[1];
+  attr_pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr_pdl[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr_pdl; cfg.numAttrs = g_pdl ? 1 : 0;
+  OFB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES>, maps, p));
   OFB_LAUNCH_CHECK();
   return 0;
 }
 
 template <int MODE, int ROW_BYTES>
 static int launch_bn(int bn, bool khr, const TcMaps& maps, const TcParams& p, cudaStream_t s) {
-  if (bn == 128) return launch_tc<128, MODE, ROW_BYTES, false, false>(maps, p, s);
+  if (bn == 128) {
+    if (g_store128) return launch_tc<128, MODE, ROW_BYTES, true, false>(maps, p, s);
+    return launch_tc<128, MODE, ROW_BYTES, false, false>(maps, p, s);
+  }
   if (MODE == MODE_F16X3 && khr) {
     if (bn == 64) return launch_tc<64, MODE_F16X3, ROW_BYTES, true, true>(maps, p, s);
+    // 32 -> 32 channels: the whole filter stays resident in shared memory
+    if (ROW_BYTES == 64 && p.c0 + p.c1 == 32 && p.cout == 32) return launch_tc<32, MODE_F16X3, 64, true, true, true>(maps, p, s);
     return launch_tc<32, MODE_F16X3, ROW_BYTES, true, true>(maps, p, s);
   }
   if (bn == 64) return launch_tc<64, MODE, ROW_BYTES, true, false>(maps, p, s);
@@ -547,14 +607,14 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
   p.residual = d->residual; p.out = d->out; p.act = d->act;
   p.plane = (long long)d->n * oh * ow * d->cout;
   const int groups = (d->n + p.BNI - 1) / p.BNI;
+  // kh-reuse tiling for the narrow 3x3 layers: 32x4 / 16x8 pixel tiles inside one image.  Decided from the
+  // layer shape only, never from the batch size, so results stay batch-invariant (it accumulates the taps
+  // in a different order).
+  const bool khr = split && d->k == 3 && d->stride == 1 && d->cout <= 64 && ow >= 16 && oh >= 8;
   // widest N tile unless that leaves most SMs without a tile
   int bn = d->cout >= 128 ? 128 : d->cout;
   // (only for really small problems such as the token linears: narrow tiles re-read the A tile more often)
-  while (bn > 32 && (long long)groups * p.tiles_x * p.tiles_y * (d->cout / bn) < num_sms() / 4) bn >>= 1;
-  // kh-reuse tiling for the narrow (L2-bound) 3x3 layers: 32x4 / 16x8 pixel tiles inside one image
-  // (decided from the layer shape only, never from the batch size, so results stay batch-invariant:
-  // kh-reuse accumulates the taps in a different order)
-  const bool khr = split && d->k == 3 && d->stride == 1 && d->cout <= 64 && ow >= 16 && oh >= 8;
+  while (!khr && bn > 32 && (long long)groups * p.tiles_x * p.tiles_y * (d->cout / bn) < num_sms() / 4) bn >>= 1;
   int groups_k = groups;
   if (khr) {
     p.BW = ow < 32 ? ow : 32; p.BH = 128 / p.BW; p.BNI = 1;
@@ -579,14 +639,14 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
     }
   }
   if (khr) {
-    // weights (cout, kh, kw, cin) seen as dims {cin, cout, kh, kw}: one box = {kc, bn, all 3 kh, one kw}
-    cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)d->cout, 3, 3};
+    // weights: the hi plane (cout, kh, kw, cin) is followed by the lo plane, i.e. one (2*cout, kh, kw, cin)
+    // tensor = the stacked [Whi; Wlo] operand.  Seen as dims {cin, 2*cout, kh, kw}: one box = {kc, 2*bn rows,
+    // all 3 kh, one kw} -> shared memory [kh][Whi rows; Wlo rows]
+    cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)2 * d->cout, 3, 3};
     cuuint64_t bstr[3] = {(cuuint64_t)9 * cin * es, (cuuint64_t)3 * cin * es, (cuuint64_t)cin * es};
-    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)bn, 3u, 1u};
-    for (int pl = 0; pl < planes; ++pl) {
-      char* a = (char*)d->wgt_split + (size_t)pl * d->cout * 9 * cin * 2;
-      if (make_map(&maps.b[pl], split, 4, a, dims, box, row_bytes, 1, bstr)) return -1;
-    }
+    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(2 * bn), 3u, 1u};
+    if (make_map(&maps.b[0], split, 4, (char*)d->wgt_split, dims, box, row_bytes, 1, bstr)) return -1;
+    maps.b[1] = maps.b[0];
   } else {
     cuuint64_t dims[2] = {(cuuint64_t)d->k * d->k * cin, (cuuint64_t)d->cout};
     cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)bn};
@@ -595,7 +655,7 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
       if (make_map(&maps.b[pl], split, 2, a, dims, box, row_bytes)) return -1;
     }
   }
-  if (bn < 128) {      // output tensor maps for the bulk-store epilogue: box = 32 columns x the pixel box
+  if (bn < 128 || g_store128) {      // output tensor maps for the bulk-store epilogue: box = 32 columns x the pixel box
     cuuint64_t dims[4] = {(cuuint64_t)d->cout, (cuuint64_t)ow, (cuuint64_t)oh, (cuuint64_t)d->n};
     cuuint32_t box[4] = {32u, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BNI};
     for (int pl = 0; pl < planes; ++pl) {

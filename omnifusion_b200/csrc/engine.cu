@@ -32,6 +32,8 @@ int stem_tc(const void* patches, int n, int h, int w, const void* wgt_split, flo
             const float* shift, void* out, cudaStream_t s);
 int conv_tc(const ofb_conv_desc* d, cudaStream_t s);
 bool conv_tc_supported(const ofb_conv_desc* d);
+void conv_tc_set_pdl(bool on);
+void conv_tc_set_store128(bool on);
 
 int conv_dispatch(const ofb_conv_desc* d, cudaStream_t s) {
   OFB_CHECK(d && d->in0 && (d->wgt || d->wgt_split) && d->out, "conv: null pointer");
@@ -643,6 +645,8 @@ extern "C" int ofb_set_option(ofb_handle* h, const char* key, int value) {
   if (!strcmp(key, "engine")) h->engine = value;
   else if (!strcmp(key, "chunk")) h->chunk = value;
   else if (!strcmp(key, "dedup")) h->dedup = value;
+  else if (!strcmp(key, "pdl")) conv_tc_set_pdl(value != 0);     // process-wide: programmatic dependent launch
+  else if (!strcmp(key, "store128")) conv_tc_set_store128(value != 0);
   else if (!strcmp(key, "format")) {
     OFB_CHECK(value == OFB_FMT_F32 || value == OFB_FMT_SPLIT16, "set_option: format must be 0 (float32) or 1 (split-half)");
     h->fmt = value;

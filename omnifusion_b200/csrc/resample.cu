@@ -242,9 +242,67 @@ __global__ void absrel_kernel(const float* __restrict__ pred, const float* __res
   }
 }
 
+// All seven metrics of metrics.py:7-26 / test.py:151-170 in one pass:
+// out = [sum |p-g|/g, sum (p-g)^2/g, sum (p-g)^2, sum (log p - log g)^2, n_log, n(d<1.25), n(d<1.25^2), n(d<1.25^3), n]
+__global__ void depth_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                     const uint8_t* __restrict__ mask, size_t n, float scale,
+                                     double* __restrict__ out) {
+  double acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    if (!mask[i]) continue;
+    float g = gt[i], p = pred[i] * scale;
+    float d = p - g;
+    acc[0] += (double)(fabsf(d) / g);
+    acc[1] += (double)((d * d) / g);
+    acc[2] += (double)(d * d);
+    if (p > 1e-7f && g > 1e-7f) {
+      float l = logf(p) - logf(g);
+      acc[3] += (double)(l * l);
+      acc[4] += 1.0;
+    }
+    float r = fmaxf(p / g, g / p);
+    acc[5] += r < 1.25f ? 1.0 : 0.0;
+    acc[6] += r < 1.5625f ? 1.0 : 0.0;
+    acc[7] += r < 1.953125f ? 1.0 : 0.0;
+    acc[8] += 1.0;
+  }
+  __shared__ double sh[9][32];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    double v = acc[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[k][wid] = v;
+  }
+  __syncthreads();
+  if (wid == 0) {
+    int nw = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      double v = lane < nw ? sh[k][lane] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) atomicAdd(&out[k], v);
+    }
+  }
+}
+
 }  // namespace ofb
 
 using namespace ofb;
+
+extern "C" int ofb_depth_metrics_partial(const float* pred, const float* gt, const uint8_t* mask, size_t n,
+                                         float scale, double* out, void* stream) {
+  OFB_CHECK(pred && gt && mask && out, "depth_metrics: null pointer");
+  int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  depth_metrics_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pred, gt, mask, n, scale, out);
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+
 
 extern "C" int ofb_equi2pers_f32(const float* erp, int B, int C, int He, int We, const float* grid,
                                  int N, int Ph, int Pw, float* out, int layout, void* stream) {

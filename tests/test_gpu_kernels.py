@@ -278,3 +278,17 @@ def test_absrel_partial_matches_metrics_py():
     s = o.absrel(pred.to(DEV), gt.to(DEV), mask.to(DEV)).cpu()
     assert int(s[1]) == int(mask.sum())
     assert abs(s[0] / s[1] - ref.item()) <= 1e-6
+
+
+def test_depth_metrics_match_oracle_eval():
+    from omnifusion_b200 import metrics
+    from oracle import model as om
+    pred = 0.1 + 7.9 * urand(2, 1, 128, 256, seed=1)
+    gt = 0.1 + 7.9 * urand(2, 1, 128, 256, seed=2)
+    mask = (gt <= 8) & (gt > 0.1) & (urand(2, 1, 128, 256, seed=3) > 0.2)
+    for med in (False, True):
+        ref = om.eval_metrics(pred, gt, mask, median_scale=med)
+        got = metrics.compute_eval_metrics(pred.to(DEV), gt.to(DEV), mask.to(DEV), use_median_scale=med)
+        assert got["n"] == ref["n"]
+        for k in metrics.METRIC_NAMES:
+            assert abs(got[k] - ref[k]) <= 2e-6 * max(1.0, abs(ref[k])), (k, got[k], ref[k])
