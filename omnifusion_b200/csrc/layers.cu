@@ -137,42 +137,59 @@ __global__ void maxpool_kernel(const void* __restrict__ in, int n, int h, int w,
 // F.interpolate(scale 2, bilinear, align_corners=False): src = (dst+0.5)/2-0.5 clamped at 0,
 // i1 = min(i0+1, size-1), lambda in {0, .25, .75}.  Same expression tree as ATen's
 // upsample_bilinear2d: h0*(w0*a + w1*b) + h1*(w0*c + w1*d).
+// One thread per (source pixel, 8-channel chunk): it loads the 3x3 source neighbourhood once
+// (clamped at the borders) and produces the 2x2 output block, i.e. 2.25 loads per output instead of 4.
+// Per output the expression tree is ATen's: h0*(w0*a + w1*b) + h1*(w0*c + w1*d).
 template <bool SPLIT>
 __global__ void upsample2x_kernel(const void* __restrict__ in, const float* __restrict__ img_bias,
                                   int n, int h, int w, int c8, void* __restrict__ out) {
-  int oh_n = h * 2, ow_n = w * 2;
-  size_t total = (size_t)n * oh_n * ow_n * c8;
+  size_t total = (size_t)n * h * w * c8;
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= total) return;
   int c = (int)(i % c8);
   size_t r = i / c8;
-  int ow = (int)(r % ow_n); r /= ow_n;
-  int oh = (int)(r % oh_n);
-  int img = (int)(r / oh_n);
-  float sy = fmaxf(0.5f * (oh + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.5f * (ow + 0.5f) - 0.5f, 0.f);
-  int y0 = (int)sy, x0 = (int)sx;
-  int y1 = y0 + (y0 < h - 1), x1 = x0 + (x0 < w - 1);
-  float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
-  const size_t in_plane = (size_t)n * h * w * c8 * 8;
-  const size_t ib = ((size_t)img * h * w * c8 + c) * 8;
-  float8 a = act_ld8<SPLIT>(in, ib + ((size_t)y0 * w + x0) * c8 * 8, in_plane);
-  float8 b = act_ld8<SPLIT>(in, ib + ((size_t)y0 * w + x1) * c8 * 8, in_plane);
-  float8 cc = act_ld8<SPLIT>(in, ib + ((size_t)y1 * w + x0) * c8 * 8, in_plane);
-  float8 d = act_ld8<SPLIT>(in, ib + ((size_t)y1 * w + x1) * c8 * 8, in_plane);
-  float8 bb;
-  bb.a = bb.b = make_float4(0.f, 0.f, 0.f, 0.f);
+  int x = (int)(r % w); r /= w;
+  int y = (int)(r % h);
+  int img = (int)(r / h);
+  const size_t in_plane = (size_t)n * h * w * c8 * 8, out_plane = in_plane * 4;
+  const int ys[3] = {max(y - 1, 0), y, min(y + 1, h - 1)};
+  const int xs[3] = {max(x - 1, 0), x, min(x + 1, w - 1)};
+  float8 v[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+      v[a][b] = act_ld8<SPLIT>(in, (((size_t)img * h + ys[a]) * w + xs[b]) * c8 * 8 + (size_t)c * 8, in_plane);
   if (img_bias) {
     const float4* bp = reinterpret_cast<const float4*>(img_bias) + ((size_t)img * c8 + c) * 2;
-    bb.a = __ldg(bp);
-    bb.b = __ldg(bp + 1);
+    float4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        v[a][b].a.x += b0.x; v[a][b].a.y += b0.y; v[a][b].a.z += b0.z; v[a][b].a.w += b0.w;
+        v[a][b].b.x += b1.x; v[a][b].b.y += b1.y; v[a][b].b.z += b1.z; v[a][b].b.w += b1.w;
+      }
   }
-  // same expression tree as ATen: h0*(w0*a + w1*b) + h1*(w0*c + w1*d), bias added to the sources first
-#define OFB_UP(f) (hy * (hx * (a.f + bb.f) + lx * (b.f + bb.f)) + ly * (hx * (cc.f + bb.f) + lx * (d.f + bb.f)))
-  float8 o;
-  o.a = make_float4(OFB_UP(a.x), OFB_UP(a.y), OFB_UP(a.z), OFB_UP(a.w));
-  o.b = make_float4(OFB_UP(b.x), OFB_UP(b.y), OFB_UP(b.z), OFB_UP(b.w));
+  // Output row 2y+dy blends source rows (dy, dy+1) of the clamped 3x3 block; same for columns.
+  // dy = 0: rows (y-1, y) weighted (0.25, 0.75); at the top border both are row 0 and the weights
+  // become (0, 1) so the value is exact, like ATen's lambda = 0.  dy = 1: rows (y, y+1) with (0.75, 0.25).
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+    const float h1 = dy == 0 ? (y == 0 ? 1.f : 0.75f) : 0.25f, h0 = 1.f - h1;
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const float w1 = dx == 0 ? (x == 0 ? 1.f : 0.75f) : 0.25f, w0 = 1.f - w1;
+      const float8 &A = v[dy][dx], &B = v[dy][dx + 1], &Cc = v[dy + 1][dx], &D = v[dy + 1][dx + 1];
+#define OFB_UP(f) (h0 * (w0 * A.f + w1 * B.f) + h1 * (w0 * Cc.f + w1 * D.f))
+      float8 o;
+      o.a = make_float4(OFB_UP(a.x), OFB_UP(a.y), OFB_UP(a.z), OFB_UP(a.w));
+      o.b = make_float4(OFB_UP(b.x), OFB_UP(b.y), OFB_UP(b.z), OFB_UP(b.w));
 #undef OFB_UP
-  act_st8<SPLIT>(out, i * 8, total * 8, o);
+      size_t o_idx = ((((size_t)img * 2 * h + 2 * y + dy) * 2 * w + 2 * x + dx) * c8 + c) * 8;
+      act_st8<SPLIT>(out, o_idx, out_plane, o);
+    }
+  }
 }
 
 // ---------------------------------------------------------------- point embed
@@ -483,7 +500,7 @@ extern "C" int ofb_maxpool3x3s2_f32(const void* in, int n, int h, int w, int c, 
 extern "C" int ofb_upsample2x_f32(const void* in, const float* img_bias, int n, int h, int w, int c,
                                   void* out, int fmt, void* stream) {
   OFB_CHECK(in && out && c % 8 == 0 && OFB_FMT_OK(fmt), "upsample2x: bad arguments");
-  size_t total = (size_t)n * h * 2 * w * 2 * (c / 8);
+  size_t total = (size_t)n * h * w * (c / 8);
   if (fmt) upsample2x_kernel<true><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, img_bias, n, h, w, c / 8, out);
   else upsample2x_kernel<false><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, img_bias, n, h, w, c / 8, out);
   OFB_LAUNCH_CHECK();
