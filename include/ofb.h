@@ -102,7 +102,11 @@ enum { OFB_FMT_F32 = 0, OFB_FMT_SPLIT16 = 1 };
  * in_fmt applies to in0/in1, out_fmt to out/residual.  The tcgen05 engine needs
  * in_fmt == out_fmt; with OFB_FMT_SPLIT16 it reads the weights from wgt_split (split-half
  * planes of wgt * 2^e made by ofb_split_f16, wgt_unscale = 2^-e); with OFB_FMT_F32 it runs
- * one kind::tf32 MMA on wgt (TF32 accuracy only - not used by the engine's default path). */
+ * one kind::tf32 MMA on wgt (TF32 accuracy only - not used by the engine's default path).
+ * ups2x != 0 fuses the decoder's F.interpolate(scale 2, bilinear, align_corners=False) of
+ * spherical_model_iterative.py:367 into the conv: in0 is then the LOW-resolution tensor
+ * (n,h/2,w/2,c0) and h,w stay the conv's input size; the upsampled tensor is never materialised
+ * (tcgen05 engine, split-half format, 32 -> 32 channels, 3x3 stride 1, w % 32 == 0, h % 4 == 0). */
 typedef struct {
   const void* in0; const void* in1; int c0, c1;
   int n, h, w;
@@ -113,6 +117,7 @@ typedef struct {
   int engine;
   int in_fmt, out_fmt;
   const void* wgt_split; float wgt_unscale;
+  int ups2x;
 } ofb_conv_desc;
 int ofb_conv_f32(const ofb_conv_desc* d, void* stream);
 

@@ -27,7 +27,8 @@ class ConvDesc(C.Structure):
                 ("wgt", C.c_void_p), ("k", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("cout", C.c_int),
                 ("scale", C.c_void_p), ("shift", C.c_void_p), ("residual", C.c_void_p),
                 ("act", C.c_int), ("out", C.c_void_p), ("engine", C.c_int),
-                ("in_fmt", C.c_int), ("out_fmt", C.c_int), ("wgt_split", C.c_void_p), ("wgt_unscale", C.c_float)]
+                ("in_fmt", C.c_int), ("out_fmt", C.c_int), ("wgt_split", C.c_void_p), ("wgt_unscale", C.c_float),
+                ("ups2x", C.c_int)]
 
 
 class Geometry(C.Structure):

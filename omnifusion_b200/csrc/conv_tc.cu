@@ -34,6 +34,8 @@ struct TcParams {
   int act;
   long long plane;   // elements per plane of out / residual (split format)
   int tiles_n, total_tiles;
+  const void* ups_src;   // UPS: low-resolution input (n_img, H/2, W/2, c0), split-half planes
+  long long ups_plane;   // elements per plane of ups_src
 };
 
 // ------------------------------------------------------------------ PTX wrappers (mbarrier: ptx.cuh)
@@ -117,10 +119,16 @@ __device__ __forceinline__ float act_fn(float v, int act) {
 // BRES (KHR layers whose whole filter is a few KB, i.e. 32->32): the weights are loaded once per CTA
 // into a resident region and the ring stages carry activations only - the layer is bound by the TMA
 // request rate on its 64-byte rows, and a third of those requests were weight re-loads.
-template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR, bool BRES = false>
+// UPS (BRES layers only): the conv input is the 2x bilinear upsample (align_corners=False) of a
+// low-resolution tensor.  Instead of a TMA load of a materialised upsampled tensor, eight producer
+// warps stage the tile's low-resolution neighbourhood as float32 in shared memory, interpolate every
+// pixel of the halo box once and write it (split-half, swizzled like the TMA would) into the three
+// kw-shifted boxes of three ring stages.  The upsampled tensor never exists in HBM.
+template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR, bool BRES = false, bool UPS = false>
 struct TcCfg {
   static constexpr int PLANES = MODE == MODE_F16X3 ? 2 : 1;
   static constexpr int ES = MODE == MODE_F16X3 ? 2 : 4;
+  static constexpr int KC_ = ROW_BYTES / ES;
   static constexpr int A_BYTES = (KHR ? 192 : 128) * ROW_BYTES;           // capacity; KHR boxes are <= 192 rows
   static constexpr int B_BYTES = (KHR ? 3 : 1) * BN * ROW_BYTES;
   static constexpr int STAGE = (A_BYTES + (BRES ? 0 : B_BYTES)) * PLANES;
@@ -128,8 +136,12 @@ struct TcCfg {
   static constexpr int OUT_ROW = 32 * ES;                                  // bytes per staged row (32 columns)
   static constexpr int OUT_BUF = TMA_STORE ? PLANES * 128 * OUT_ROW : 0;   // one staging buffer
   static constexpr int MISC = 1024 /*align*/ + 256 /*barriers*/ + BN * 8;
-  static constexpr int NST_RAW = (227 * 1024 - MISC - 2 * OUT_BUF - RES) / STAGE;
-  static constexpr int NST = NST_RAW > 8 ? 8 : NST_RAW;
+  static constexpr int UPS_WARPS = UPS ? 8 : 0;                            // interpolating producer warps
+  static constexpr int THREADS = 192 + 32 * UPS_WARPS;
+  static constexpr int LR_ROWS = 4, LR_COLS = 18;                          // low-res halo of a 4 x 32 pixel tile
+  static constexpr int LR_BYTES = UPS ? LR_ROWS * LR_COLS * KC_ * 4 : 0;   // float32 staging of that halo
+  static constexpr int NST_RAW = (227 * 1024 - MISC - 2 * OUT_BUF - RES - LR_BYTES) / STAGE;
+  static constexpr int NST = UPS ? 6 : (NST_RAW > 8 ? 8 : NST_RAW);        // UPS: two tiles x three kw boxes
   static constexpr int KC = ROW_BYTES / ES;                                // channels per K-step
   static constexpr int MMA_PER_TILE = ROW_BYTES / 32;                      // UMMA_K spans 32 bytes
   // Every MMA re-reads its 128 x 32 B slice of A from shared memory, which is what bounds the narrow
@@ -140,8 +152,9 @@ struct TcCfg {
   static constexpr bool STACK = MODE == MODE_F16X3;
   static constexpr int ACC_COLS = STACK ? 2 * BN : BN;                     // accumulator columns per buffer
   static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;  // two accumulator buffers
-  static constexpr int SMEM = NST * STAGE + 2 * OUT_BUF + RES + MISC;
-  static_assert(NST >= 2, "pipeline needs at least two stages");
+  static constexpr int SMEM = NST * STAGE + 2 * OUT_BUF + RES + LR_BYTES + MISC;
+  static_assert(NST >= 2 && NST <= NST_RAW, "pipeline needs at least two stages that fit in shared memory");
+  static_assert(!UPS || (KHR && BRES && MODE == MODE_F16X3), "UPS is a variant of the resident-filter kh-reuse kernel");
 };
 
 // tensor maps: a[src][plane] activations, b[plane] weights, o[plane] output (TMA_STORE only)
@@ -163,10 +176,10 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
 // Persistent kernel: each CTA walks tiles t = blockIdx.x, +gridDim.x, ...; the smem ring and its
 // phases run continuously across tiles, and two TMEM accumulator buffers let the MMA warp start
 // tile i+1 while the epilogue warps drain tile i.
-template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR, bool BRES = false>
-__global__ void __launch_bounds__(192, 1)
+template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR, bool BRES = false, bool UPS = false>
+__global__ void __launch_bounds__((TcCfg<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES, UPS>::THREADS), 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
-  using Cfg = TcCfg<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES>;
+  using Cfg = TcCfg<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES, UPS>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023) & ~1023u;
@@ -175,7 +188,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   const uint32_t stage_out = base + RING;                        // 2 staging buffers (TMA_STORE)
   uint8_t* stage_out_ptr = base_ptr + RING;
   const uint32_t res_b = base + RING + 2 * Cfg::OUT_BUF;         // resident weights (BRES)
-  constexpr int AFTER = RING + 2 * Cfg::OUT_BUF + Cfg::RES;
+  float* lr = reinterpret_cast<float*>(base_ptr + RING + 2 * Cfg::OUT_BUF + Cfg::RES);   // UPS: low-res halo, float32
+  constexpr int AFTER = RING + 2 * Cfg::OUT_BUF + Cfg::RES + Cfg::LR_BYTES;
   const uint32_t bars = base + AFTER;                            // full[NST], empty[NST], tfull[2], tempty[2], res
   const uint32_t bar_tfull = bars + 8 * (2 * Cfg::NST), bar_tempty = bar_tfull + 16, bar_res = bar_tempty + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + AFTER + 8 * (2 * Cfg::NST + 5));
@@ -190,7 +204,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < Cfg::NST; ++i) {
-      mbar_init(bars + 8 * i, 1);
+      mbar_init(bars + 8 * i, UPS ? Cfg::UPS_WARPS : 1);     // full: the TMA thread, or one arrival per producer warp
       mbar_init(bars + 8 * (Cfg::NST + i), 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -199,7 +213,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     }
     mbar_init(bar_res, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    tma_prefetch_desc(&maps.a[0][0]);
+    if (!UPS) tma_prefetch_desc(&maps.a[0][0]);
     tma_prefetch_desc(&maps.b[0]);
     if (TMA_STORE) tma_prefetch_desc(&maps.o[0]);
   }
@@ -227,7 +241,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         for (int kw = 0; kw < 3; ++kw)
           tma_load_4d(res_b + kw * Cfg::PLANES * Cfg::B_BYTES, &maps.b[0], bar_res, 0, 0, 0, kw);
       }
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = blockIdx.x; !UPS && t < p.total_tiles; t += gridDim.x) {
         const int nt = t % p.tiles_n, mt = t / p.tiles_n;
         const int grp = mt / tiles_per_group, trem = mt - grp * tiles_per_group;
         const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
@@ -324,7 +338,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         tc_commit(bar_tfull + 8 * buf);                // accumulator complete
       }
     }
-  } else {
+  } else if (warp < 6) {
     // ===================== epilogue (warps 2..5 <-> TMEM lane quarters) =====================
     const int q = warp & 3;                    // a warp may only touch TMEM lanes [32*(warp%4), +32)
     const int r = q * 32 + lane;               // accumulator row = pixel within the tile
@@ -469,6 +483,127 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       }
     }
     if (TMA_STORE && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else if (UPS) {
+    // ===================== interpolating producers (warps 6..13) =====================
+    // Tile = 4 x 32 output pixels of one image; its halo box covers input pixels Y = y0-1 .. y0+4,
+    // X = x0-1 .. x0+32 of the (virtual) upsampled tensor, which interpolate the low-res rows
+    // y0/2-1 .. y0/2+2 and columns x0/2-1 .. x0/2+16 (clamped at the borders).  The low-res halo of
+    // the NEXT tile is fetched into registers while this tile is interpolated, so the global-load
+    // latency is hidden.
+    constexpr int NT = UPS ? 32 * Cfg::UPS_WARPS : 32, C8 = Cfg::KC / 8, LC = Cfg::LR_COLS, LR = Cfg::LR_ROWS;
+    constexpr int BW = 32, BH = 4, BWX = BW + 2;
+    constexpr int LRI = LR * LC * C8;                 // 16-byte-pair items of the low-res halo
+    constexpr int LRK = (LRI + NT - 1) / NT;
+    // lr: two planes of float4 (channels 0-3 / 4-7 of every 8-channel chunk) so that a warp's
+    // 16-byte reads are contiguous (no bank conflicts)
+    float4* lrA = reinterpret_cast<float4*>(lr);
+    float4* lrB = lrA + LRI;
+    const int pt = threadIdx.x - 192;
+    const int lh = p.H >> 1, lw = p.W >> 1;
+    const __half* src_hi = reinterpret_cast<const __half*>(p.ups_src);
+    const __half* src_lo = src_hi + p.ups_plane;
+    uint4 pa[LRK], pb[LRK];
+    auto prefetch = [&](int t) {
+      const int grp = t / tiles_per_group, trem = t - grp * tiles_per_group;     // tiles_n == 1, BNI == 1
+      const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
+      const int ly0 = ((ty * BH) >> 1) - 1, lx0 = ((tx * BW) >> 1) - 1;
+#pragma unroll
+      for (int k = 0; k < LRK; ++k) {
+        const int i = pt + k * NT;
+        if (i < LRI) {
+          const int ch = i % C8, c = (i / C8) % LC, r = i / (C8 * LC);
+          const int yy = min(max(ly0 + r, 0), lh - 1), xx = min(max(lx0 + c, 0), lw - 1);
+          const size_t idx = (((size_t)grp * lh + yy) * lw + xx) * Cfg::KC + ch * 8;
+          pa[k] = __ldg(reinterpret_cast<const uint4*>(src_hi + idx));
+          pb[k] = __ldg(reinterpret_cast<const uint4*>(src_lo + idx));
+        }
+      }
+    };
+    if ((int)blockIdx.x < p.total_tiles) prefetch(blockIdx.x);
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, it += 3) {
+      const int grp = t / tiles_per_group, trem = t - grp * tiles_per_group;
+      const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
+      const int y0 = ty * BH, x0 = tx * BW;
+      const int ly0 = (y0 >> 1) - 1, lx0 = (x0 >> 1) - 1;
+      asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory");        // the previous tile no longer reads lr
+#pragma unroll
+      for (int k = 0; k < LRK; ++k) {
+        const int i = pt + k * NT;
+        if (i < LRI) {
+          const __half2* ah = reinterpret_cast<const __half2*>(&pa[k]);
+          const __half2* bh = reinterpret_cast<const __half2*>(&pb[k]);
+          float v[8];
+#pragma unroll
+          for (int tt = 0; tt < 4; ++tt) {
+            const float2 x = __half22float2(ah[tt]), y = __half22float2(bh[tt]);
+            v[2 * tt] = x.x + y.x; v[2 * tt + 1] = x.y + y.y;
+          }
+          lrA[i] = make_float4(v[0], v[1], v[2], v[3]);
+          lrB[i] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory");
+      if (t + (int)gridDim.x < p.total_tiles) prefetch(t + gridDim.x);
+      // the three ring stages of this tile (kw = 0, 1, 2) must have been consumed by the MMA warp
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const uint32_t j = it + kw;
+        mbar_wait(bars + 8 * (Cfg::NST + j % Cfg::NST), ((j / Cfg::NST) & 1) ^ 1);
+      }
+      const uint32_t st0 = it % Cfg::NST;                          // NST is a multiple of 3: stages st0, st0+1, st0+2
+      uint8_t* const sbase = base_ptr + st0 * Cfg::STAGE;
+#pragma unroll 1
+      for (int i = pt; i < (BH + 2) * BWX * C8; i += NT) {
+        const int ch = i % C8, px = i / C8;
+        const int by = px / BWX, bx = px - by * BWX;
+        const int Y = y0 - 1 + by, X = x0 - 1 + bx;
+        uint4 hi4 = make_uint4(0u, 0u, 0u, 0u), lo4 = hi4;
+        if (Y >= 0 && Y < p.H && X >= 0 && X < p.W) {
+          // F.interpolate(scale 2, bilinear, align_corners=False), same expression tree as upsample2x_kernel
+          const int y = Y >> 1, dy = Y & 1, x = X >> 1, dx = X & 1;
+          const float h1 = dy == 0 ? (y == 0 ? 1.f : 0.75f) : 0.25f, h0 = 1.f - h1;
+          const float w1 = dx == 0 ? (x == 0 ? 1.f : 0.75f) : 0.25f, w0 = 1.f - w1;
+          const int q = ((y - 1 + dy - ly0) * LC + (x - 1 + dx - lx0)) * C8 + ch;
+          const float4 a0 = lrA[q], a1 = lrB[q], b0 = lrA[q + C8], b1 = lrB[q + C8];
+          const float4 c0v = lrA[q + LC * C8], c1v = lrB[q + LC * C8], d0 = lrA[q + LC * C8 + C8], d1 = lrB[q + LC * C8 + C8];
+          float f[8];
+#define OFB_UP(A, B, Cc, D) (h0 * (w0 * (A) + w1 * (B)) + h1 * (w0 * (Cc) + w1 * (D)))
+          f[0] = OFB_UP(a0.x, b0.x, c0v.x, d0.x); f[1] = OFB_UP(a0.y, b0.y, c0v.y, d0.y);
+          f[2] = OFB_UP(a0.z, b0.z, c0v.z, d0.z); f[3] = OFB_UP(a0.w, b0.w, c0v.w, d0.w);
+          f[4] = OFB_UP(a1.x, b1.x, c1v.x, d1.x); f[5] = OFB_UP(a1.y, b1.y, c1v.y, d1.y);
+          f[6] = OFB_UP(a1.z, b1.z, c1v.z, d1.z); f[7] = OFB_UP(a1.w, b1.w, c1v.w, d1.w);
+#undef OFB_UP
+          __half2* hh = reinterpret_cast<__half2*>(&hi4);
+          __half2* ll = reinterpret_cast<__half2*>(&lo4);
+#pragma unroll
+          for (int tt = 0; tt < 4; ++tt) {
+            const __half2 h = __floats2half2_rn(f[2 * tt], f[2 * tt + 1]);
+            const float2 hf = __half22float2(h);
+            hh[tt] = h;
+            ll[tt] = __floats2half2_rn(f[2 * tt] - hf.x, f[2 * tt + 1] - hf.y);
+          }
+        }
+        // pixel column bx of the halo box is column bx - kw of the kw-shifted box
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int xx = bx - kw;
+          if (xx >= 0 && xx < BW) {
+            const int r = by * BW + xx;
+            uint8_t* dst = sbase + kw * Cfg::STAGE + r * ROW_BYTES +
+                           ((ROW_BYTES == 64 ? (ch ^ ((r >> 1) & 3)) : (ch ^ (r & 7))) << 4);
+            *reinterpret_cast<uint4*>(dst) = hi4;
+            *reinterpret_cast<uint4*>(dst + Cfg::A_BYTES) = lo4;
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) mbar_arrive(bars + 8 * (st0 + kw));
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -518,7 +653,14 @@ static int make_map(CUtensorMap* m, bool half, int rank, void* addr, const cuuin
 
 static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
+// 2x-upsample-fused variant: 32 -> 32 channels, 3x3 stride 1, split-half format, 32 x 4 pixel tiles
+static bool conv_tc_ups_supported(const ofb_conv_desc* d) {
+  return d->in_fmt == OFB_FMT_SPLIT16 && d->out_fmt == OFB_FMT_SPLIT16 && d->wgt_split && d->k == 3 && d->stride == 1 &&
+         d->pad == 1 && d->c0 == 32 && (!d->in1 || d->c1 == 0) && d->cout == 32 && d->w % 32 == 0 && d->h % 4 == 0;
+}
+
 bool conv_tc_supported(const ofb_conv_desc* d) {
+  if (d->ups2x) return conv_tc_ups_supported(d);
   if (d->in_fmt != d->out_fmt) return false;
   if (d->stride != 1 && d->stride != 2) return false;
   if (!((d->k == 3 && d->pad == 1) || (d->k == 1 && d->pad == 0))) return false;
@@ -550,22 +692,22 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR, bool BRES = false>
+template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR, bool BRES = false, bool UPS = false>
 static int launch_tc(const TcMaps& maps, const TcParams& p, cudaStream_t s) {
-  using Cfg = TcCfg<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES>;
+  using Cfg = TcCfg<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES, UPS>;
   static bool attr = false;
   if (!attr) {
-    OFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    OFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES, UPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr = true;
   }
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();      // persistent: one CTA per SM
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;
   cudaLaunchAttribute attr_pdl[1];
   attr_pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr_pdl[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr_pdl; cfg.numAttrs = g_pdl ? 1 : 0;
-  OFB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES>, maps, p));
+  OFB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES, UPS>, maps, p));
   OFB_LAUNCH_CHECK();
   return 0;
 }
@@ -577,6 +719,10 @@ static int launch_bn(int bn, bool khr, const TcMaps& maps, const TcParams& p, cu
     return launch_tc<128, MODE, ROW_BYTES, false, false>(maps, p, s);
   }
   if (MODE == MODE_F16X3 && khr) {
+    if (p.ups_src) {
+      if (ROW_BYTES == 64) return launch_tc<32, MODE_F16X3, 64, true, true, true, true>(maps, p, s);
+      OFB_CHECK(false, "conv_tc: fused upsample needs 64-byte rows");
+    }
     if (bn == 64) return launch_tc<64, MODE_F16X3, ROW_BYTES, true, true>(maps, p, s);
     // 32 -> 32 channels: the whole filter stays resident in shared memory
     if (ROW_BYTES == 64 && p.c0 + p.c1 == 32 && p.cout == 32) return launch_tc<32, MODE_F16X3, 64, true, true, true>(maps, p, s);
@@ -627,7 +773,12 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
   const int planes = split ? 2 : 1;
-  for (int src = 0; src < 2; ++src) {
+  if (d->ups2x) {
+    OFB_CHECK(khr && p.BW == 32 && p.BH == 4, "conv_tc: fused upsample needs 32x4 pixel tiles");
+    p.ups_src = d->in0;
+    p.ups_plane = (long long)d->n * (d->h / 2) * (d->w / 2) * d->c0;
+  }
+  for (int src = 0; src < 2 && !d->ups2x; ++src) {       // (the fused-upsample producers read in0 directly)
     const void* ptr = src == 0 ? d->in0 : d->in1;
     int c = src == 0 ? d->c0 : c1;
     if (!ptr || c == 0) { ptr = d->in0; c = d->c0; }      // unused map: keep it valid

@@ -45,6 +45,7 @@ int conv_dispatch(const ofb_conv_desc* d, cudaStream_t s) {
   // AUTO only picks the tensor-core engine where it is fp32-accurate (split-half operands);
   // its single-pass TF32 mode on float32 tensors must be requested explicitly
   if (d->engine == OFB_ENGINE_AUTO && d->in_fmt == OFB_FMT_SPLIT16 && conv_tc_supported(d)) return conv_tc(d, s);
+  OFB_CHECK(!d->ups2x, "conv: the fused 2x upsample exists only on the tcgen05 engine (split-half format, 32 -> 32 channels)");
   return conv_simt(d, s);
 }
 
@@ -80,6 +81,7 @@ struct ofb_handle {
   // workspace
   float* ws = nullptr; size_t ws_floats = 0; size_t ws_used = 0;
   int engine = OFB_ENGINE_AUTO, chunk = 0, dedup = 1;
+  int fuse_ups = 1;                // fold the last decoder upsample into de_conv4_0's operand producer
   int fmt = OFB_FMT_SPLIT16;       // activation storage inside the network
   bool patches_zeroed = false;      // row pads of the stem-layout patch buffer are zero
   int patches_imgs = 0;
@@ -384,8 +386,9 @@ static void conv_work(const ofb_conv_desc& d, double* flops, double* bytes) {
 }
 
 static int run_conv(Ctx& c, const ConvW& w, const float* in0, int c0, const float* in1, int c1, int hh, int ww,
-                    int stride, int pad, const float* residual, int act, float* out) {
+                    int stride, int pad, const float* residual, int act, float* out, int ups2x = 0) {
   ofb_conv_desc d{};
+  d.ups2x = ups2x;
   d.in0 = in0; d.in1 = in1; d.c0 = c0; d.c1 = c1; d.n = c.imgs; d.h = hh; d.w = ww;
   d.wgt = w.w; d.k = w.k; d.stride = stride; d.pad = pad; d.cout = w.cout;
   d.scale = w.scale; d.shift = w.shift; d.residual = residual; d.act = act; d.out = out;
@@ -394,8 +397,18 @@ static int run_conv(Ctx& c, const ConvW& w, const float* in0, int c0, const floa
   OFB_CHECK(w.w && w.cin == c0 + c1, "forward: conv weight/channel mismatch (%d vs %d+%d)", w.cin, c0, c1);
   double fl, by;
   conv_work(d, &fl, &by);
-  Prof pr(c.h, c.s, conv_class(d), fl, by);
+  if (ups2x) by -= 4.0 * 0.75 * (double)d.n * d.h * d.w * (d.c0 + d.c1);     // reads the low-resolution tensor
+  Prof pr(c.h, c.s, conv_class(d) + (ups2x ? "_ups" : ""), fl, by);
   return conv_dispatch(&d, c.s);
+}
+
+// can the 2x upsample in front of this conv be folded into its operand producer?
+static bool can_fuse_ups(ofb_handle* h, const ConvW& w, int n, int hh, int ww) {
+  if (!h->fuse_ups || h->fmt != OFB_FMT_SPLIT16 || h->engine == OFB_ENGINE_SIMT) return false;
+  ofb_conv_desc d{};
+  d.ups2x = 1; d.c0 = w.cin; d.n = n; d.h = hh; d.w = ww; d.k = w.k; d.stride = 1; d.pad = 1; d.cout = w.cout;
+  d.in_fmt = d.out_fmt = h->fmt; d.wgt_split = w.ws;
+  return conv_tc_supported(&d);
 }
 
 static int run_linear(Ctx& c, const ConvW& w, const float* in, const float* residual, int act, float* out) {
@@ -538,9 +551,13 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
     if (ofb_upsample2x_f32(b.d21, nullptr, imgs, p4, p4, 64, b.up3, F, vs)) return -1; }
     if (run_conv(c, h->conv["de_conv3_0"], b.up3, 64, nullptr, 0, P / 2, P / 2, 1, 1, nullptr, OFB_ACT_RELU, b.d30)) return -1;
     if (run_conv(c, h->conv["de_conv3_1"], b.d30, 64, b.conv1, 64, P / 2, P / 2, 1, 1, nullptr, OFB_ACT_RELU, b.d31)) return -1;
-    { Prof pr(h, s, "upsample2x_c32", 0.0, 4.0*5.0*(double)imgs*(P / 2)*(P / 2)*32);
-    if (ofb_upsample2x_f32(b.d31, nullptr, imgs, P / 2, P / 2, 32, b.up4, F, vs)) return -1; }
-    if (run_conv(c, h->conv["de_conv4_0"], b.up4, 32, nullptr, 0, P, P, 1, 1, nullptr, OFB_ACT_RELU, b.d40)) return -1;
+    if (can_fuse_ups(h, h->conv["de_conv4_0"], imgs, P, P)) {
+      if (run_conv(c, h->conv["de_conv4_0"], b.d31, 32, nullptr, 0, P, P, 1, 1, nullptr, OFB_ACT_RELU, b.d40, 1)) return -1;
+    } else {
+      { Prof pr(h, s, "upsample2x_c32", 0.0, 4.0*5.0*(double)imgs*(P / 2)*(P / 2)*32);
+      if (ofb_upsample2x_f32(b.d31, nullptr, imgs, P / 2, P / 2, 32, b.up4, F, vs)) return -1; }
+      if (run_conv(c, h->conv["de_conv4_0"], b.up4, 32, nullptr, 0, P, P, 1, 1, nullptr, OFB_ACT_RELU, b.d40)) return -1;
+    }
 
     // heads + ERP merge (:371-380)
     { Prof pr(h, s, "heads", 0.0, 4.0*((double)imgs*P*P*34));
@@ -645,6 +662,7 @@ extern "C" int ofb_set_option(ofb_handle* h, const char* key, int value) {
   if (!strcmp(key, "engine")) h->engine = value;
   else if (!strcmp(key, "chunk")) h->chunk = value;
   else if (!strcmp(key, "dedup")) h->dedup = value;
+  else if (!strcmp(key, "fuse_ups")) h->fuse_ups = value;
   else if (!strcmp(key, "pdl")) conv_tc_set_pdl(value != 0);     // process-wide: programmatic dependent launch
   else if (!strcmp(key, "store128")) conv_tc_set_store128(value != 0);
   else if (!strcmp(key, "format")) {

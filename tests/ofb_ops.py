@@ -171,9 +171,12 @@ def weight_scale(w):
 
 
 def conv_fmt(in0, wgt, k, stride, pad, in1=None, scale=None, shift=None, residual=None, act=0, engine=0,
-             in_fmt=0, out_fmt=0):
-    """conv with explicit storage formats: float32 NHWC tensors in, converted to/from split planes here."""
+             in_fmt=0, out_fmt=0, ups2x=0):
+    """conv with explicit storage formats: float32 NHWC tensors in, converted to/from split planes here.
+    ups2x: in0 is the low-resolution tensor, bilinearly upsampled x2 inside the conv kernel."""
     n, h, w, c0 = in0.shape
+    if ups2x:
+        h, w = 2 * h, 2 * w
     cout = wgt.shape[0]
     oh = (h + 2 * pad - k) // stride + 1
     ow = (w + 2 * pad - k) // stride + 1
@@ -199,5 +202,6 @@ def conv_fmt(in0, wgt, k, stride, pad, in1=None, scale=None, shift=None, residua
     out = torch.empty(2 * numel, dtype=torch.float16, device=in0.device) if out_fmt == 1 else \
         torch.empty((n, oh, ow, cout), device=in0.device)
     d.act, d.out, d.engine, d.in_fmt, d.out_fmt = act, out.data_ptr(), engine, in_fmt, out_fmt
+    d.ups2x = ups2x
     ck(L().ofb_conv_f32(C.byref(d), _st(in0)))
     return merge16(out, (n, oh, ow, cout)) if out_fmt == 1 else out

@@ -138,3 +138,44 @@ def test_stem_on_tensor_cores_matches_fp32():
     err = (got - ref).abs()
     print(f"[parity] stem_tc: max_abs_err={err.max().item():.3e} ref_absmax={ref.abs().max().item():.3e}")
     assert (err <= 3e-5 + 3e-5 * ref.abs()).all()
+
+
+@pytest.mark.parametrize("n,hw", [(1, 64), (3, 16), (2, 32)])
+def test_conv_tc_fused_upsample_matches_interpolate_then_conv(n, hw):
+    """de_conv4_0 with the decoder's last F.interpolate(x2, bilinear, align_corners=False) folded into the
+    conv's operand producer (ofb_conv_desc.ups2x): against torch-CPU fp32, and against libofb's own
+    unfused upsample2x kernel + conv (same expression tree, same accumulation order)."""
+    o = ops()
+    x = rand(n, 32, hw, hw, seed=11)
+    w = rand(32, 32, 3, 3, seed=12, scale=(1.0 / (32 * 9)) ** 0.5)
+    scale = 0.5 + torch.rand(32, generator=torch.Generator().manual_seed(13))
+    shift = rand(32, seed=14, scale=0.1)
+    up = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+    ref = F.relu(F.conv2d(up, w, None, 1, 1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    xd, wd, sd, td = o.nhwc(x).to(DEV), o.ohwi(w).to(DEV), scale.to(DEV), shift.to(DEV)
+    fused = o.conv_fmt(xd, wd, 3, 1, 1, scale=sd, shift=td, act=1, engine=_lib.ENGINE_TC,
+                       in_fmt=_lib.FMT_SPLIT16, out_fmt=_lib.FMT_SPLIT16, ups2x=1)
+    # unfused: upsample kernel on split-half planes, then the same conv kernel family
+    up_planes = torch.empty(2 * n * 4 * hw * hw * 32, dtype=torch.float16, device=DEV)
+    xs = o.split16(xd)
+    _lib.check(_lib.lib().ofb_upsample2x_f32(_lib.ptr(xs), None, n, hw, hw, 32, _lib.ptr(up_planes), 1,
+                                              _lib.stream_of(torch.device(DEV))))
+    up_f32 = o.merge16(up_planes, (n, 2 * hw, 2 * hw, 32))
+    unfused = o.conv_fmt(up_f32, wd, 3, 1, 1, scale=sd, shift=td, act=1, engine=_lib.ENGINE_TC,
+                         in_fmt=_lib.FMT_SPLIT16, out_fmt=_lib.FMT_SPLIT16)
+    torch.cuda.synchronize()
+    got = o.nchw(fused.cpu())
+    err = (got - ref).abs()
+    d2 = (fused - unfused).abs().max().item()
+    print(f"[parity] conv_tc fused upsample n={n} {hw}->{2 * hw}: max_abs_err={err.max().item():.3e} "
+          f"ref_absmax={ref.abs().max().item():.3e} vs unfused libofb path max diff {d2:.3e}")
+    assert (err <= 1.5e-4 + 5e-5 * ref.abs()).all()
+    assert d2 <= 2e-6
+
+
+def test_conv_fused_upsample_rejected_by_cuda_core_engine():
+    o = ops()
+    x = o.nhwc(rand(1, 32, 16, 16, seed=1)).to(DEV)
+    w = o.ohwi(rand(32, 32, 3, 3, seed=2)).to(DEV)
+    with pytest.raises(_lib.OfbError):
+        o.conv_fmt(x, w, 3, 1, 1, engine=_lib.ENGINE_SIMT, in_fmt=_lib.FMT_SPLIT16, out_fmt=_lib.FMT_SPLIT16, ups2x=1)

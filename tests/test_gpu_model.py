@@ -146,6 +146,14 @@ def test_batch_invariance_chunking_dedup_and_graph(fmt):
         full = net(rgb, iter=2, confidence=True)
         assert torch.equal(full[1], base[1]), "re-using the iteration-invariant stem must not change results"
         net.set_option("dedup", 1)
+        if FORMATS[fmt] == 1:
+            # the last decoder upsample is folded into de_conv4_0's operand producer; unfused must agree
+            net.set_option("fuse_ups", 0)
+            unfused = net(rgb, iter=2, confidence=True)
+            net.set_option("fuse_ups", 1)
+            d = ((unfused[1] - base[1]).abs() / base[1].abs().clamp_min(1e-6)).max().item()
+            print(f"[parity] fused vs materialised upsample: depth max rel diff {d:.3e}")
+            assert d <= 2e-6
         g = net.forward_graphed(rgb, 2, True)
         assert torch.equal(g[1], base[1])
         g2 = net.forward_graphed(rgb.flip(0).contiguous(), 2, True)
