@@ -36,6 +36,9 @@ struct TcParams {
   int tiles_n, total_tiles;
   const void* ups_src;   // UPS: low-resolution input (n_img, H/2, W/2, c0), split-half planes
   long long ups_plane;   // elements per plane of ups_src
+  int dbg;               // timing experiments only (results are wrong): 1 skip lo*Whi MMA, 2 skip stacked MMA,
+                         // 4 skip weight loads, 8 skip activation loads, 16 record clock stamps of CTA 0
+  long long* dbg_buf;    // dbg & 16: [role 0 producer / 1 MMA][step][4] clock64 stamps
 };
 
 // ------------------------------------------------------------------ PTX wrappers (mbarrier: ptx.cuh)
@@ -52,6 +55,41 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// cta_group::2 variants: both CTAs of a pair load into their own shared memory, the transaction bytes are
+// counted on the LEADER CTA's mbarrier (shared::cluster address with the CTA-rank bit cleared)
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n.reg .b32 ra;\nmapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n}\n" ::"r"(bar), "r"(rank) : "memory");
+}
+// tcgen05.commit of a CTA pair: arrives on the barrier at this offset in both CTAs
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -60,9 +98,14 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-template <int MODE>
+template <int MODE, bool CTA2 = false>
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  if (MODE == MODE_TF32) {
+  if (CTA2) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+  } else if (MODE == MODE_TF32) {
     asm volatile(
         "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
@@ -124,13 +167,19 @@ __device__ __forceinline__ float act_fn(float v, int act) {
 // warps stage the tile's low-resolution neighbourhood as float32 in shared memory, interpolate every
 // pixel of the halo box once and write it (split-half, swizzled like the TMA would) into the three
 // kw-shifted boxes of three ring stages.  The upsampled tensor never exists in HBM.
-template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR, bool BRES = false, bool UPS = false>
+// CTA2 (BN = 128 tiles, F16X3): a cluster of two CTAs computes two adjacent M tiles of the same N tile with
+// cta_group::2 MMAs (M = 256).  Each CTA stages its own activation tile but only HALF of the weight tile
+// (rank r holds [Whi rows 64r..64r+63 ; Wlo rows 64(1-r)..]), so the weight traffic from L2 and the
+// shared-memory reads of the B operand per SM are halved - the mid layers are bound by exactly that.
+// Accumulator columns (per CTA, 128 lanes = its own 128 pixels): [0,64) hi*Whi[0:64] + lo*Whi[0:64],
+// [64,128) hi*Wlo[64:128] + lo*Whi[64:128], [128,192) hi*Whi[64:128], [192,256) hi*Wlo[0:64].
+template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR, bool BRES = false, bool UPS = false, bool CTA2 = false>
 struct TcCfg {
   static constexpr int PLANES = MODE == MODE_F16X3 ? 2 : 1;
   static constexpr int ES = MODE == MODE_F16X3 ? 2 : 4;
   static constexpr int KC_ = ROW_BYTES / ES;
   static constexpr int A_BYTES = (KHR ? 192 : 128) * ROW_BYTES;           // capacity; KHR boxes are <= 192 rows
-  static constexpr int B_BYTES = (KHR ? 3 : 1) * BN * ROW_BYTES;
+  static constexpr int B_BYTES = (KHR ? 3 : 1) * (CTA2 ? BN / 2 : BN) * ROW_BYTES;
   static constexpr int STAGE = (A_BYTES + (BRES ? 0 : B_BYTES)) * PLANES;
   static constexpr int RES = BRES ? 3 * PLANES * B_BYTES : 0;               // resident weights (all 3 kw)
   static constexpr int OUT_ROW = 32 * ES;                                  // bytes per staged row (32 columns)
@@ -155,6 +204,7 @@ struct TcCfg {
   static constexpr int SMEM = NST * STAGE + 2 * OUT_BUF + RES + LR_BYTES + MISC;
   static_assert(NST >= 2 && NST <= NST_RAW, "pipeline needs at least two stages that fit in shared memory");
   static_assert(!UPS || (KHR && BRES && MODE == MODE_F16X3), "UPS is a variant of the resident-filter kh-reuse kernel");
+  static_assert(!CTA2 || (BN == 128 && MODE == MODE_F16X3 && !KHR && !BRES && !UPS), "CTA2 is a variant of the plain 128-wide F16X3 kernel");
 };
 
 // tensor maps: a[src][plane] activations, b[plane] weights, o[plane] output (TMA_STORE only)
@@ -176,10 +226,10 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
 // Persistent kernel: each CTA walks tiles t = blockIdx.x, +gridDim.x, ...; the smem ring and its
 // phases run continuously across tiles, and two TMEM accumulator buffers let the MMA warp start
 // tile i+1 while the epilogue warps drain tile i.
-template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR, bool BRES = false, bool UPS = false>
-__global__ void __launch_bounds__((TcCfg<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES, UPS>::THREADS), 1)
+template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR, bool BRES = false, bool UPS = false, bool CTA2 = false>
+__global__ void __launch_bounds__((TcCfg<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES, UPS, CTA2>::THREADS), 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
-  using Cfg = TcCfg<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES, UPS>;
+  using Cfg = TcCfg<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES, UPS, CTA2>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023) & ~1023u;
@@ -197,6 +247,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   float* s_shift = s_scale + BN;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // CTA2: cluster c = blockIdx.x / 2 walks pair-tiles; CTA rank r takes M tile 2*mp + r of pair-tile (mp, nt)
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const int tile0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int cin = p.c0 + p.c1;
   const int cchunks = cin / Cfg::KC;
   const int ksteps = (KHR ? 3 : p.taps) * cchunks;
@@ -209,7 +262,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, 4);          // one arrival per epilogue warp
+      mbar_init(bar_tempty + 8 * i, CTA2 ? 8 : 4);   // one arrival per epilogue warp (of both CTAs of a pair)
     }
     mbar_init(bar_res, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -218,12 +271,19 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     if (TMA_STORE) tma_prefetch_desc(&maps.o[0]);
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTA2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();          // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
@@ -235,106 +295,152 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t it = 0;
       if (BRES) {      // the whole filter (3 kw x all kh x cin x cout, both planes) once per CTA
         mbar_expect_tx(bar_res, Cfg::RES);
         for (int kw = 0; kw < 3; ++kw)
           tma_load_4d(res_b + kw * Cfg::PLANES * Cfg::B_BYTES, &maps.b[0], bar_res, 0, 0, 0, kw);
       }
-      for (int t = blockIdx.x; !UPS && t < p.total_tiles; t += gridDim.x) {
-        const int nt = t % p.tiles_n, mt = t / p.tiles_n;
+      // (everything below runs on ONE thread per K-step: no divisions, ring stage / phase advanced incrementally)
+      uint32_t st = 0, ph = 0;
+      int dstep = 0;
+      const int ntap = KHR ? 3 : p.taps;
+      for (int t = tile0; !UPS && t < p.total_tiles; t += tile_step) {
+        const int nt = t % p.tiles_n, mt = CTA2 ? 2 * (t / p.tiles_n) + (int)rank : t / p.tiles_n;
         const int grp = mt / tiles_per_group, trem = mt - grp * tiles_per_group;
         const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
         const int img0 = grp * p.BNI, y0 = ty * p.BH, x0 = tx * p.BW, n0 = nt * BN;
-        for (int ks = 0; ks < ksteps; ++ks, ++it) {
-          const int st = it % Cfg::NST;
-          const uint32_t ph = (it / Cfg::NST) & 1;
-          mbar_wait(bars + 8 * (Cfg::NST + st), ph ^ 1);
-          const int tap = ks / cchunks, cq = ks - tap * cchunks;
-          const int kh = tap / p.kdiv, kw = tap - kh * p.kdiv;
-          int c = cq * Cfg::KC;
-          int src = 0;
-          if (c >= p.c0) { src = 1; c -= p.c0; }
-          const uint32_t full = bars + 8 * st;
-          const uint32_t sa = base + st * Cfg::STAGE;
-          const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
-          if (KHR) {
-            // here `tap` is kw; the box carries rows y0-1 .. y0+BH, the weights all three kh
-            mbar_expect_tx(full, (uint32_t)(Cfg::PLANES * ((p.BH + 2) * p.BW * ROW_BYTES + (BRES ? 0 : Cfg::B_BYTES))));
-#pragma unroll
-            for (int pl = 0; pl < Cfg::PLANES; ++pl)
-              tma_load_4d(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, x0 + tap - 1, y0 - 1, img0);
-            // one box = {kc, stacked [Whi; Wlo] rows, all 3 kh, this kw}
-            if (!BRES) tma_load_4d(sb, &maps.b[0], full, cq * Cfg::KC, 0, 0, tap);
-          } else {
-            mbar_expect_tx(full, Cfg::STAGE);
-#pragma unroll
-            for (int pl = 0; pl < Cfg::PLANES; ++pl) {
-              tma_load_4d(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, x0 * p.sx + kw - p.padx,
-                          y0 * p.sy + kh - p.pady, img0);
-              tma_load_2d(sb + pl * Cfg::B_BYTES, &maps.b[pl], full, tap * cin + cq * Cfg::KC, n0);
+        int kh = 0, kw = 0;
+        for (int tap = 0; tap < ntap; ++tap) {
+          // KHR: `tap` is kw; the box carries rows y0-1 .. y0+BH, the weights all three kh
+          const int cx = KHR ? x0 + tap - 1 : x0 * p.sx + kw - p.padx;
+          const int cy = KHR ? y0 - 1 : y0 * p.sy + kh - p.pady;
+          const int wk = tap * cin;
+          for (int cq = 0; cq < cchunks; ++cq) {
+            int c = cq * Cfg::KC;
+            int src = 0;
+            if (c >= p.c0) { src = 1; c -= p.c0; }
+            const uint32_t full = bars + 8 * st;
+            const uint32_t sa = base + st * Cfg::STAGE;
+            const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
+            long long tw0 = 0;
+            if ((p.dbg & 16) && blockIdx.x == 0) tw0 = clock64();
+            mbar_wait(bars + 8 * (Cfg::NST + st), ph ^ 1);
+            if ((p.dbg & 16) && blockIdx.x == 0 && dstep < 4096) {
+              p.dbg_buf[(0 * 4096 + dstep) * 4 + 0] = tw0; p.dbg_buf[(0 * 4096 + dstep) * 4 + 1] = clock64();
             }
+            if (KHR) {
+              mbar_expect_tx(full, (uint32_t)(Cfg::PLANES * ((p.BH + 2) * p.BW * ROW_BYTES + (BRES ? 0 : Cfg::B_BYTES))));
+#pragma unroll
+              for (int pl = 0; pl < Cfg::PLANES; ++pl)
+                tma_load_4d(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, cx, cy, img0);
+              // one box = {kc, stacked [Whi; Wlo] rows, all 3 kh, this kw}
+              if (!BRES) tma_load_4d(sb, &maps.b[0], full, cq * Cfg::KC, 0, 0, tap);
+            } else if (CTA2) {
+              const uint32_t nb = Cfg::PLANES * ((p.dbg & 8 ? 0 : Cfg::A_BYTES) + (p.dbg & 4 ? 0 : Cfg::B_BYTES));
+              if (rank == 0) mbar_expect_tx(full, 2 * nb);      // both CTAs' bytes land on the leader's barrier
+#pragma unroll
+              for (int pl = 0; pl < Cfg::PLANES; ++pl) {
+                if (!(p.dbg & 8)) tma_load_4d_2sm(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, cx, cy, img0);
+                // rank r: [Whi rows 64r.. ; Wlo rows 64(1-r)..]
+                if (!(p.dbg & 4))
+                  tma_load_2d_2sm(sb + pl * Cfg::B_BYTES, &maps.b[pl], full, wk + cq * Cfg::KC,
+                                  n0 + (BN / 2) * (pl == 0 ? (int)rank : 1 - (int)rank));
+              }
+            } else {
+              mbar_expect_tx(full, Cfg::PLANES * ((p.dbg & 8 ? 0 : Cfg::A_BYTES) + (p.dbg & 4 ? 0 : Cfg::B_BYTES)));
+#pragma unroll
+              for (int pl = 0; pl < Cfg::PLANES; ++pl) {
+                if (!(p.dbg & 8)) tma_load_4d(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, cx, cy, img0);
+                if (!(p.dbg & 4)) tma_load_2d(sb + pl * Cfg::B_BYTES, &maps.b[pl], full, wk + cq * Cfg::KC, n0);
+              }
+            }
+            if ((p.dbg & 16) && blockIdx.x == 0 && dstep < 4096) p.dbg_buf[(0 * 4096 + dstep) * 4 + 2] = clock64();
+            ++dstep;
+            if (++st == Cfg::NST) { st = 0; ph ^= 1; }
           }
+          if (++kw == p.kdiv) { kw = 0; ++kh; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (bit 4), a/b format
       // (bits 7/10: 0 = F16, 2 = TF32), K-major A and B, N >> 3 at bit 17, M >> 4 at bit 24.
       const uint32_t fmt = MODE == MODE_TF32 ? 2u : 0u;
-      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
-      uint32_t it = 0, i = 0;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | (((CTA2 ? 256u : 128u) >> 4) << 24);
+      uint32_t st = 0, ph = 0, i = 0;
+      int dstep = 0;
+      const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * BN) >> 3) << 17);   // N = 2*BN
+      const uint32_t idesc64 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(64 >> 3) << 17);        // N = 64
+      const uint64_t dconst = umma_desc<ROW_BYTES>(0);            // descriptor without the start address
       if (BRES) mbar_wait(bar_res, 0);
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
+      for (int t = tile0; t < p.total_tiles; t += tile_step, ++i) {
         const uint32_t buf = i & 1;
         mbar_wait(bar_tempty + 8 * buf, ((i >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t acc = tmem + buf * Cfg::ACC_COLS;
-        for (int ks = 0; ks < ksteps; ++ks, ++it) {
-          const int st = it % Cfg::NST;
-          const uint32_t ph = (it / Cfg::NST) & 1;
+        // Column grouping of the three products, identical in every tile configuration so that results do
+        // not depend on the tile choice (which follows the batch size): within each block of 128 output
+        // channels, channels [0,64) accumulate hi*Whi + lo*Whi in one column and hi*Wlo in the other;
+        // channels [64,128) accumulate hi*Wlo + lo*Whi in one column and hi*Whi in the other (that is
+        // what the cta_group::2 operand split produces); the epilogue adds the two columns.
+        const bool upper = !CTA2 && BN < 128 && (((t % p.tiles_n) * BN) & 64) != 0;
+        const uint32_t acc_lo = acc + (upper ? BN : 0);           // where lo*Whi accumulates
+        for (int ks = 0; ks < ksteps; ++ks) {
+          long long tw0 = 0;
+          if ((p.dbg & 16) && blockIdx.x == 0) tw0 = clock64();
           mbar_wait(bars + 8 * st, ph);
           tc_fence_after();
+          if ((p.dbg & 16) && blockIdx.x == 0 && dstep < 4096) {
+            p.dbg_buf[(1 * 4096 + dstep) * 4 + 0] = tw0; p.dbg_buf[(1 * 4096 + dstep) * 4 + 1] = clock64();
+          }
           const uint32_t sa = base + st * Cfg::STAGE;
           // BRES: one K-step per kw (cin == KC), its weights sit in the resident region
           const uint32_t sb = BRES ? res_b + (uint32_t)(ks * Cfg::PLANES * Cfg::B_BYTES) : sa + Cfg::PLANES * Cfg::A_BYTES;
-          const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * BN) >> 3) << 17);   // N = 2*BN
           if (KHR) {
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
               // tap kh reads the halo box kh image rows further down; weights: [kh][Whi rows; Wlo rows]
               const uint32_t ao = (uint32_t)(kh * p.BW * ROW_BYTES), bo = (uint32_t)(kh * 2 * BN * ROW_BYTES);
-              const uint64_t a_hi = umma_desc<ROW_BYTES>(sa + ao), a_lo = umma_desc<ROW_BYTES>(sa + Cfg::A_BYTES + ao);
-              const uint64_t b_st = umma_desc<ROW_BYTES>(sb + bo);
+              const uint64_t a_hi = dconst | (((sa + ao) >> 4) & 0x3FFF), a_lo = dconst | (((sa + Cfg::A_BYTES + ao) >> 4) & 0x3FFF);
+              const uint64_t b_st = dconst | (((sb + bo) >> 4) & 0x3FFF);
 #pragma unroll
               for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk) {
                 tc_mma<MODE>(acc, a_hi + 2 * kk, b_st + 2 * kk, idesc2, (ks | kh | kk) != 0);   // hi*Whi | hi*Wlo
-                tc_mma<MODE>(acc, a_lo + 2 * kk, b_st + 2 * kk, idesc, 1);                     // + lo*Whi
+                tc_mma<MODE>(acc_lo, a_lo + 2 * kk, b_st + 2 * kk, idesc, 1);                  // + lo*Whi
               }
             }
-          } else
-#pragma unroll
-          for (int kh = 0; kh < 1; ++kh) {
-            const uint32_t ao = 0u, bo = 0u;
-            const uint64_t a_hi = umma_desc<ROW_BYTES>(sa + ao), b_hi = umma_desc<ROW_BYTES>(sb + bo);
+          } else {
+            const uint64_t a_hi = dconst | ((sa >> 4) & 0x3FFF), b_hi = dconst | ((sb >> 4) & 0x3FFF);
             if (MODE == MODE_TF32) {
 #pragma unroll
               for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk)
-                tc_mma<MODE>(acc, a_hi + 2 * kk, b_hi + 2 * kk, idesc, (ks | kh | kk) != 0);
+                tc_mma<MODE>(acc, a_hi + 2 * kk, b_hi + 2 * kk, idesc, (ks | kk) != 0);
             } else {
               // sb holds [Whi rows][Wlo rows] back to back = the stacked operand
-              const uint64_t a_lo = umma_desc<ROW_BYTES>(sa + Cfg::A_BYTES + ao);
+              const uint64_t a_lo = dconst | (((sa + Cfg::A_BYTES) >> 4) & 0x3FFF);
 #pragma unroll
               for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk) {
-                tc_mma<MODE>(acc, a_hi + 2 * kk, b_hi + 2 * kk, idesc2, (ks | kh | kk) != 0);   // hi*Whi | hi*Wlo
-                tc_mma<MODE>(acc, a_lo + 2 * kk, b_hi + 2 * kk, idesc, 1);                     // + lo*Whi
+                if (!(p.dbg & 2)) tc_mma<MODE, CTA2>(acc, a_hi + 2 * kk, b_hi + 2 * kk, idesc2, (ks | kk) != 0);   // hi*Whi | hi*Wlo
+                if (p.dbg & 1) continue;
+                if (!CTA2 && BN == 128) {
+                  // + lo*Whi: channels [0,64) onto the hi*Whi columns, [64,128) onto the hi*Wlo columns
+                  tc_mma<MODE>(acc, a_lo + 2 * kk, b_hi + 2 * kk, idesc64, 1);
+                  tc_mma<MODE>(acc + BN + 64, a_lo + 2 * kk, b_hi + ((64 * ROW_BYTES) >> 4) + 2 * kk, idesc64, 1);
+                } else {
+                  tc_mma<MODE, CTA2>(acc_lo, a_lo + 2 * kk, b_hi + 2 * kk, idesc, 1);
+                }
               }
             }
           }
+          if (CTA2) tc_commit_2sm(bars + 8 * (Cfg::NST + st)); else
           tc_commit(bars + 8 * (Cfg::NST + st));       // frees this smem stage when the MMAs retire
+          if ((p.dbg & 16) && blockIdx.x == 0 && dstep < 4096) p.dbg_buf[(1 * 4096 + dstep) * 4 + 2] = clock64();
+          ++dstep;
+          if (++st == Cfg::NST) { st = 0; ph ^= 1; }
         }
+        if (CTA2) tc_commit_2sm(bar_tfull + 8 * buf); else
         tc_commit(bar_tfull + 8 * buf);                // accumulator complete
       }
     }
@@ -346,8 +452,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     const int et = threadIdx.x - 64;           // 0..127
     int last_n0 = -1;
     uint32_t i = 0, chunk_ctr = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
-      const int nt = t % p.tiles_n, mt = t / p.tiles_n;
+    for (int t = tile0; t < p.total_tiles; t += tile_step, ++i) {
+      const int nt = t % p.tiles_n, mt = CTA2 ? 2 * (t / p.tiles_n) + (int)rank : t / p.tiles_n;
       const int grp = mt / tiles_per_group, trem = mt - grp * tiles_per_group;
       const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
       const int img0 = grp * p.BNI, y0 = ty * p.BH, x0 = tx * p.BW, n0 = nt * BN;
@@ -373,14 +479,18 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * Cfg::ACC_COLS + cb, v);
         if (Cfg::STACK) {                        // second column block (hi*Wlo) of the stacked accumulator
           uint32_t v2[32];
-          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * Cfg::ACC_COLS + BN + cb, v2);
+          // CTA2: see the column map above TcCfg
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * Cfg::ACC_COLS + (CTA2 ? (cb < 64 ? 192 : 64) : BN) + cb, v2);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
         }
         if (cb + 32 >= BN) {                     // accumulator fully read: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+          if (lane == 0) {
+            if (CTA2 && rank != 0) mbar_arrive_remote(bar_tempty + 8 * buf, 0);
+            else mbar_arrive(bar_tempty + 8 * buf);
+          }
         }
         float f[32];
 #pragma unroll
@@ -607,9 +717,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();          // the leader's MMAs read the peer's shared memory until the very end
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    if (CTA2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
   }
 }
 
@@ -678,6 +790,15 @@ bool conv_tc_supported(const ofb_conv_desc* d) {
 
 static bool g_pdl = true;      // programmatic dependent launch for the tensor-core kernels
 static bool g_store128 = true;  // bulk-tensor-store epilogue also for the 128-wide tiles
+static bool g_cta2 = true;      // cta_group::2 CTA pairs for the 128-wide split-half tiles
+void conv_tc_set_cta2(bool on) { g_cta2 = on; }
+static int g_dbg = 0;           // TcParams::dbg (timing experiments)
+static long long* g_dbg_buf = nullptr;
+void conv_tc_set_debug(int v) { g_dbg = v; }
+long long* conv_tc_debug_buffer() {
+  if (!g_dbg_buf) cudaMalloc(&g_dbg_buf, 2 * 4096 * 4 * sizeof(long long));
+  return g_dbg_buf;
+}
 void conv_tc_set_pdl(bool on) { g_pdl = on; }
 void conv_tc_set_store128(bool on) { g_store128 = on; }
 
@@ -692,28 +813,46 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR, bool BRES = false, bool UPS = false>
+template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR, bool BRES = false, bool UPS = false, bool CTA2 = false>
 static int launch_tc(const TcMaps& maps, const TcParams& p, cudaStream_t s) {
-  using Cfg = TcCfg<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES, UPS>;
+  using Cfg = TcCfg<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES, UPS, CTA2>;
   static bool attr = false;
   if (!attr) {
-    OFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES, UPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    OFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES, UPS, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr = true;
   }
-  int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();      // persistent: one CTA per SM
+  // persistent: one CTA per SM (CTA2: one CTA pair per TPC, total_tiles counts pair-tiles)
+  const int units = CTA2 ? num_sms() / 2 : num_sms();
+  int grid = (p.total_tiles < units ? p.total_tiles : units) * (CTA2 ? 2 : 1);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;
-  cudaLaunchAttribute attr_pdl[1];
-  attr_pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr_pdl[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr_pdl; cfg.numAttrs = g_pdl ? 1 : 0;
-  OFB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES, UPS>, maps, p));
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
+  if (g_pdl) {
+    attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (CTA2) {
+    attrs[na].id = cudaLaunchAttributeClusterDimension;
+    attrs[na].val.clusterDim.x = 2; attrs[na].val.clusterDim.y = 1; attrs[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attrs; cfg.numAttrs = na;
+  OFB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES, UPS, CTA2>, maps, p));
   OFB_LAUNCH_CHECK();
   return 0;
 }
 
 template <int MODE, int ROW_BYTES>
-static int launch_bn(int bn, bool khr, const TcMaps& maps, const TcParams& p, cudaStream_t s) {
+static int launch_bn(int bn, bool khr, bool cta2, const TcMaps& maps, const TcParams& p, cudaStream_t s) {
+  if (bn == 128 && cta2) {
+    if (MODE == MODE_F16X3 && ROW_BYTES == 128) {
+      if (g_store128) return launch_tc<128, MODE_F16X3, 128, true, false, false, false, true>(maps, p, s);
+      return launch_tc<128, MODE_F16X3, 128, false, false, false, false, true>(maps, p, s);
+    }
+    OFB_CHECK(false, "conv_tc: CTA pairs need split-half operands with 128-byte rows");
+  }
   if (bn == 128) {
     if (g_store128) return launch_tc<128, MODE, ROW_BYTES, true, false>(maps, p, s);
     return launch_tc<128, MODE, ROW_BYTES, false, false>(maps, p, s);
@@ -752,6 +891,8 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
   p.scale = d->scale; p.shift = d->shift; p.wscale = split ? d->wgt_unscale : 1.f;
   p.residual = d->residual; p.out = d->out; p.act = d->act;
   p.plane = (long long)d->n * oh * ow * d->cout;
+  p.dbg = g_dbg;
+  p.dbg_buf = (g_dbg & 16) ? conv_tc_debug_buffer() : nullptr;
   const int groups = (d->n + p.BNI - 1) / p.BNI;
   // kh-reuse tiling for the narrow 3x3 layers: 32x4 / 16x8 pixel tiles inside one image.  Decided from the
   // layer shape only, never from the batch size, so results stay batch-invariant (it accumulates the taps
@@ -769,6 +910,9 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
   }
   p.tiles_n = d->cout / bn;
   p.total_tiles = groups_k * p.tiles_x * p.tiles_y * p.tiles_n;
+  // CTA pairs (cta_group::2): two adjacent M tiles share one weight tile.  Decided from the layer shape only.
+  const bool cta2 = g_cta2 && split && bn == 128 && !khr && row_bytes == 128;
+  if (cta2) p.total_tiles = ((groups_k * p.tiles_x * p.tiles_y + 1) / 2) * p.tiles_n;
 
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
@@ -800,7 +944,7 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
     maps.b[1] = maps.b[0];
   } else {
     cuuint64_t dims[2] = {(cuuint64_t)d->k * d->k * cin, (cuuint64_t)d->cout};
-    cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)bn};
+    cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)(cta2 ? bn / 2 : bn)};      // a CTA pair splits the weight tile
     for (int pl = 0; pl < planes; ++pl) {
       char* a = split ? (char*)d->wgt_split + (size_t)pl * d->cout * d->k * d->k * cin * 2 : (char*)d->wgt;
       if (make_map(&maps.b[pl], split, 2, a, dims, box, row_bytes)) return -1;
@@ -815,11 +959,11 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
     }
   }
   if (split) {
-    if (row_bytes == 128) return launch_bn<MODE_F16X3, 128>(bn, khr, maps, p, s);
-    return launch_bn<MODE_F16X3, 64>(bn, khr, maps, p, s);
+    if (row_bytes == 128) return launch_bn<MODE_F16X3, 128>(bn, khr, cta2, maps, p, s);
+    return launch_bn<MODE_F16X3, 64>(bn, khr, false, maps, p, s);
   }
-  if (row_bytes == 128) return launch_bn<MODE_TF32, 128>(bn, false, maps, p, s);
-  return launch_bn<MODE_TF32, 64>(bn, false, maps, p, s);
+  if (row_bytes == 128) return launch_bn<MODE_TF32, 128>(bn, false, false, maps, p, s);
+  return launch_bn<MODE_TF32, 64>(bn, false, false, maps, p, s);
 }
 
 // ------------------------------------------------------------------ stem on tensor cores

@@ -1,0 +1,93 @@
+#!/usr/bin/env python
+"""Timing experiments on the tcgen05 conv engine (not a test, not a benchmark line): runs one layer shape
+with parts of the pipeline disabled (TcParams::dbg) to see which resource bounds it."""
+import ctypes as C
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import torch
+from omnifusion_b200 import _lib
+import ofb_ops as o
+
+DEV = torch.device("cuda:0")
+L = _lib.lib()
+h = C.c_void_p()
+_lib.check(L.ofb_create(0, C.byref(h)))
+
+
+def opt(k, v):
+    _lib.check(L.ofb_set_option(h, k.encode(), int(v)))
+
+
+def make(n, hw, cin, cout, k=3, stride=1):
+    x = o.split16(torch.randn(n, hw, hw, cin, device=DEV))
+    w = torch.randn(cout, k, k, cin, device=DEV) * (1.0 / (cin * k * k)) ** 0.5
+    mul = o.weight_scale(w)
+    ws = o.split16(w, mul)
+    oh = hw // stride
+    out = torch.empty(2 * n * oh * oh * cout, dtype=torch.float16, device=DEV)
+    scale = torch.ones(cout, device=DEV); shift = torch.zeros(cout, device=DEV)
+    d = _lib.ConvDesc()
+    d.in0 = x.data_ptr(); d.c0 = cin; d.c1 = 0; d.n, d.h, d.w = n, hw, hw
+    d.wgt = w.data_ptr(); d.k, d.stride, d.pad, d.cout = k, stride, k // 2, cout
+    d.scale, d.shift = scale.data_ptr(), shift.data_ptr()
+    d.act, d.out, d.engine, d.in_fmt, d.out_fmt = 1, out.data_ptr(), _lib.ENGINE_TC, 1, 1
+    d.wgt_split, d.wgt_unscale = ws.data_ptr(), 1.0 / mul
+    return d, (x, w, ws, out, scale, shift)
+
+
+def time_conv(d, iters=30):
+    st = _lib.stream_of(DEV)
+    for _ in range(5):
+        _lib.check(L.ofb_conv_f32(C.byref(d), st))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        _lib.check(L.ofb_conv_f32(C.byref(d), st))
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3
+
+
+shapes = [(144, 8, 256, 256), (144, 16, 128, 128), (144, 4, 512, 512), (576, 8, 256, 256)]
+names = {0: "full", 1: "no lo*Whi MMA", 2: "no stacked MMA", 3: "no MMA", 4: "no B loads", 8: "no A loads",
+         12: "no loads", 15: "nothing"}
+opt("store128", 0)
+for (n, hw, cin, cout) in shapes:
+    d, keep = make(n, hw, cin, cout)
+    fl = 2.0 * n * hw * hw * cout * 9 * cin
+    for cta2 in (0, 1):
+        opt("cta2", cta2)
+        row = []
+        for dbg in (0, 1, 2, 3, 4, 8, 12, 15):
+            opt("tc_debug", dbg)
+            us = time_conv(d)
+            row.append(f"{names[dbg]}={us:.1f}us")
+        opt("tc_debug", 0)
+        print(f"n={n} {hw}x{hw} c{cin}->o{cout} cta2={cta2} ({fl / 1e9:.1f} GFLOP): " + "  ".join(row), flush=True)
+
+# ---- clock-stamp trace of CTA 0 (producer / MMA threads), one launch
+import numpy as np
+L.ofb_debug_stamps.restype = C.c_int
+L.ofb_debug_stamps.argtypes = [C.c_void_p]
+for (n, hw, cin, cout) in [(576, 8, 256, 256)]:
+    d, keep = make(n, hw, cin, cout)
+    for cta2 in (0, 1):
+        opt("cta2", cta2)
+        for dbg in (16, 16 + 15):
+            opt("tc_debug", dbg)
+            st = _lib.stream_of(DEV)
+            for _ in range(2):
+                _lib.check(L.ofb_conv_f32(C.byref(d), st))
+            buf = np.zeros((2, 4096, 4), dtype=np.int64)
+            _lib.check(L.ofb_debug_stamps(buf.ctypes.data))
+            nstep = 144
+            P, M = buf[0, :nstep], buf[1, :nstep]
+            t0 = min(P[0, 0], M[0, 0])
+            print(f"--- cta2={cta2} dbg={dbg}: clocks relative to start; producer(wait_start, wait_end, issued) | mma(wait_start, wait_end, committed)")
+            for sidx in list(range(0, 12)) + list(range(36, 42)):
+                print(sidx, (P[sidx, :3] - t0).tolist(), (M[sidx, :3] - t0).tolist())
+            pw = (P[:, 1] - P[:, 0]); mw = (M[:, 1] - M[:, 0]); mi = (M[:, 2] - M[:, 1]); pi = (P[:, 2] - P[:, 1])
+            print(f"mean per step: producer wait {pw.mean():.0f} issue {pi.mean():.0f} | mma wait {mw.mean():.0f} issue {mi.mean():.0f} | total {(M[nstep-1,2]-t0)} clk for {nstep} steps")
+opt("tc_debug", 0)
