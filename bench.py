@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--store128", type=int, default=0)
     ap.add_argument("--pdl", type=int, default=1, help="programmatic dependent launch for the tcgen05 kernels")
     ap.add_argument("--cpu-sample-steps", type=int, default=2)
+    ap.add_argument("--opt", action="append", default=[], help="engine option key=value (experiments)")
     return ap.parse_args()
 
 
@@ -168,6 +169,9 @@ def main():
     net.set_option("pdl", args.pdl)
     if args.store128:
         net.set_option("store128", 1)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        net.set_option(k, int(v))
 
     R = 4
     gens = [torch.Generator().manual_seed(123 + 17 * rank + i) for i in range(R)]

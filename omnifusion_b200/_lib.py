@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libofb.so")
+LIB_PATH = os.environ.get("OFB_LIB") or os.path.join(_HERE, "libofb.so")   # OFB_LIB: A/B experiments with another build
 
 LAYOUT_REF, LAYOUT_FOLDED, LAYOUT_STEM16 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2

@@ -36,9 +36,9 @@ struct TcParams {
   int tiles_n, total_tiles;
   const void* ups_src;   // UPS: low-resolution input (n_img, H/2, W/2, c0), split-half planes
   long long ups_plane;   // elements per plane of ups_src
-  int dbg;               // timing experiments only (results are wrong): 1 skip lo*Whi MMA, 2 skip stacked MMA,
-                         // 4 skip weight loads, 8 skip activation loads, 16 record clock stamps of CTA 0
-  long long* dbg_buf;    // dbg & 16: [role 0 producer / 1 MMA][step][4] clock64 stamps
+  int dbg;               // timing experiments only (results are wrong):
+                         // 32 skip the fused-upsample interpolation, 64 skip the epilogue math and stores
+  int group64;           // accumulate the three split-half products in the cta_group::2 column grouping (see the MMA warp)
 };
 
 // ------------------------------------------------------------------ PTX wrappers (mbarrier: ptx.cuh)
@@ -90,6 +90,17 @@ __device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
+// One lane of a fully converged warp.  The producer and MMA warps run their loops with all 32 lanes (uniform
+// control flow, operands provably warp-uniform so that they live in uniform registers) and only the issue of
+// the TMA / tcgen05 instructions is predicated on this: a `lane == 0` branch around the whole loop makes the
+// compiler wrap every such instruction in a divergence "waterfall" (ELECT + R2UR.BROADCAST x5 + BRA.U.ANY),
+// ~70 clocks of issue per MMA on the one thread that paces the tensor pipe.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.b32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -246,9 +257,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   float* s_scale = reinterpret_cast<float*>(base_ptr + AFTER + 256);
   float* s_shift = s_scale + BN;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;
   // CTA2: cluster c = blockIdx.x / 2 walks pair-tiles; CTA rank r takes M tile 2*mp + r of pair-tile (mp, nt)
-  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const uint32_t rank = CTA2 ? uniform(cluster_ctarank()) : 0u;
   const int tile0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int cin = p.c0 + p.c1;
   const int cchunks = cin / Cfg::KC;
@@ -285,7 +296,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   __syncthreads();
   if (CTA2) cluster_sync_all();          // the peer's barriers are initialised before anything signals them
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = uniform(*tmem_slot);
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
   // prefetch) may overlap the tail of the previous kernel in the stream; no global memory is
   // touched before this point.  Let the next kernel start its own prologue as early as possible.
@@ -293,155 +304,148 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      if (BRES) {      // the whole filter (3 kw x all kh x cin x cout, both planes) once per CTA
+    // ===================== TMA producer (whole warp, one elected lane issues) =====================
+    if (BRES) {      // the whole filter (3 kw x all kh x cin x cout, both planes) once per CTA
+      if (elect_one()) {
         mbar_expect_tx(bar_res, Cfg::RES);
         for (int kw = 0; kw < 3; ++kw)
           tma_load_4d(res_b + kw * Cfg::PLANES * Cfg::B_BYTES, &maps.b[0], bar_res, 0, 0, 0, kw);
       }
-      // (everything below runs on ONE thread per K-step: no divisions, ring stage / phase advanced incrementally)
-      uint32_t st = 0, ph = 0;
-      int dstep = 0;
-      const int ntap = KHR ? 3 : p.taps;
-      for (int t = tile0; !UPS && t < p.total_tiles; t += tile_step) {
-        const int nt = t % p.tiles_n, mt = CTA2 ? 2 * (t / p.tiles_n) + (int)rank : t / p.tiles_n;
-        const int grp = mt / tiles_per_group, trem = mt - grp * tiles_per_group;
-        const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
-        const int img0 = grp * p.BNI, y0 = ty * p.BH, x0 = tx * p.BW, n0 = nt * BN;
-        int kh = 0, kw = 0;
-        for (int tap = 0; tap < ntap; ++tap) {
-          // KHR: `tap` is kw; the box carries rows y0-1 .. y0+BH, the weights all three kh
-          const int cx = KHR ? x0 + tap - 1 : x0 * p.sx + kw - p.padx;
-          const int cy = KHR ? y0 - 1 : y0 * p.sy + kh - p.pady;
-          const int wk = tap * cin;
-          for (int cq = 0; cq < cchunks; ++cq) {
-            int c = cq * Cfg::KC;
-            int src = 0;
-            if (c >= p.c0) { src = 1; c -= p.c0; }
-            const uint32_t full = bars + 8 * st;
-            const uint32_t sa = base + st * Cfg::STAGE;
-            const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
-            long long tw0 = 0;
-            if ((p.dbg & 16) && blockIdx.x == 0) tw0 = clock64();
-            mbar_wait(bars + 8 * (Cfg::NST + st), ph ^ 1);
-            if ((p.dbg & 16) && blockIdx.x == 0 && dstep < 4096) {
-              p.dbg_buf[(0 * 4096 + dstep) * 4 + 0] = tw0; p.dbg_buf[(0 * 4096 + dstep) * 4 + 1] = clock64();
-            }
+      __syncwarp();
+    }
+    // (no divisions per K-step; ring stage / phase advanced incrementally)
+    uint32_t st = 0, ph = 0;
+    const int ntap = KHR ? 3 : p.taps;
+    constexpr bool ld_a = true, ld_b = !BRES;
+    const uint32_t a_bytes = KHR ? (uint32_t)((p.BH + 2) * p.BW * ROW_BYTES) : (uint32_t)Cfg::A_BYTES;
+    const uint32_t tx = (uint32_t)Cfg::PLANES * ((ld_a ? a_bytes : 0u) + (ld_b ? (uint32_t)Cfg::B_BYTES : 0u));
+    for (int t = tile0; !UPS && t < p.total_tiles; t += tile_step) {
+      const int nt = t % p.tiles_n, mt = CTA2 ? 2 * (t / p.tiles_n) + (int)rank : t / p.tiles_n;
+      const int grp = mt / tiles_per_group, trem = mt - grp * tiles_per_group;
+      const int ty = trem / p.tiles_x, tx_ = trem - ty * p.tiles_x;
+      const int img0 = grp * p.BNI, y0 = ty * p.BH, x0 = tx_ * p.BW, n0 = nt * BN;
+      int kh = 0, kw = 0;
+      for (int tap = 0; tap < ntap; ++tap) {
+        // KHR: `tap` is kw; the box carries rows y0-1 .. y0+BH, the weights all three kh
+        const int cx = KHR ? x0 + tap - 1 : x0 * p.sx + kw - p.padx;
+        const int cy = KHR ? y0 - 1 : y0 * p.sy + kh - p.pady;
+        const int wk = tap * cin;
+        for (int cq = 0; cq < cchunks; ++cq) {
+          int c = cq * Cfg::KC;
+          int src = 0;
+          if (c >= p.c0) { src = 1; c -= p.c0; }
+          const uint32_t full = bars + 8 * st;
+          const uint32_t sa = base + st * Cfg::STAGE;
+          const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
+          mbar_wait(bars + 8 * (Cfg::NST + st), ph ^ 1);
+          if (elect_one()) {
             if (KHR) {
-              mbar_expect_tx(full, (uint32_t)(Cfg::PLANES * ((p.BH + 2) * p.BW * ROW_BYTES + (BRES ? 0 : Cfg::B_BYTES))));
+              mbar_expect_tx(full, tx);
 #pragma unroll
               for (int pl = 0; pl < Cfg::PLANES; ++pl)
-                tma_load_4d(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, cx, cy, img0);
+                if (ld_a) tma_load_4d(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, cx, cy, img0);
               // one box = {kc, stacked [Whi; Wlo] rows, all 3 kh, this kw}
-              if (!BRES) tma_load_4d(sb, &maps.b[0], full, cq * Cfg::KC, 0, 0, tap);
+              if (ld_b) tma_load_4d(sb, &maps.b[0], full, cq * Cfg::KC, 0, 0, tap);
             } else if (CTA2) {
-              const uint32_t nb = Cfg::PLANES * ((p.dbg & 8 ? 0 : Cfg::A_BYTES) + (p.dbg & 4 ? 0 : Cfg::B_BYTES));
-              if (rank == 0) mbar_expect_tx(full, 2 * nb);      // both CTAs' bytes land on the leader's barrier
+              if (rank == 0) mbar_expect_tx(full, 2 * tx);      // both CTAs' bytes land on the leader's barrier
 #pragma unroll
               for (int pl = 0; pl < Cfg::PLANES; ++pl) {
-                if (!(p.dbg & 8)) tma_load_4d_2sm(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, cx, cy, img0);
+                if (ld_a) tma_load_4d_2sm(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, cx, cy, img0);
                 // rank r: [Whi rows 64r.. ; Wlo rows 64(1-r)..]
-                if (!(p.dbg & 4))
+                if (ld_b)
                   tma_load_2d_2sm(sb + pl * Cfg::B_BYTES, &maps.b[pl], full, wk + cq * Cfg::KC,
                                   n0 + (BN / 2) * (pl == 0 ? (int)rank : 1 - (int)rank));
               }
             } else {
-              mbar_expect_tx(full, Cfg::PLANES * ((p.dbg & 8 ? 0 : Cfg::A_BYTES) + (p.dbg & 4 ? 0 : Cfg::B_BYTES)));
+              mbar_expect_tx(full, tx);
 #pragma unroll
               for (int pl = 0; pl < Cfg::PLANES; ++pl) {
-                if (!(p.dbg & 8)) tma_load_4d(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, cx, cy, img0);
-                if (!(p.dbg & 4)) tma_load_2d(sb + pl * Cfg::B_BYTES, &maps.b[pl], full, wk + cq * Cfg::KC, n0);
+                if (ld_a) tma_load_4d(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, cx, cy, img0);
+                if (ld_b) tma_load_2d(sb + pl * Cfg::B_BYTES, &maps.b[pl], full, wk + cq * Cfg::KC, n0);
               }
             }
-            if ((p.dbg & 16) && blockIdx.x == 0 && dstep < 4096) p.dbg_buf[(0 * 4096 + dstep) * 4 + 2] = clock64();
-            ++dstep;
-            if (++st == Cfg::NST) { st = 0; ph ^= 1; }
           }
-          if (++kw == p.kdiv) { kw = 0; ++kh; }
+          __syncwarp();
+          if (++st == Cfg::NST) { st = 0; ph ^= 1; }
         }
+        if (++kw == p.kdiv) { kw = 0; ++kh; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0 && rank == 0) {
+    // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+    if (rank == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (bit 4), a/b format
       // (bits 7/10: 0 = F16, 2 = TF32), K-major A and B, N >> 3 at bit 17, M >> 4 at bit 24.
       const uint32_t fmt = MODE == MODE_TF32 ? 2u : 0u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | (((CTA2 ? 256u : 128u) >> 4) << 24);
-      uint32_t st = 0, ph = 0, i = 0;
-      int dstep = 0;
       const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * BN) >> 3) << 17);   // N = 2*BN
       const uint32_t idesc64 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(64 >> 3) << 17);        // N = 64
       const uint64_t dconst = umma_desc<ROW_BYTES>(0);            // descriptor without the start address
+      uint32_t st = 0, ph = 0, i = 0;
       if (BRES) mbar_wait(bar_res, 0);
       for (int t = tile0; t < p.total_tiles; t += tile_step, ++i) {
         const uint32_t buf = i & 1;
         mbar_wait(bar_tempty + 8 * buf, ((i >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t acc = tmem + buf * Cfg::ACC_COLS;
-        // Column grouping of the three products, identical in every tile configuration so that results do
-        // not depend on the tile choice (which follows the batch size): within each block of 128 output
-        // channels, channels [0,64) accumulate hi*Whi + lo*Whi in one column and hi*Wlo in the other;
-        // channels [64,128) accumulate hi*Wlo + lo*Whi in one column and hi*Whi in the other (that is
-        // what the cta_group::2 operand split produces); the epilogue adds the two columns.
-        const bool upper = !CTA2 && BN < 128 && (((t % p.tiles_n) * BN) & 64) != 0;
+        // Column grouping of the three products (p.group64, the default): identical in every tile configuration
+        // so that results do not depend on the tile choice (which follows the batch size): within each block of
+        // 128 output channels, channels [0,64) accumulate hi*Whi + lo*Whi in one column and hi*Wlo in the other;
+        // channels [64,128) accumulate hi*Wlo + lo*Whi in one column and hi*Whi in the other (that is what the
+        // cta_group::2 operand split produces); the epilogue adds the two columns.
+        const bool upper = !CTA2 && BN < 128 && p.group64 && (((t % p.tiles_n) * BN) & 64) != 0;
         const uint32_t acc_lo = acc + (upper ? BN : 0);           // where lo*Whi accumulates
         for (int ks = 0; ks < ksteps; ++ks) {
-          long long tw0 = 0;
-          if ((p.dbg & 16) && blockIdx.x == 0) tw0 = clock64();
           mbar_wait(bars + 8 * st, ph);
           tc_fence_after();
-          if ((p.dbg & 16) && blockIdx.x == 0 && dstep < 4096) {
-            p.dbg_buf[(1 * 4096 + dstep) * 4 + 0] = tw0; p.dbg_buf[(1 * 4096 + dstep) * 4 + 1] = clock64();
-          }
           const uint32_t sa = base + st * Cfg::STAGE;
           // BRES: one K-step per kw (cin == KC), its weights sit in the resident region
           const uint32_t sb = BRES ? res_b + (uint32_t)(ks * Cfg::PLANES * Cfg::B_BYTES) : sa + Cfg::PLANES * Cfg::A_BYTES;
-          if (KHR) {
+          if (elect_one()) {
+            if (KHR) {
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-              // tap kh reads the halo box kh image rows further down; weights: [kh][Whi rows; Wlo rows]
-              const uint32_t ao = (uint32_t)(kh * p.BW * ROW_BYTES), bo = (uint32_t)(kh * 2 * BN * ROW_BYTES);
-              const uint64_t a_hi = dconst | (((sa + ao) >> 4) & 0x3FFF), a_lo = dconst | (((sa + Cfg::A_BYTES + ao) >> 4) & 0x3FFF);
-              const uint64_t b_st = dconst | (((sb + bo) >> 4) & 0x3FFF);
+              for (int kh = 0; kh < 3; ++kh) {
+                // tap kh reads the halo box kh image rows further down; weights: [kh][Whi rows; Wlo rows]
+                const uint32_t ao = (uint32_t)(kh * p.BW * ROW_BYTES), bo = (uint32_t)(kh * 2 * BN * ROW_BYTES);
+                const uint64_t a_hi = dconst | (((sa + ao) >> 4) & 0x3FFF), a_lo = dconst | (((sa + Cfg::A_BYTES + ao) >> 4) & 0x3FFF);
+                const uint64_t b_st = dconst | (((sb + bo) >> 4) & 0x3FFF);
 #pragma unroll
-              for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk) {
-                tc_mma<MODE>(acc, a_hi + 2 * kk, b_st + 2 * kk, idesc2, (ks | kh | kk) != 0);   // hi*Whi | hi*Wlo
-                tc_mma<MODE>(acc_lo, a_lo + 2 * kk, b_st + 2 * kk, idesc, 1);                  // + lo*Whi
+                for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk) {
+                  tc_mma<MODE>(acc, a_hi + 2 * kk, b_st + 2 * kk, idesc2, (ks | kh | kk) != 0);   // hi*Whi | hi*Wlo
+                  tc_mma<MODE>(acc_lo, a_lo + 2 * kk, b_st + 2 * kk, idesc, 1);                  // + lo*Whi
+                }
               }
-            }
-          } else {
-            const uint64_t a_hi = dconst | ((sa >> 4) & 0x3FFF), b_hi = dconst | ((sb >> 4) & 0x3FFF);
-            if (MODE == MODE_TF32) {
-#pragma unroll
-              for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk)
-                tc_mma<MODE>(acc, a_hi + 2 * kk, b_hi + 2 * kk, idesc, (ks | kk) != 0);
             } else {
-              // sb holds [Whi rows][Wlo rows] back to back = the stacked operand
-              const uint64_t a_lo = dconst | (((sa + Cfg::A_BYTES) >> 4) & 0x3FFF);
+              const uint64_t a_hi = dconst | ((sa >> 4) & 0x3FFF), b_hi = dconst | ((sb >> 4) & 0x3FFF);
+              if (MODE == MODE_TF32) {
 #pragma unroll
-              for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk) {
-                if (!(p.dbg & 2)) tc_mma<MODE, CTA2>(acc, a_hi + 2 * kk, b_hi + 2 * kk, idesc2, (ks | kk) != 0);   // hi*Whi | hi*Wlo
-                if (p.dbg & 1) continue;
-                if (!CTA2 && BN == 128) {
-                  // + lo*Whi: channels [0,64) onto the hi*Whi columns, [64,128) onto the hi*Wlo columns
-                  tc_mma<MODE>(acc, a_lo + 2 * kk, b_hi + 2 * kk, idesc64, 1);
-                  tc_mma<MODE>(acc + BN + 64, a_lo + 2 * kk, b_hi + ((64 * ROW_BYTES) >> 4) + 2 * kk, idesc64, 1);
-                } else {
-                  tc_mma<MODE, CTA2>(acc_lo, a_lo + 2 * kk, b_hi + 2 * kk, idesc, 1);
+                for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk)
+                  tc_mma<MODE>(acc, a_hi + 2 * kk, b_hi + 2 * kk, idesc, (ks | kk) != 0);
+              } else {
+                // sb holds [Whi rows][Wlo rows] back to back = the stacked operand
+                const uint64_t a_lo = dconst | (((sa + Cfg::A_BYTES) >> 4) & 0x3FFF);
+#pragma unroll
+                for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk) {
+                  tc_mma<MODE, CTA2>(acc, a_hi + 2 * kk, b_hi + 2 * kk, idesc2, (ks | kk) != 0);   // hi*Whi | hi*Wlo
+                  if (!CTA2 && BN == 128 && p.group64) {
+                    // + lo*Whi: channels [0,64) onto the hi*Whi columns, [64,128) onto the hi*Wlo columns
+                    tc_mma<MODE>(acc, a_lo + 2 * kk, b_hi + 2 * kk, idesc64, 1);
+                    tc_mma<MODE>(acc + BN + 64, a_lo + 2 * kk, b_hi + ((64 * ROW_BYTES) >> 4) + 2 * kk, idesc64, 1);
+                  } else {
+                    tc_mma<MODE, CTA2>(acc_lo, a_lo + 2 * kk, b_hi + 2 * kk, idesc, 1);
+                  }
                 }
               }
             }
+            // frees this smem stage when the MMAs retire
+            if (CTA2) tc_commit_2sm(bars + 8 * (Cfg::NST + st)); else tc_commit(bars + 8 * (Cfg::NST + st));
+            if (ks == ksteps - 1) {                         // accumulator complete
+              if (CTA2) tc_commit_2sm(bar_tfull + 8 * buf); else tc_commit(bar_tfull + 8 * buf);
+            }
           }
-          if (CTA2) tc_commit_2sm(bars + 8 * (Cfg::NST + st)); else
-          tc_commit(bars + 8 * (Cfg::NST + st));       // frees this smem stage when the MMAs retire
-          if ((p.dbg & 16) && blockIdx.x == 0 && dstep < 4096) p.dbg_buf[(1 * 4096 + dstep) * 4 + 2] = clock64();
-          ++dstep;
+          __syncwarp();
           if (++st == Cfg::NST) { st = 0; ph ^= 1; }
         }
-        if (CTA2) tc_commit_2sm(bar_tfull + 8 * buf); else
-        tc_commit(bar_tfull + 8 * buf);                // accumulator complete
       }
     }
   } else if (warp < 6) {
@@ -492,6 +496,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             else mbar_arrive(bar_tempty + 8 * buf);
           }
         }
+        if (p.dbg & 64) continue;
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * s_scale[cb + j] + s_shift[cb + j];
@@ -664,7 +669,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       const uint32_t st0 = it % Cfg::NST;                          // NST is a multiple of 3: stages st0, st0+1, st0+2
       uint8_t* const sbase = base_ptr + st0 * Cfg::STAGE;
 #pragma unroll 1
-      for (int i = pt; i < (BH + 2) * BWX * C8; i += NT) {
+      for (int i = pt; i < ((p.dbg & 32) ? 0 : (BH + 2) * BWX * C8); i += NT) {
         const int ch = i % C8, px = i / C8;
         const int by = px / BWX, bx = px - by * BWX;
         const int Y = y0 - 1 + by, X = x0 - 1 + bx;
@@ -793,12 +798,7 @@ static bool g_store128 = true;  // bulk-tensor-store epilogue also for the 128-w
 static bool g_cta2 = true;      // cta_group::2 CTA pairs for the 128-wide split-half tiles
 void conv_tc_set_cta2(bool on) { g_cta2 = on; }
 static int g_dbg = 0;           // TcParams::dbg (timing experiments)
-static long long* g_dbg_buf = nullptr;
 void conv_tc_set_debug(int v) { g_dbg = v; }
-long long* conv_tc_debug_buffer() {
-  if (!g_dbg_buf) cudaMalloc(&g_dbg_buf, 2 * 4096 * 4 * sizeof(long long));
-  return g_dbg_buf;
-}
 void conv_tc_set_pdl(bool on) { g_pdl = on; }
 void conv_tc_set_store128(bool on) { g_store128 = on; }
 
@@ -892,7 +892,7 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
   p.residual = d->residual; p.out = d->out; p.act = d->act;
   p.plane = (long long)d->n * oh * ow * d->cout;
   p.dbg = g_dbg;
-  p.dbg_buf = (g_dbg & 16) ? conv_tc_debug_buffer() : nullptr;
+  p.group64 = g_cta2 ? 1 : 0;
   const int groups = (d->n + p.BNI - 1) / p.BNI;
   // kh-reuse tiling for the narrow 3x3 layers: 32x4 / 16x8 pixel tiles inside one image.  Decided from the
   // layer shape only, never from the batch size, so results stay batch-invariant (it accumulates the taps

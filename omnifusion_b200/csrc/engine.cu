@@ -36,7 +36,6 @@ void conv_tc_set_pdl(bool on);
 void conv_tc_set_store128(bool on);
 void conv_tc_set_cta2(bool on);
 void conv_tc_set_debug(int v);
-long long* conv_tc_debug_buffer();
 
 int conv_dispatch(const ofb_conv_desc* d, cudaStream_t s) {
   OFB_CHECK(d && d->in0 && (d->wgt || d->wgt_split) && d->out, "conv: null pointer");
@@ -696,13 +695,6 @@ extern "C" int ofb_forward_f32(ofb_handle* h, const float* rgb, int B, int iters
                       (cudaStream_t)stream))
       return -1;
   }
-  return 0;
-}
-
-// timing experiments: copies the clock stamps recorded with tc_debug & 16 (2 x 4096 x 4 int64) to the host
-extern "C" int ofb_debug_stamps(long long* host_dst) {
-  OFB_CUDA(cudaDeviceSynchronize());
-  OFB_CUDA(cudaMemcpy(host_dst, conv_tc_debug_buffer(), 2 * 4096 * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
   return 0;
 }
 

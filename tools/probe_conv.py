@@ -67,27 +67,4 @@ for (n, hw, cin, cout) in shapes:
         opt("tc_debug", 0)
         print(f"n={n} {hw}x{hw} c{cin}->o{cout} cta2={cta2} ({fl / 1e9:.1f} GFLOP): " + "  ".join(row), flush=True)
 
-# ---- clock-stamp trace of CTA 0 (producer / MMA threads), one launch
-import numpy as np
-L.ofb_debug_stamps.restype = C.c_int
-L.ofb_debug_stamps.argtypes = [C.c_void_p]
-for (n, hw, cin, cout) in [(576, 8, 256, 256)]:
-    d, keep = make(n, hw, cin, cout)
-    for cta2 in (0, 1):
-        opt("cta2", cta2)
-        for dbg in (16, 16 + 15):
-            opt("tc_debug", dbg)
-            st = _lib.stream_of(DEV)
-            for _ in range(2):
-                _lib.check(L.ofb_conv_f32(C.byref(d), st))
-            buf = np.zeros((2, 4096, 4), dtype=np.int64)
-            _lib.check(L.ofb_debug_stamps(buf.ctypes.data))
-            nstep = 144
-            P, M = buf[0, :nstep], buf[1, :nstep]
-            t0 = min(P[0, 0], M[0, 0])
-            print(f"--- cta2={cta2} dbg={dbg}: clocks relative to start; producer(wait_start, wait_end, issued) | mma(wait_start, wait_end, committed)")
-            for sidx in list(range(0, 12)) + list(range(36, 42)):
-                print(sidx, (P[sidx, :3] - t0).tolist(), (M[sidx, :3] - t0).tolist())
-            pw = (P[:, 1] - P[:, 0]); mw = (M[:, 1] - M[:, 0]); mi = (M[:, 2] - M[:, 1]); pi = (P[:, 2] - P[:, 1])
-            print(f"mean per step: producer wait {pw.mean():.0f} issue {pi.mean():.0f} | mma wait {mw.mean():.0f} issue {mi.mean():.0f} | total {(M[nstep-1,2]-t0)} clk for {nstep} steps")
 opt("tc_debug", 0)
