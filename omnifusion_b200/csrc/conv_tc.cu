@@ -37,7 +37,9 @@ struct TcParams {
   const void* ups_src;   // UPS: low-resolution input (n_img, H/2, W/2, c0), split-half planes
   long long ups_plane;   // elements per plane of ups_src
   int dbg;               // timing experiments only (results are wrong):
-                         // 32 skip the fused-upsample interpolation, 64 skip the epilogue math and stores
+                         // 32 skip the fused-upsample interpolation, 64 skip the epilogue math and stores,
+                         // 128 skip only the global stores of the epilogue
+  long long* dbg_buf;    // dbg & 16: clock stamps of the epilogue warp 2 of CTA 0: [tile][8]
   int group64;           // accumulate the three split-half products in the cta_group::2 column grouping (see the MMA warp)
 };
 
@@ -128,7 +130,7 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
   }
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
@@ -139,8 +141,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
 // LBO (unused for swizzled K-major) = 1, SBO = bytes between 8-row groups >> 4, version = 1
@@ -173,11 +175,17 @@ __device__ __forceinline__ float act_fn(float v, int act) {
 // BRES (KHR layers whose whole filter is a few KB, i.e. 32->32): the weights are loaded once per CTA
 // into a resident region and the ring stages carry activations only - the layer is bound by the TMA
 // request rate on its 64-byte rows, and a third of those requests were weight re-loads.
-// UPS (BRES layers only): the conv input is the 2x bilinear upsample (align_corners=False) of a
-// low-resolution tensor.  Instead of a TMA load of a materialised upsampled tensor, eight producer
-// warps stage the tile's low-resolution neighbourhood as float32 in shared memory, interpolate every
-// pixel of the halo box once and write it (split-half, swizzled like the TMA would) into the three
-// kw-shifted boxes of three ring stages.  The upsampled tensor never exists in HBM.
+// UPS (BRES layers only, image width 128): the conv input is the 2x bilinear upsample (align_corners=False) of a
+// low-resolution tensor, which never exists in HBM.  A CTA walks a contiguous range of output rows (tile =
+// one image row of 128 pixels) and keeps a ring of UPSAMPLED rows in shared memory: every output row adds ONE
+// new row (130 pixels: zero column, 128 interpolated pixels, zero column) that eight producer warps
+// interpolate from the low-resolution tensor (thread = low-res column x 8-channel chunk; the horizontally
+// blended low-res rows are cached in registers, so a row costs 16 lerps and 4 shared stores per thread).
+// All nine taps read the ring through ROW-SHIFTED operand descriptors: tap (kh, kw) of output row y is the 128
+// consecutive ring rows starting at pixel kw of upsampled row y-1+kh (the swizzle is a function of the
+// shared-memory address, so a descriptor may start at any 64-byte row - verified by tools/mma_probe.cu).
+// Against the tile-box scheme (three kw-shifted copies of a 6-row halo box per 4x32 tile) the producers
+// interpolate 1.02 instead of 1.6 pixels and store 1.02 instead of 4.8 pixels per output pixel.
 // CTA2 (BN = 128 tiles, F16X3): a cluster of two CTAs computes two adjacent M tiles of the same N tile with
 // cta_group::2 MMAs (M = 256).  Each CTA stages its own activation tile but only HALF of the weight tile
 // (rank r holds [Whi rows 64r..64r+63 ; Wlo rows 64(1-r)..]), so the weight traffic from L2 and the
@@ -191,17 +199,19 @@ struct TcCfg {
   static constexpr int KC_ = ROW_BYTES / ES;
   static constexpr int A_BYTES = (KHR ? 192 : 128) * ROW_BYTES;           // capacity; KHR boxes are <= 192 rows
   static constexpr int B_BYTES = (KHR ? 3 : 1) * (CTA2 ? BN / 2 : BN) * ROW_BYTES;
-  static constexpr int STAGE = (A_BYTES + (BRES ? 0 : B_BYTES)) * PLANES;
+  static constexpr int UPS_PX = 130;                                       // UPS: pixels per ring row (one zero column each side)
+  static constexpr int UPS_PLANE = UPS_PX * ROW_BYTES;                     // UPS: bytes of one upsampled row, one plane
+  static constexpr int STAGE = UPS ? UPS_PLANE * PLANES : (A_BYTES + (BRES ? 0 : B_BYTES)) * PLANES;
   static constexpr int RES = BRES ? 3 * PLANES * B_BYTES : 0;               // resident weights (all 3 kw)
   static constexpr int OUT_ROW = 32 * ES;                                  // bytes per staged row (32 columns)
   static constexpr int OUT_BUF = TMA_STORE ? PLANES * 128 * OUT_ROW : 0;   // one staging buffer
   static constexpr int MISC = 1024 /*align*/ + 256 /*barriers*/ + BN * 8;
   static constexpr int UPS_WARPS = UPS ? 8 : 0;                            // interpolating producer warps
   static constexpr int THREADS = 192 + 32 * UPS_WARPS;
-  static constexpr int LR_ROWS = 4, LR_COLS = 18;                          // low-res halo of a 4 x 32 pixel tile
-  static constexpr int LR_BYTES = UPS ? LR_ROWS * LR_COLS * KC_ * 4 : 0;   // float32 staging of that halo
+  static constexpr int LR_BYTES = 0;
   static constexpr int NST_RAW = (227 * 1024 - MISC - 2 * OUT_BUF - RES - LR_BYTES) / STAGE;
-  static constexpr int NST = UPS ? 6 : (NST_RAW > 8 ? 8 : NST_RAW);        // UPS: two tiles x three kw boxes
+  static constexpr int NST = NST_RAW > 8 ? 8 : NST_RAW;                    // UPS: ring of upsampled rows (multiple of 4:
+                                                                           // keeps the lo-plane ring 512-byte aligned)
   static constexpr int KC = ROW_BYTES / ES;                                // channels per K-step
   static constexpr int MMA_PER_TILE = ROW_BYTES / 32;                      // UMMA_K spans 32 bytes
   // Every MMA re-reads its 128 x 32 B slice of A from shared memory, which is what bounds the narrow
@@ -214,7 +224,7 @@ struct TcCfg {
   static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;  // two accumulator buffers
   static constexpr int SMEM = NST * STAGE + 2 * OUT_BUF + RES + LR_BYTES + MISC;
   static_assert(NST >= 2 && NST <= NST_RAW, "pipeline needs at least two stages that fit in shared memory");
-  static_assert(!UPS || (KHR && BRES && MODE == MODE_F16X3), "UPS is a variant of the resident-filter kh-reuse kernel");
+  static_assert(!UPS || (KHR && BRES && MODE == MODE_F16X3 && ROW_BYTES == 64 && NST == 8), "UPS is a variant of the resident-filter kh-reuse kernel");
   static_assert(!CTA2 || (BN == 128 && MODE == MODE_F16X3 && !KHR && !BRES && !UPS), "CTA2 is a variant of the plain 128-wide F16X3 kernel");
 };
 
@@ -249,7 +259,6 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   const uint32_t stage_out = base + RING;                        // 2 staging buffers (TMA_STORE)
   uint8_t* stage_out_ptr = base_ptr + RING;
   const uint32_t res_b = base + RING + 2 * Cfg::OUT_BUF;         // resident weights (BRES)
-  float* lr = reinterpret_cast<float*>(base_ptr + RING + 2 * Cfg::OUT_BUF + Cfg::RES);   // UPS: low-res halo, float32
   constexpr int AFTER = RING + 2 * Cfg::OUT_BUF + Cfg::RES + Cfg::LR_BYTES;
   const uint32_t bars = base + AFTER;                            // full[NST], empty[NST], tfull[2], tempty[2], res
   const uint32_t bar_tfull = bars + 8 * (2 * Cfg::NST), bar_tempty = bar_tfull + 16, bar_res = bar_tempty + 16;
@@ -261,6 +270,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   // CTA2: cluster c = blockIdx.x / 2 walks pair-tiles; CTA rank r takes M tile 2*mp + r of pair-tile (mp, nt)
   const uint32_t rank = CTA2 ? uniform(cluster_ctarank()) : 0u;
   const int tile0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // UPS: the CTA owns the contiguous output rows [ups_r0, ups_r1) (global row index = image * H + y)
+  const int ups_per = UPS ? (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int ups_r0 = UPS ? min((int)blockIdx.x * ups_per, p.total_tiles) : 0, ups_r1 = UPS ? min(ups_r0 + ups_per, p.total_tiles) : 0;
   const int cin = p.c0 + p.c1;
   const int cchunks = cin / Cfg::KC;
   const int ksteps = (KHR ? 3 : p.taps) * cchunks;
@@ -383,7 +395,50 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       const uint64_t dconst = umma_desc<ROW_BYTES>(0);            // descriptor without the start address
       uint32_t st = 0, ph = 0, i = 0;
       if (BRES) mbar_wait(bar_res, 0);
-      for (int t = tile0; t < p.total_tiles; t += tile_step, ++i) {
+      if (UPS) {
+        // produced-row counter of the top halo row of the current output row; ring slot = counter % NST
+        uint32_t pb = 0;
+        for (int g = ups_r0; g < ups_r1; ++g, ++i) {
+          const int y = g % p.H;
+          const bool seg_start = g == ups_r0 || y == 0, seg_end = g == ups_r1 - 1 || y == p.H - 1;
+          const uint32_t buf = i & 1;
+          mbar_wait(bar_tempty + 8 * buf, ((i >> 1) & 1) ^ 1);
+          if (seg_start) {
+            mbar_wait(bars + 8 * (pb % Cfg::NST), (pb / Cfg::NST) & 1);
+            mbar_wait(bars + 8 * ((pb + 1) % Cfg::NST), ((pb + 1) / Cfg::NST) & 1);
+          }
+          mbar_wait(bars + 8 * ((pb + 2) % Cfg::NST), ((pb + 2) / Cfg::NST) & 1);
+          tc_fence_after();
+          const uint32_t acc = tmem + buf * Cfg::ACC_COLS;
+          if (elect_one()) {
+            // same accumulation order as the tile-box kernels: kw outer, kh, then the two 16-channel slices
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+              for (int kh = 0; kh < 3; ++kh) {
+                const uint32_t row = ((pb + kh) % Cfg::NST) * Cfg::UPS_PX + kw;          // first ring row of this tap
+                const uint32_t a0 = base + row * ROW_BYTES, b0 = res_b + (uint32_t)((kw * Cfg::PLANES * 3 + kh * 2) * BN * ROW_BYTES);
+                const uint64_t a_hi = dconst | ((a0 >> 4) & 0x3FFF), a_lo = dconst | (((a0 + Cfg::NST * Cfg::UPS_PLANE) >> 4) & 0x3FFF);
+                const uint64_t b_st = dconst | ((b0 >> 4) & 0x3FFF);
+#pragma unroll
+                for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk) {
+                  tc_mma<MODE>(acc, a_hi + 2 * kk, b_st + 2 * kk, idesc2, (kw | kh | kk) != 0);   // hi*Whi | hi*Wlo
+                  tc_mma<MODE>(acc, a_lo + 2 * kk, b_st + 2 * kk, idesc, 1);                      // + lo*Whi
+                }
+              }
+            }
+            tc_commit(bars + 8 * (Cfg::NST + pb % Cfg::NST));            // the top halo row is no longer needed
+            if (seg_end) {
+              tc_commit(bars + 8 * (Cfg::NST + (pb + 1) % Cfg::NST));
+              tc_commit(bars + 8 * (Cfg::NST + (pb + 2) % Cfg::NST));
+            }
+            tc_commit(bar_tfull + 8 * buf);
+          }
+          __syncwarp();
+          pb += seg_end ? 3 : 1;
+        }
+      }
+      for (int t = tile0; !UPS && t < p.total_tiles; t += tile_step, ++i) {
         const uint32_t buf = i & 1;
         mbar_wait(bar_tempty + 8 * buf, ((i >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
@@ -456,7 +511,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     const int et = threadIdx.x - 64;           // 0..127
     int last_n0 = -1;
     uint32_t i = 0, chunk_ctr = 0;
-    for (int t = tile0; t < p.total_tiles; t += tile_step, ++i) {
+    for (int t = UPS ? ups_r0 : tile0; t < (UPS ? ups_r1 : p.total_tiles); t += UPS ? 1 : tile_step, ++i) {
       const int nt = t % p.tiles_n, mt = CTA2 ? 2 * (t / p.tiles_n) + (int)rank : t / p.tiles_n;
       const int grp = mt / tiles_per_group, trem = mt - grp * tiles_per_group;
       const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
@@ -471,8 +526,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         last_n0 = n0;
       }
       const uint32_t buf = i & 1;
+      const bool stamp = (p.dbg & 16) && blockIdx.x == 0 && et == 0 && i < 512;
+      if (stamp) p.dbg_buf[i * 8 + 0] = clock64();
       mbar_wait(bar_tfull + 8 * buf, (i >> 1) & 1);
       tc_fence_after();
+      if (stamp) p.dbg_buf[i * 8 + 1] = clock64();
       const int img = img0 + ni;
       const bool ok = img < p.n_img;
       const size_t pix = ((size_t)(ok ? img : 0) * p.H + (y0 + yy)) * p.W + (x0 + xx);
@@ -480,13 +538,16 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 #pragma unroll 1
       for (int cb = 0; cb < BN; cb += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * Cfg::ACC_COLS + cb, v);
+        tmem_ld32_issue(tmem + ((uint32_t)(q * 32) << 16) + buf * Cfg::ACC_COLS + cb, v);
         if (Cfg::STACK) {                        // second column block (hi*Wlo) of the stacked accumulator
           uint32_t v2[32];
           // CTA2: see the column map above TcCfg
-          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * Cfg::ACC_COLS + (CTA2 ? (cb < 64 ? 192 : 64) : BN) + cb, v2);
+          tmem_ld32_issue(tmem + ((uint32_t)(q * 32) << 16) + buf * Cfg::ACC_COLS + (CTA2 ? (cb < 64 ? 192 : 64) : BN) + cb, v2);
+          tmem_ld_wait();                        // both loads in flight together
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        } else {
+          tmem_ld_wait();
         }
         if (cb + 32 >= BN) {                     // accumulator fully read: hand it back to the MMA warp
           tc_fence_before();
@@ -496,6 +557,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             else mbar_arrive(bar_tempty + 8 * buf);
           }
         }
+        if (stamp) p.dbg_buf[i * 8 + 2] = clock64();
         if (p.dbg & 64) continue;
         float f[32];
 #pragma unroll
@@ -526,15 +588,26 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             }
           }
         }
+        // one (uniform) branch per chunk, not per element: with act_fn's run-time switch inlined 32 times the
+        // epilogue warp spent ~1700 clocks per chunk in taken branches
+        if (p.act == OFB_ACT_RELU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = act_fn(f[j], p.act);
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        } else if (p.act == OFB_ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752440f));
+        }
 
+        if (stamp) p.dbg_buf[i * 8 + 3] = clock64();
         if (TMA_STORE) {
           // stage the 128 x 32-column chunk (swizzled like the output tensor map expects) and let
           // one thread write it with a bulk tensor store; two staging buffers alternate
+          // Each epilogue warp stages and stores its own 32 pixels (a sub-box of the tile): no CTA-wide barrier,
+          // the four warps drain the accumulator independently.
           const uint32_t sbuf = chunk_ctr & 1;
-          if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          epi_bar();                                         // staging buffer `sbuf` is free again
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();                                      // this warp's slice of staging buffer `sbuf` is free again
+          if (stamp) p.dbg_buf[i * 8 + 4] = clock64();
           uint8_t* dst = stage_out_ptr + sbuf * Cfg::OUT_BUF;
           if (MODE == MODE_TF32) {
             // 128-byte rows, SWIZZLE_128B: 16-byte chunk index ^= row & 7
@@ -560,17 +633,23 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
               *reinterpret_cast<uint4*>(dst + 128 * 64 + r * 64 + sw) = lo4;
             }
           }
+          if (stamp) p.dbg_buf[i * 8 + 5] = clock64();
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          epi_bar();
-          if (et == 0) {
-            const uint32_t src = stage_out + sbuf * Cfg::OUT_BUF;
+          __syncwarp();
+          if (stamp) p.dbg_buf[i * 8 + 6] = clock64();
+          if (lane == 0 && !(p.dbg & 128)) {
+            // sub-box of warp q = pixels 32q .. 32q+31 of the tile (box dims chosen on the host to match)
+            const int r0 = q * 32;
+            const int sx = r0 % p.BW, sy = (r0 / p.BW) % p.BH, sn = r0 / (p.BW * p.BH);
+            const uint32_t src = stage_out + sbuf * Cfg::OUT_BUF + (uint32_t)(r0 * Cfg::OUT_ROW);
 #pragma unroll
             for (int pl = 0; pl < Cfg::PLANES; ++pl)
-              tma_store_4d(&maps.o[pl], src + pl * 128 * Cfg::OUT_ROW, n0 + cb, x0, y0, img0);   // OOB images are clipped
+              tma_store_4d(&maps.o[pl], src + pl * 128 * Cfg::OUT_ROW, n0 + cb, x0 + sx, y0 + sy, img0 + sn);   // OOB images are clipped
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+          if (stamp) p.dbg_buf[i * 8 + 7] = clock64();
           ++chunk_ctr;
-        } else if (ok) {
+        } else if (ok && !(p.dbg & 128)) {
           if (MODE == MODE_TF32) {
             float* o = reinterpret_cast<float*>(p.out) + off + cb;
 #pragma unroll
@@ -597,127 +676,120 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         }
       }
     }
-    if (TMA_STORE && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (TMA_STORE && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (UPS) {
     // ===================== interpolating producers (warps 6..13) =====================
-    // Tile = 4 x 32 output pixels of one image; its halo box covers input pixels Y = y0-1 .. y0+4,
-    // X = x0-1 .. x0+32 of the (virtual) upsampled tensor, which interpolate the low-res rows
-    // y0/2-1 .. y0/2+2 and columns x0/2-1 .. x0/2+16 (clamped at the borders).  The low-res halo of
-    // the NEXT tile is fetched into registers while this tile is interpolated, so the global-load
-    // latency is hidden.
-    constexpr int NT = UPS ? 32 * Cfg::UPS_WARPS : 32, C8 = Cfg::KC / 8, LC = Cfg::LR_COLS, LR = Cfg::LR_ROWS;
-    constexpr int BW = 32, BH = 4, BWX = BW + 2;
-    constexpr int LRI = LR * LC * C8;                 // 16-byte-pair items of the low-res halo
-    constexpr int LRK = (LRI + NT - 1) / NT;
-    // lr: two planes of float4 (channels 0-3 / 4-7 of every 8-channel chunk) so that a warp's
-    // 16-byte reads are contiguous (no bank conflicts)
-    float4* lrA = reinterpret_cast<float4*>(lr);
-    float4* lrB = lrA + LRI;
+    // thread = (low-res column x, 8-channel chunk ch): it owns pixels X = 2x, 2x+1 of every upsampled row.
+    // F.interpolate(scale 2, bilinear, align_corners=False): row Y = 2y+dy blends low-res rows y-1+dy, y+dy
+    // (clamped) with weights h0, h1; same for columns.  T(r) = the horizontally blended low-res row r (2 pixels
+    // x 8 channels per thread) is cached in registers for the two rows in use: consecutive upsampled rows
+    // share them, so a new low-res row is fetched only every second row.
+    constexpr int NT = 32 * Cfg::UPS_WARPS, C8 = Cfg::KC / 8;
+    static_assert(!UPS || (NT == 64 * C8), "one producer thread per (low-res column, 8-channel chunk)");
     const int pt = threadIdx.x - 192;
+    const int x = pt / C8, ch = pt % C8;
     const int lh = p.H >> 1, lw = p.W >> 1;
     const __half* src_hi = reinterpret_cast<const __half*>(p.ups_src);
     const __half* src_lo = src_hi + p.ups_plane;
-    uint4 pa[LRK], pb[LRK];
-    auto prefetch = [&](int t) {
-      const int grp = t / tiles_per_group, trem = t - grp * tiles_per_group;     // tiles_n == 1, BNI == 1
-      const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
-      const int ly0 = ((ty * BH) >> 1) - 1, lx0 = ((tx * BW) >> 1) - 1;
+    const int xm = max(x - 1, 0), xp = min(x + 1, lw - 1);
+    const float w1a = x == 0 ? 1.f : 0.75f, w0a = 1.f - w1a;       // X = 2x   : w0a * L[x-1] + w1a * L[x]
+    const float w1b = 0.25f, w0b = 0.75f;                          // X = 2x+1 : w0b * L[x]   + w1b * L[x+1]
+    uint8_t* const ring_hi = base_ptr;
+    uint8_t* const ring_lo = base_ptr + Cfg::NST * Cfg::UPS_PLANE;
+    // zero columns X = -1 and X = 128 of every ring row, once (the slots keep their layout)
+    if (pt < Cfg::NST * 2 * C8) {
+      const int slot = pt / (2 * C8), side = (pt / C8) & 1, c = pt % C8;
+      const uint32_t r = slot * Cfg::UPS_PX + (side ? Cfg::UPS_PX - 1 : 0);
+      const uint32_t off = r * ROW_BYTES + ((c ^ ((r >> 1) & 3)) << 4);
+      *reinterpret_cast<uint4*>(ring_hi + off) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(ring_lo + off) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    float ta[16], tb[16];            // T(row_a), T(row_b): [pixel 0 | pixel 1][8 channels]
+    int id_a = -1, id_b = -1;        // (image * lh + low-res row) held in ta / tb
+    auto load_t = [&](int img, int r, float* t) {
+      const size_t rowoff = ((size_t)img * lh + r) * lw;
+      float l[3][8];
 #pragma unroll
-      for (int k = 0; k < LRK; ++k) {
-        const int i = pt + k * NT;
-        if (i < LRI) {
-          const int ch = i % C8, c = (i / C8) % LC, r = i / (C8 * LC);
-          const int yy = min(max(ly0 + r, 0), lh - 1), xx = min(max(lx0 + c, 0), lw - 1);
-          const size_t idx = (((size_t)grp * lh + yy) * lw + xx) * Cfg::KC + ch * 8;
-          pa[k] = __ldg(reinterpret_cast<const uint4*>(src_hi + idx));
-          pb[k] = __ldg(reinterpret_cast<const uint4*>(src_lo + idx));
+      for (int k = 0; k < 3; ++k) {
+        const int xx = k == 0 ? xm : (k == 1 ? x : xp);
+        const size_t idx = (rowoff + xx) * Cfg::KC + ch * 8;
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(src_hi + idx));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(src_lo + idx));
+        const __half2* ah = reinterpret_cast<const __half2*>(&a);
+        const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+        for (int tt = 0; tt < 4; ++tt) {
+          const float2 u = __half22float2(ah[tt]), v = __half22float2(bh[tt]);
+          l[k][2 * tt] = u.x + v.x; l[k][2 * tt + 1] = u.y + v.y;
         }
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        t[c] = w0a * l[0][c] + w1a * l[1][c];
+        t[8 + c] = w0b * l[1][c] + w1b * l[2][c];
       }
     };
-    if ((int)blockIdx.x < p.total_tiles) prefetch(blockIdx.x);
-    uint32_t it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, it += 3) {
-      const int grp = t / tiles_per_group, trem = t - grp * tiles_per_group;
-      const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
-      const int y0 = ty * BH, x0 = tx * BW;
-      const int ly0 = (y0 >> 1) - 1, lx0 = (x0 >> 1) - 1;
-      asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory");        // the previous tile no longer reads lr
-#pragma unroll
-      for (int k = 0; k < LRK; ++k) {
-        const int i = pt + k * NT;
-        if (i < LRI) {
-          const __half2* ah = reinterpret_cast<const __half2*>(&pa[k]);
-          const __half2* bh = reinterpret_cast<const __half2*>(&pb[k]);
-          float v[8];
-#pragma unroll
-          for (int tt = 0; tt < 4; ++tt) {
-            const float2 x = __half22float2(ah[tt]), y = __half22float2(bh[tt]);
-            v[2 * tt] = x.x + y.x; v[2 * tt + 1] = x.y + y.y;
-          }
-          lrA[i] = make_float4(v[0], v[1], v[2], v[3]);
-          lrB[i] = make_float4(v[4], v[5], v[6], v[7]);
-        }
-      }
-      asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory");
-      if (t + (int)gridDim.x < p.total_tiles) prefetch(t + gridDim.x);
-      // the three ring stages of this tile (kw = 0, 1, 2) must have been consumed by the MMA warp
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const uint32_t j = it + kw;
-        mbar_wait(bars + 8 * (Cfg::NST + j % Cfg::NST), ((j / Cfg::NST) & 1) ^ 1);
-      }
-      const uint32_t st0 = it % Cfg::NST;                          // NST is a multiple of 3: stages st0, st0+1, st0+2
-      uint8_t* const sbase = base_ptr + st0 * Cfg::STAGE;
-#pragma unroll 1
-      for (int i = pt; i < ((p.dbg & 32) ? 0 : (BH + 2) * BWX * C8); i += NT) {
-        const int ch = i % C8, px = i / C8;
-        const int by = px / BWX, bx = px - by * BWX;
-        const int Y = y0 - 1 + by, X = x0 - 1 + bx;
-        uint4 hi4 = make_uint4(0u, 0u, 0u, 0u), lo4 = hi4;
-        if (Y >= 0 && Y < p.H && X >= 0 && X < p.W) {
-          // F.interpolate(scale 2, bilinear, align_corners=False), same expression tree as upsample2x_kernel
-          const int y = Y >> 1, dy = Y & 1, x = X >> 1, dx = X & 1;
+    uint32_t pc = 0;                 // produced-row counter
+    int g = ups_r0;
+    while (g < ups_r1) {
+      // segment = the rows of [g, ups_r1) that lie in one image: upsampled rows ys-1 .. ye are produced
+      const int img = g / p.H, ys = g - img * p.H;
+      const int ye = min(p.H, ys + (ups_r1 - g));
+      for (int Y = ys - 1; Y <= ye; ++Y, ++pc) {
+        const uint32_t slot = pc % Cfg::NST;
+        mbar_wait(bars + 8 * (Cfg::NST + slot), ((pc / Cfg::NST) & 1) ^ 1);
+        uint4 hi4[2], lo4[2];
+        hi4[0] = hi4[1] = lo4[0] = lo4[1] = make_uint4(0u, 0u, 0u, 0u);
+        if (Y >= 0 && Y < p.H && !(p.dbg & 32)) {
+          const int y = Y >> 1, dy = Y & 1;
+          const int ra = img * lh + max(y - 1 + dy, 0), rb = img * lh + min(y + dy, lh - 1);
           const float h1 = dy == 0 ? (y == 0 ? 1.f : 0.75f) : 0.25f, h0 = 1.f - h1;
-          const float w1 = dx == 0 ? (x == 0 ? 1.f : 0.75f) : 0.25f, w0 = 1.f - w1;
-          const int q = ((y - 1 + dy - ly0) * LC + (x - 1 + dx - lx0)) * C8 + ch;
-          const float4 a0 = lrA[q], a1 = lrB[q], b0 = lrA[q + C8], b1 = lrB[q + C8];
-          const float4 c0v = lrA[q + LC * C8], c1v = lrB[q + LC * C8], d0 = lrA[q + LC * C8 + C8], d1 = lrB[q + LC * C8 + C8];
-          float f[8];
-#define OFB_UP(A, B, Cc, D) (h0 * (w0 * (A) + w1 * (B)) + h1 * (w0 * (Cc) + w1 * (D)))
-          f[0] = OFB_UP(a0.x, b0.x, c0v.x, d0.x); f[1] = OFB_UP(a0.y, b0.y, c0v.y, d0.y);
-          f[2] = OFB_UP(a0.z, b0.z, c0v.z, d0.z); f[3] = OFB_UP(a0.w, b0.w, c0v.w, d0.w);
-          f[4] = OFB_UP(a1.x, b1.x, c1v.x, d1.x); f[5] = OFB_UP(a1.y, b1.y, c1v.y, d1.y);
-          f[6] = OFB_UP(a1.z, b1.z, c1v.z, d1.z); f[7] = OFB_UP(a1.w, b1.w, c1v.w, d1.w);
-#undef OFB_UP
-          __half2* hh = reinterpret_cast<__half2*>(&hi4);
-          __half2* ll = reinterpret_cast<__half2*>(&lo4);
+          // CTA-uniform branches: the row ids depend on Y only
+          if (ra != id_a) {
+            if (ra == id_b) {
 #pragma unroll
-          for (int tt = 0; tt < 4; ++tt) {
-            const __half2 h = __floats2half2_rn(f[2 * tt], f[2 * tt + 1]);
-            const float2 hf = __half22float2(h);
-            hh[tt] = h;
-            ll[tt] = __floats2half2_rn(f[2 * tt] - hf.x, f[2 * tt + 1] - hf.y);
+              for (int c = 0; c < 16; ++c) ta[c] = tb[c];
+            } else {
+              load_t(img, ra - img * lh, ta);
+            }
+            id_a = ra;
+          }
+          if (rb != id_b) {
+            if (rb == id_a) {
+#pragma unroll
+              for (int c = 0; c < 16; ++c) tb[c] = ta[c];
+            } else {
+              load_t(img, rb - img * lh, tb);
+            }
+            id_b = rb;
+          }
+#pragma unroll
+          for (int px = 0; px < 2; ++px) {
+            __half2* hh = reinterpret_cast<__half2*>(&hi4[px]);
+            __half2* ll = reinterpret_cast<__half2*>(&lo4[px]);
+#pragma unroll
+            for (int tt = 0; tt < 4; ++tt) {
+              const float f0 = h0 * ta[px * 8 + 2 * tt] + h1 * tb[px * 8 + 2 * tt];
+              const float f1 = h0 * ta[px * 8 + 2 * tt + 1] + h1 * tb[px * 8 + 2 * tt + 1];
+              const __half2 hv = __floats2half2_rn(f0, f1);
+              const float2 hf = __half22float2(hv);
+              hh[tt] = hv;
+              ll[tt] = __floats2half2_rn(f0 - hf.x, f1 - hf.y);
+            }
           }
         }
-        // pixel column bx of the halo box is column bx - kw of the kw-shifted box
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int xx = bx - kw;
-          if (xx >= 0 && xx < BW) {
-            const int r = by * BW + xx;
-            uint8_t* dst = sbase + kw * Cfg::STAGE + r * ROW_BYTES +
-                           ((ROW_BYTES == 64 ? (ch ^ ((r >> 1) & 3)) : (ch ^ (r & 7))) << 4);
-            *reinterpret_cast<uint4*>(dst) = hi4;
-            *reinterpret_cast<uint4*>(dst + Cfg::A_BYTES) = lo4;
-          }
+        for (int px = 0; px < 2; ++px) {
+          const uint32_t r = slot * Cfg::UPS_PX + 1 + 2 * x + px;
+          const uint32_t off = r * ROW_BYTES + ((ch ^ ((r >> 1) & 3)) << 4);
+          *reinterpret_cast<uint4*>(ring_hi + off) = hi4[px];
+          *reinterpret_cast<uint4*>(ring_lo + off) = lo4[px];
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + 8 * slot);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
-      __syncwarp();
-      if (lane == 0) {
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) mbar_arrive(bars + 8 * (st0 + kw));
-      }
+      g += ye - ys;
     }
   }
   tc_fence_before();
@@ -773,7 +845,7 @@ static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 // 2x-upsample-fused variant: 32 -> 32 channels, 3x3 stride 1, split-half format, 32 x 4 pixel tiles
 static bool conv_tc_ups_supported(const ofb_conv_desc* d) {
   return d->in_fmt == OFB_FMT_SPLIT16 && d->out_fmt == OFB_FMT_SPLIT16 && d->wgt_split && d->k == 3 && d->stride == 1 &&
-         d->pad == 1 && d->c0 == 32 && (!d->in1 || d->c1 == 0) && d->cout == 32 && d->w % 32 == 0 && d->h % 4 == 0;
+         d->pad == 1 && d->c0 == 32 && (!d->in1 || d->c1 == 0) && d->cout == 32 && d->w == 128 && d->h % 2 == 0;
 }
 
 bool conv_tc_supported(const ofb_conv_desc* d) {
@@ -797,8 +869,17 @@ static bool g_pdl = true;      // programmatic dependent launch for the tensor-c
 static bool g_store128 = true;  // bulk-tensor-store epilogue also for the 128-wide tiles
 static bool g_cta2 = true;      // cta_group::2 CTA pairs for the 128-wide split-half tiles
 void conv_tc_set_cta2(bool on) { g_cta2 = on; }
+static bool g_direct32 = false;  // BN = 32 split-half tiles store straight from registers instead of bulk tensor stores
+void conv_tc_set_direct32(bool on) { g_direct32 = on; }
+static int g_fill_div = 2;      // shrink the N tile while fewer than num_sms / g_fill_div tiles exist
+void conv_tc_set_fill_div(int v) { g_fill_div = v > 0 ? v : 2; }
 static int g_dbg = 0;           // TcParams::dbg (timing experiments)
+static long long* g_dbg_buf = nullptr;
 void conv_tc_set_debug(int v) { g_dbg = v; }
+long long* conv_tc_debug_buffer() {
+  if (!g_dbg_buf) cudaMalloc(&g_dbg_buf, 512 * 8 * sizeof(long long));
+  return g_dbg_buf;
+}
 void conv_tc_set_pdl(bool on) { g_pdl = on; }
 void conv_tc_set_store128(bool on) { g_store128 = on; }
 
@@ -859,12 +940,19 @@ static int launch_bn(int bn, bool khr, bool cta2, const TcMaps& maps, const TcPa
   }
   if (MODE == MODE_F16X3 && khr) {
     if (p.ups_src) {
-      if (ROW_BYTES == 64) return launch_tc<32, MODE_F16X3, 64, true, true, true, true>(maps, p, s);
+      if (ROW_BYTES == 64) {
+        if (g_direct32) return launch_tc<32, MODE_F16X3, 64, false, true, true, true>(maps, p, s);
+        return launch_tc<32, MODE_F16X3, 64, true, true, true, true>(maps, p, s);
+      }
       OFB_CHECK(false, "conv_tc: fused upsample needs 64-byte rows");
     }
     if (bn == 64) return launch_tc<64, MODE_F16X3, ROW_BYTES, true, true>(maps, p, s);
     // 32 -> 32 channels: the whole filter stays resident in shared memory
-    if (ROW_BYTES == 64 && p.c0 + p.c1 == 32 && p.cout == 32) return launch_tc<32, MODE_F16X3, 64, true, true, true>(maps, p, s);
+    if (ROW_BYTES == 64 && p.c0 + p.c1 == 32 && p.cout == 32) {
+      if (g_direct32) return launch_tc<32, MODE_F16X3, 64, false, true, true>(maps, p, s);
+      return launch_tc<32, MODE_F16X3, 64, true, true, true>(maps, p, s);
+    }
+    if (g_direct32) return launch_tc<32, MODE_F16X3, ROW_BYTES, false, true>(maps, p, s);
     return launch_tc<32, MODE_F16X3, ROW_BYTES, true, true>(maps, p, s);
   }
   if (bn == 64) return launch_tc<64, MODE, ROW_BYTES, true, false>(maps, p, s);
@@ -892,6 +980,7 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
   p.residual = d->residual; p.out = d->out; p.act = d->act;
   p.plane = (long long)d->n * oh * ow * d->cout;
   p.dbg = g_dbg;
+  p.dbg_buf = (g_dbg & 16) ? conv_tc_debug_buffer() : nullptr;
   p.group64 = g_cta2 ? 1 : 0;
   const int groups = (d->n + p.BNI - 1) / p.BNI;
   // kh-reuse tiling for the narrow 3x3 layers: 32x4 / 16x8 pixel tiles inside one image.  Decided from the
@@ -901,7 +990,7 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
   // widest N tile unless that leaves most SMs without a tile
   int bn = d->cout >= 128 ? 128 : d->cout;
   // (only for really small problems such as the token linears: narrow tiles re-read the A tile more often)
-  while (!khr && bn > 32 && (long long)groups * p.tiles_x * p.tiles_y * (d->cout / bn) < num_sms() / 4) bn >>= 1;
+  while (!khr && bn > 32 && (long long)groups * p.tiles_x * p.tiles_y * (d->cout / bn) < num_sms() / g_fill_div) bn >>= 1;
   int groups_k = groups;
   if (khr) {
     p.BW = ow < 32 ? ow : 32; p.BH = 128 / p.BW; p.BNI = 1;
@@ -918,7 +1007,10 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
   memset(&maps, 0, sizeof(maps));
   const int planes = split ? 2 : 1;
   if (d->ups2x) {
-    OFB_CHECK(khr && p.BW == 32 && p.BH == 4, "conv_tc: fused upsample needs 32x4 pixel tiles");
+    // rolling-row kernel: tile = one image row of 128 pixels, a CTA walks a contiguous range of rows
+    OFB_CHECK(khr && ow == 128, "conv_tc: fused upsample needs 128-pixel rows");
+    p.BW = 128; p.BH = 1; p.BNI = 1; p.tiles_x = 1; p.tiles_y = oh;
+    p.total_tiles = d->n * oh;
     p.ups_src = d->in0;
     p.ups_plane = (long long)d->n * (d->h / 2) * (d->w / 2) * d->c0;
   }
@@ -952,7 +1044,9 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
   }
   if (bn < 128 || g_store128) {      // output tensor maps for the bulk-store epilogue: box = 32 columns x the pixel box
     cuuint64_t dims[4] = {(cuuint64_t)d->cout, (cuuint64_t)ow, (cuuint64_t)oh, (cuuint64_t)d->n};
-    cuuint32_t box[4] = {32u, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BNI};
+    // one store per epilogue warp: 32 consecutive pixels of the tile
+    const int sbw = p.BW < 32 ? p.BW : 32, sbh = 32 / sbw < p.BH ? 32 / sbw : p.BH, sbn = 32 / (sbw * sbh);
+    cuuint32_t box[4] = {32u, (cuuint32_t)sbw, (cuuint32_t)sbh, (cuuint32_t)sbn};
     for (int pl = 0; pl < planes; ++pl) {
       char* a = (char*)d->out + (size_t)pl * p.plane * es;
       if (make_map(&maps.o[pl], split, 4, a, dims, box, 32 * es)) return -1;
@@ -1003,7 +1097,7 @@ int stem_tc(const void* patches, int n, int h, int w, const void* wgt_split, flo
     cuuint32_t bb[2] = {32u, 64u};
     if (make_map(&maps.b[pl], true, 2, (char*)wgt_split + (size_t)pl * 64 * 7 * 32 * 2, bd, bb, 64)) return -1;
     cuuint64_t od[4] = {64, (cuuint64_t)ow, (cuuint64_t)oh, (cuuint64_t)n};
-    cuuint32_t ob[4] = {32u, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1u};
+    cuuint32_t ob[4] = {32u, (cuuint32_t)(p.BW < 32 ? p.BW : 32), (cuuint32_t)(p.BW < 32 ? 32 / p.BW : 1), 1u};   // per-warp sub-box
     if (make_map(&maps.o[pl], true, 4, (char*)out + (size_t)pl * p.plane * 2, od, ob, 64)) return -1;
   }
   return launch_tc<64, MODE_F16X3, 64, true, false>(maps, p, s);

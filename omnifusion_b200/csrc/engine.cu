@@ -36,6 +36,9 @@ void conv_tc_set_pdl(bool on);
 void conv_tc_set_store128(bool on);
 void conv_tc_set_cta2(bool on);
 void conv_tc_set_debug(int v);
+void conv_tc_set_fill_div(int v);
+long long* conv_tc_debug_buffer();
+void conv_tc_set_direct32(bool on);
 
 int conv_dispatch(const ofb_conv_desc* d, cudaStream_t s) {
   OFB_CHECK(d && d->in0 && (d->wgt || d->wgt_split) && d->out, "conv: null pointer");
@@ -668,6 +671,8 @@ extern "C" int ofb_set_option(ofb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "pdl")) conv_tc_set_pdl(value != 0);     // process-wide: programmatic dependent launch
   else if (!strcmp(key, "store128")) conv_tc_set_store128(value != 0);
   else if (!strcmp(key, "tc_debug")) conv_tc_set_debug(value);         // timing experiments only (wrong results)
+  else if (!strcmp(key, "fill_div")) conv_tc_set_fill_div(value);   // process-wide: N-tile shrink threshold (experiments)
+  else if (!strcmp(key, "direct32")) conv_tc_set_direct32(value != 0);   // process-wide (experiments)
   else if (!strcmp(key, "cta2")) conv_tc_set_cta2(value != 0);          // process-wide: cta_group::2 CTA pairs
   else if (!strcmp(key, "format")) {
     OFB_CHECK(value == OFB_FMT_F32 || value == OFB_FMT_SPLIT16, "set_option: format must be 0 (float32) or 1 (split-half)");
@@ -695,6 +700,13 @@ extern "C" int ofb_forward_f32(ofb_handle* h, const float* rgb, int B, int iters
                       (cudaStream_t)stream))
       return -1;
   }
+  return 0;
+}
+
+// timing experiments: copies the clock stamps recorded with tc_debug & 16 (512 x 8 int64) to the host
+extern "C" int ofb_debug_stamps(long long* host_dst) {
+  OFB_CUDA(cudaDeviceSynchronize());
+  OFB_CUDA(cudaMemcpy(host_dst, conv_tc_debug_buffer(), 512 * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -301,68 +301,76 @@ __global__ void layernorm_kernel(const void* __restrict__ x, const float* __rest
 }
 
 // ------------------------------------------------------------------ attention
-// One CTA per (panorama, head): N <= 64 tokens, head_dim 128.  Q,K,V staged in shared
-// memory (rows padded to 129 floats), scores + softmax + PV entirely on chip.
-constexpr int ATT_MAXN = 64, ATT_D = 128, ATT_LD = ATT_D + 1;
+// One CTA per (panorama, head, group of ATT_RG query rows): N <= 64 tokens, head_dim 128.  K, V and the
+// group's Q rows are staged in shared memory (rows padded to 132 floats: 16-byte aligned, bank-skewed),
+// scores + softmax + PV entirely on chip.  Splitting the query rows over CTAs triples the number of CTAs
+// of this latency-bound kernel (32 -> 96 at 8 panoramas).
+constexpr int ATT_MAXN = 64, ATT_D = 128, ATT_LD = ATT_D + 4, ATT_RG = 6;
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(128)
 attention_kernel(const void* __restrict__ q, int q_ld, const void* __restrict__ kv, int kv_ld, int kv_col0,
-                 int N, int heads, float scale, void* __restrict__ out, int rows) {
-  extern __shared__ float sm[];
-  float* sq = sm;
-  float* sk = sq + N * ATT_LD;
-  float* sv = sk + N * ATT_LD;
-  float* sp = sv + N * ATT_LD;        // [N][N+1]
-  int b = blockIdx.x / heads, hd = blockIdx.x % heads;
-  int dim = heads * ATT_D;
-  int tid = threadIdx.x;
+                 int N, int heads, int groups, float scale, void* __restrict__ out, int rows) {
+  extern __shared__ __align__(16) float sm[];
+  float* sq = sm;                       // [ATT_RG][ATT_LD]
+  float* sk = sq + ATT_RG * ATT_LD;     // [N][ATT_LD]
+  float* sv = sk + N * ATT_LD;          // [N][ATT_LD]
+  float* sp = sv + N * ATT_LD;          // [ATT_RG][N+1]
+  const int g = blockIdx.x % groups, bh = blockIdx.x / groups;
+  const int b = bh / heads, hd = bh % heads;
+  const int r_begin = g * ATT_RG, nr = min(ATT_RG, N - r_begin);
+  const int dim = heads * ATT_D;
+  const int tid = threadIdx.x;
   // fill: 8 channels per load, four independent loads in flight per thread before the smem stores
   {
-    const int chunks = N * 16 * 3;                 // (row, 8-channel chunk) x {q,k,v}
+    const int qchunks = nr * 16, chunks = qchunks + 2 * N * 16;     // (row, 8-channel chunk) of q | k | v
     const size_t qplane = (size_t)rows * q_ld, kvplane = (size_t)rows * kv_ld;
     for (int i0 = tid; i0 < chunks; i0 += 128 * 4) {
       float8 v[4];
       int dst[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        int i = i0 + u * 128;
+        const int i = i0 + u * 128;
         dst[u] = -1;
         if (i < chunks) {
-          int which = i / (N * 16), rem = i - which * (N * 16);
-          int r = rem >> 4, d = (rem & 15) * 8;
-          size_t row = (size_t)b * N + r;
-          if (which == 0) v[u] = act_ld8<SPLIT>(q, row * q_ld + hd * ATT_D + d, qplane);
-          else v[u] = act_ld8<SPLIT>(kv, row * kv_ld + kv_col0 + (which - 1) * dim + hd * ATT_D + d, kvplane);
-          dst[u] = which * N * ATT_LD + r * ATT_LD + d;
+          if (i < qchunks) {
+            const int r = i >> 4, d = (i & 15) * 8;
+            v[u] = act_ld8<SPLIT>(q, ((size_t)b * N + r_begin + r) * q_ld + hd * ATT_D + d, qplane);
+            dst[u] = r * ATT_LD + d;
+          } else {
+            const int j = i - qchunks;
+            const int which = j / (N * 16), rem = j - which * (N * 16);
+            const int r = rem >> 4, d = (rem & 15) * 8;
+            v[u] = act_ld8<SPLIT>(kv, ((size_t)b * N + r) * kv_ld + kv_col0 + which * dim + hd * ATT_D + d, kvplane);
+            dst[u] = (ATT_RG + which * N + r) * ATT_LD + d;
+          }
         }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (dst[u] < 0) continue;
-        float* o = sm + dst[u];
-        o[0] = v[u].a.x; o[1] = v[u].a.y; o[2] = v[u].a.z; o[3] = v[u].a.w;
-        o[4] = v[u].b.x; o[5] = v[u].b.y; o[6] = v[u].b.z; o[7] = v[u].b.w;
+        *reinterpret_cast<float4*>(sm + dst[u]) = v[u].a;
+        *reinterpret_cast<float4*>(sm + dst[u] + 4) = v[u].b;
       }
     }
   }
   __syncthreads();
-  for (int i = tid; i < N * N; i += 128) {
-    int r = i / N, c = i % N;
+  for (int i = tid; i < nr * N; i += 128) {
+    const int r = i / N, c = i % N;
+    const float4* qr = reinterpret_cast<const float4*>(sq + r * ATT_LD);
+    const float4* kr = reinterpret_cast<const float4*>(sk + c * ATT_LD);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 8
-    for (int d = 0; d < ATT_D; d += 4) {
-      a0 += sq[r * ATT_LD + d] * sk[c * ATT_LD + d];
-      a1 += sq[r * ATT_LD + d + 1] * sk[c * ATT_LD + d + 1];
-      a2 += sq[r * ATT_LD + d + 2] * sk[c * ATT_LD + d + 2];
-      a3 += sq[r * ATT_LD + d + 3] * sk[c * ATT_LD + d + 3];
+    for (int d = 0; d < ATT_D / 4; ++d) {
+      const float4 x = qr[d], y = kr[d];
+      a0 += x.x * y.x; a1 += x.y * y.y; a2 += x.z * y.z; a3 += x.w * y.w;
     }
     sp[r * (N + 1) + c] = ((a0 + a1) + (a2 + a3)) * scale;
   }
   __syncthreads();
   // softmax: one warp per row
-  int lane = tid & 31, wid = tid >> 5;
-  for (int r = wid; r < N; r += 4) {
+  const int lane = tid & 31, wid = tid >> 5;
+  for (int r = wid; r < nr; r += 4) {
     float m = -INFINITY;
     for (int c = lane; c < N; c += 32) m = fmaxf(m, sp[r * (N + 1) + c]);
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -378,17 +386,17 @@ attention_kernel(const void* __restrict__ q, int q_ld, const void* __restrict__ 
   }
   __syncthreads();
   // out[r][d] = sum_c P[r][c] V[c][d]; thread = d
-  for (int r0 = 0; r0 < N; r0 += 4) {
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int c = 0; c < N; ++c) {
-      float vv = sv[c * ATT_LD + tid];
+  float a[ATT_RG];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) a[u] += sp[min(r0 + u, N - 1) * (N + 1) + c] * vv;
-    }
+  for (int u = 0; u < ATT_RG; ++u) a[u] = 0.f;
+  for (int c = 0; c < N; ++c) {
+    const float vv = sv[c * ATT_LD + tid];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (r0 + u < N) act_st1<SPLIT>(out, ((size_t)b * N + r0 + u) * dim + hd * ATT_D + tid, (size_t)rows * dim, a[u]);
+    for (int u = 0; u < ATT_RG; ++u) a[u] += sp[min(u, nr - 1) * (N + 1) + c] * vv;
   }
+#pragma unroll
+  for (int u = 0; u < ATT_RG; ++u)
+    if (u < nr) act_st1<SPLIT>(out, ((size_t)b * N + r_begin + u) * dim + hd * ATT_D + tid, (size_t)rows * dim, a[u]);
 }
 
 // ---------------------------------------------------------------------- heads
@@ -548,7 +556,8 @@ static int attention_launch(const void* q, int q_ld, const void* kv, int kv_ld, 
                             int head_dim, void* out, int fmt, void* stream) {
   OFB_CHECK(q && kv && out && OFB_FMT_OK(fmt), "attention: bad arguments");
   OFB_CHECK(head_dim == ATT_D && N <= ATT_MAXN && N > 0, "attention: head_dim must be 128 and N <= 64 (got %d, %d)", head_dim, N);
-  int smem = (3 * N * ATT_LD + N * (N + 1)) * 4;
+  const int groups = (N + ATT_RG - 1) / ATT_RG;
+  int smem = ((ATT_RG + 2 * N) * ATT_LD + ATT_RG * (N + 1)) * 4;
   static int attr_smem = 0;
   if (smem > attr_smem) {
     OFB_CUDA(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -556,8 +565,8 @@ static int attention_launch(const void* q, int q_ld, const void* kv, int kv_ld, 
     attr_smem = smem;
   }
   float sc = 1.f / sqrtf((float)head_dim);
-  if (fmt) attention_kernel<true><<<B * heads, 128, smem, (cudaStream_t)stream>>>(q, q_ld, kv, kv_ld, kv_col0, N, heads, sc, out, B * N);
-  else attention_kernel<false><<<B * heads, 128, smem, (cudaStream_t)stream>>>(q, q_ld, kv, kv_ld, kv_col0, N, heads, sc, out, B * N);
+  if (fmt) attention_kernel<true><<<B * heads * groups, 128, smem, (cudaStream_t)stream>>>(q, q_ld, kv, kv_ld, kv_col0, N, heads, groups, sc, out, B * N);
+  else attention_kernel<false><<<B * heads * groups, 128, smem, (cudaStream_t)stream>>>(q, q_ld, kv, kv_ld, kv_col0, N, heads, groups, sc, out, B * N);
   OFB_LAUNCH_CHECK();
   return 0;
 }

@@ -140,11 +140,14 @@ def test_stem_on_tensor_cores_matches_fp32():
     assert (err <= 3e-5 + 3e-5 * ref.abs()).all()
 
 
-@pytest.mark.parametrize("n,hw", [(1, 64), (3, 16), (2, 32)])
+@pytest.mark.parametrize("n,hw", [(1, 64), (3, 64), (150, 64)])
 def test_conv_tc_fused_upsample_matches_interpolate_then_conv(n, hw):
     """de_conv4_0 with the decoder's last F.interpolate(x2, bilinear, align_corners=False) folded into the
     conv's operand producer (ofb_conv_desc.ups2x): against torch-CPU fp32, and against libofb's own
-    unfused upsample2x kernel + conv (same expression tree, same accumulation order)."""
+    unfused upsample2x kernel + conv (same expression tree, same accumulation order).  The fused kernel
+    walks contiguous ranges of 128-pixel output rows per CTA: n=1 gives CTAs one row each (every row is a
+    segment with both halo rows re-produced), n=3 makes ranges cross image boundaries, n=150 exceeds the
+    ring of upsampled rows many times over."""
     o = ops()
     x = rand(n, 32, hw, hw, seed=11)
     w = rand(32, 32, 3, 3, seed=12, scale=(1.0 / (32 * 9)) ** 0.5)

@@ -57,8 +57,19 @@ def time_conv(d, iters=20):
 shapes = [("de_conv4_0 ups", 144, 128, 32, 0, 32, 1), ("de_conv4_0 plain", 144, 128, 32, 0, 32, 0),
           ("de_conv3_1", 144, 64, 64, 64, 32, 0), ("de_conv3_0", 144, 64, 64, 0, 64, 0),
           ("layer1", 144, 32, 64, 0, 64, 0), ("de_conv2_1", 144, 32, 64, 64, 64, 0)]
-names = {0: "full", 3: "noMMA", 32: "noInterp", 64: "noEpi", 67: "noMMA+noEpi", 99: "noMMA+noInterp+noEpi", 12: "noLoads", 79: "noLoads+noMMA+noEpi"}
-for (nm, n, hw, c0, c1, cout, ups) in shapes:
+names = {128: "noStore", 160: "noStore+noInterp", 0: "full", 3: "noMMA", 32: "noInterp", 64: "noEpi", 67: "noMMA+noEpi", 99: "noMMA+noInterp+noEpi", 12: "noLoads", 79: "noLoads+noMMA+noEpi"}
+for direct in (0, 1):
+  opt("direct32", direct)
+  print("direct32 =", direct)
+  for (nm, n, hw, c0, c1, cout, ups) in shapes[:3]:
+    d, keep = make(n, hw, c0, c1, cout, ups)
+    row = []
+    for dbg in (0, 64, 128, 32, 160):
+        opt("tc_debug", dbg)
+        row.append(f"{names[dbg]}={time_conv(d):.1f}us")
+    opt("tc_debug", 0)
+    print(f"{nm} n={n} {hw}x{hw} c{c0}+{c1}->o{cout}: " + "  ".join(row), flush=True)
+for (nm, n, hw, c0, c1, cout, ups) in []:
     d, keep = make(n, hw, c0, c1, cout, ups)
     row = []
     for dbg in ((0, 3, 32, 64, 67, 99) if ups else (0, 3, 64, 67, 12, 79)):
@@ -66,3 +77,23 @@ for (nm, n, hw, c0, c1, cout, ups) in shapes:
         row.append(f"{names[dbg]}={time_conv(d):.1f}us")
     opt("tc_debug", 0)
     print(f"{nm} n={n} {hw}x{hw} c{c0}+{c1}->o{cout}: " + "  ".join(row), flush=True)
+
+# ---- clock stamps of epilogue warp 2 of CTA 0
+import numpy as np
+L.ofb_debug_stamps.restype = C.c_int
+L.ofb_debug_stamps.argtypes = [C.c_void_p]
+opt("direct32", 0)
+for (nm, n, hw, c0, c1, cout, ups) in shapes[:3]:
+    d, keep = make(n, hw, c0, c1, cout, ups)
+    opt("tc_debug", 16)
+    st = _lib.stream_of(DEV)
+    for _ in range(2):
+        _lib.check(L.ofb_conv_f32(C.byref(d), st))
+    buf = np.zeros((512, 8), dtype=np.int64)
+    _lib.check(L.ofb_debug_stamps(buf.ctypes.data))
+    opt("tc_debug", 0)
+    T = buf[8:28]
+    print(nm, "stamps per tile: wait_tfull | ldtm+arrive | math | wait_group | sts | fence | store ; period")
+    for k in range(len(T) - 1):
+        r = T[k]
+        print("  ", [int(r[j + 1] - r[j]) for j in range(7)], int(T[k + 1][0] - r[0]))
