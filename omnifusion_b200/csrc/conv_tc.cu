@@ -509,6 +509,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     const int r = q * 32 + lane;               // accumulator row = pixel within the tile
     const int xx = r % p.BW, yy = (r / p.BW) % p.BH, ni = r / (p.BW * p.BH);
     const int et = threadIdx.x - 64;           // 0..127
+    // sub-box of warp q for the bulk stores = pixels 32q .. 32q+31 of the tile (box dims chosen on the host to match)
+    const int sub_x = (q * 32) % p.BW, sub_y = ((q * 32) / p.BW) % p.BH, sub_n = (q * 32) / (p.BW * p.BH);
     int last_n0 = -1;
     uint32_t i = 0, chunk_ctr = 0;
     for (int t = UPS ? ups_r0 : tile0; t < (UPS ? ups_r1 : p.total_tiles); t += UPS ? 1 : tile_step, ++i) {
@@ -638,13 +640,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           __syncwarp();
           if (stamp) p.dbg_buf[i * 8 + 6] = clock64();
           if (lane == 0 && !(p.dbg & 128)) {
-            // sub-box of warp q = pixels 32q .. 32q+31 of the tile (box dims chosen on the host to match)
-            const int r0 = q * 32;
-            const int sx = r0 % p.BW, sy = (r0 / p.BW) % p.BH, sn = r0 / (p.BW * p.BH);
-            const uint32_t src = stage_out + sbuf * Cfg::OUT_BUF + (uint32_t)(r0 * Cfg::OUT_ROW);
+            const uint32_t src = stage_out + sbuf * Cfg::OUT_BUF + (uint32_t)(q * 32 * Cfg::OUT_ROW);
 #pragma unroll
             for (int pl = 0; pl < Cfg::PLANES; ++pl)
-              tma_store_4d(&maps.o[pl], src + pl * 128 * Cfg::OUT_ROW, n0 + cb, x0 + sx, y0 + sy, img0 + sn);   // OOB images are clipped
+              tma_store_4d(&maps.o[pl], src + pl * 128 * Cfg::OUT_ROW, n0 + cb, x0 + sub_x, y0 + sub_y, img0 + sub_n);   // OOB images are clipped
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           if (stamp) p.dbg_buf[i * 8 + 7] = clock64();

@@ -207,41 +207,46 @@ point_embed_kernel(const float* __restrict__ pts, int N, int cin, int p,
   __shared__ __align__(16) float w2s[16][64];
   for (int i = threadIdx.x; i < 1024; i += 256) w2s[i & 15][i >> 4] = __ldg(&w2[i]);   // w2 is [co][k]
   __syncthreads();
-  size_t total = (size_t)imgs * p * p * 16;
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  bool live = i < total;
-  if (!live) i = total - 1;
-  int g = (int)(i & 15);
-  size_t pix = i >> 4;
-  int xy = (int)(pix % (p * p));
-  int img = (int)(pix / (p * p));
-  int n = img % N;
-  float dsc = depth ? __ldg(&depth[pix]) : 1.f;
-  float a = 0.f;
-  for (int c = 0; c < cin; ++c) {
-    float v = __ldg(&pts[((size_t)n * cin + c) * p * p + xy]);
-    if (depth && c < 3) v *= dsc;
-    a += v * __ldg(&w1[g * cin + c]);
-  }
-  float hid = fmaxf(a * __ldg(&s1[g]) + __ldg(&t1[g]), 0.f);
-  float o[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    float hk = __shfl_sync(0xffffffffu, hid, k, 16);
-    float4 w = *reinterpret_cast<const float4*>(&w2s[k][g * 4]);
-    o[0] += hk * w.x; o[1] += hk * w.y; o[2] += hk * w.z; o[3] += hk * w.w;
-  }
-  if (!live) return;
-  float4 sc = __ldg(reinterpret_cast<const float4*>(s2 + g * 4)), sh = __ldg(reinterpret_cast<const float4*>(t2 + g * 4));
-  float4 v = make_float4(fmaxf(o[0] * sc.x + sh.x, 0.f), fmaxf(o[1] * sc.y + sh.y, 0.f),
-                         fmaxf(o[2] * sc.z + sh.z, 0.f), fmaxf(o[3] * sc.w + sh.w, 0.f));
-  size_t off = pix * 64 + g * 4;
+  const size_t total = (size_t)imgs * p * p * 16;
   const size_t plane = (size_t)imgs * p * p * 64;
-  if (base) {
-    float4 b = act_ld4<SPLIT>(base, off, plane);
-    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+  const float s1g = __ldg(&s1[threadIdx.x & 15]), t1g = __ldg(&t1[threadIdx.x & 15]);
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(s2 + (threadIdx.x & 15) * 4));
+  const float4 sh = __ldg(reinterpret_cast<const float4*>(t2 + (threadIdx.x & 15) * 4));
+  // grid-stride over 16-pixel groups: the 4 KB weight stage above is paid once per CTA, not once per 16 pixels
+  for (size_t i0 = blockIdx.x * (size_t)blockDim.x; i0 < total; i0 += gridDim.x * (size_t)blockDim.x) {
+    size_t i = i0 + threadIdx.x;
+    const bool live = i < total;
+    if (!live) i = total - 1;
+    const int g = (int)(i & 15);
+    const size_t pix = i >> 4;
+    const int xy = (int)(pix % (p * p));
+    const int img = (int)(pix / (p * p));
+    const int n = img % N;
+    const float dsc = depth ? __ldg(&depth[pix]) : 1.f;
+    float a = 0.f;
+    for (int c = 0; c < cin; ++c) {
+      float v = __ldg(&pts[((size_t)n * cin + c) * p * p + xy]);
+      if (depth && c < 3) v *= dsc;
+      a += v * __ldg(&w1[g * cin + c]);
+    }
+    const float hid = fmaxf(a * s1g + t1g, 0.f);
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float hk = __shfl_sync(0xffffffffu, hid, k, 16);
+      const float4 w = *reinterpret_cast<const float4*>(&w2s[k][g * 4]);
+      o[0] += hk * w.x; o[1] += hk * w.y; o[2] += hk * w.z; o[3] += hk * w.w;
+    }
+    if (!live) continue;
+    float4 v = make_float4(fmaxf(o[0] * sc.x + sh.x, 0.f), fmaxf(o[1] * sc.y + sh.y, 0.f),
+                           fmaxf(o[2] * sc.z + sh.z, 0.f), fmaxf(o[3] * sc.w + sh.w, 0.f));
+    const size_t off = pix * 64 + g * 4;
+    if (base) {
+      const float4 b = act_ld4<SPLIT>(base, off, plane);
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    act_st4<SPLIT>(out, off, plane, v);
   }
-  act_st4<SPLIT>(out, off, plane, v);
 }
 
 // ----------------------------------------------------------------- token pack
@@ -522,8 +527,9 @@ extern "C" int ofb_point_embed_f32(const float* pts, int N, int cin, int p, cons
   OFB_CHECK(pts && w1 && s1 && t1 && w2 && s2 && t2 && out && OFB_FMT_OK(fmt), "point_embed: bad arguments");
   OFB_CHECK(cin >= 1 && cin <= 5, "point_embed: cin must be <= 5 (got %d)", cin);
   size_t total = (size_t)imgs * p * p * 16;
-  if (fmt) point_embed_kernel<true><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(pts, N, cin, p, depth, imgs, w1, s1, t1, w2, s2, t2, base, out);
-  else point_embed_kernel<false><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(pts, N, cin, p, depth, imgs, w1, s1, t1, w2, s2, t2, base, out);
+  const int blocks = (int)(cdiv(total, 256) < 148 * 8 ? cdiv(total, 256) : 148 * 8);
+  if (fmt) point_embed_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(pts, N, cin, p, depth, imgs, w1, s1, t1, w2, s2, t2, base, out);
+  else point_embed_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(pts, N, cin, p, depth, imgs, w1, s1, t1, w2, s2, t2, base, out);
   OFB_LAUNCH_CHECK();
   return 0;
 }
