@@ -288,12 +288,12 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
         if os.path.exists(tpath):
             t = json.load(open(tpath))
-            k = t["kernels"].get("conv_tc_kernel<128, 1, 128, 0, 0>")
+            k = t["kernels"].get("conv_tc_kernel<128, 1, 128, 1, 0, 0, 0, 1>")
             if k:
                 traffic = (k["dram_read_mb_per_launch"] + k["dram_write_mb_per_launch"]) * 1e6
                 traffic_src = t["source"]
         roofline = {"bound": "tensor",
-                    "kernel": "conv_tc_kernel<BN=128, F16X3, 128B rows> (tcgen05 implicit-GEMM conv, all launches with cout >= 128)",
+                    "kernel": "conv_tc_kernel<BN=128, F16X3, 128B rows, TMA store, cta_group::2> (tcgen05 implicit-GEMM conv, all launches with cout >= 128)",
                     "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"],
                     "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu)", "traffic_source": traffic_src,
                     "peak_source": pk["source"] + ", dense bf16 sustained",
