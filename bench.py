@@ -132,7 +132,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "panoramas/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "panoramas/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def parse_profile(text):
@@ -144,8 +144,25 @@ def parse_profile(text):
     return rows
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything a library prints to stdout while
+    the benchmark runs (e.g. NCCL's version banner) is diverted to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
     args = parse()
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -330,7 +347,7 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": "panoramas/s", "cores": cores, "kind": "port", "sample": sample}
     else:
         line["cpu_baseline"] = None
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 if __name__ == "__main__":

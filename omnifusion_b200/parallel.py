@@ -18,7 +18,13 @@ def init_from_env(backend=None):
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+            # NCCL_DEBUG=VERSION/INFO prints to stdout; callers (bench.py) own stdout for one JSON line
+            if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
+                os.environ["NCCL_DEBUG"] = "WARN"
+            dist.init_process_group(backend=backend, rank=rank, world_size=world,
+                                    device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return rank, world, local
 
 
@@ -50,4 +56,7 @@ def max_over_ranks(value, device):
 
 def barrier():
     if dist.is_initialized() and dist.get_world_size() > 1:
-        dist.barrier()
+        if dist.get_backend() == "nccl":
+            dist.barrier(device_ids=[torch.cuda.current_device()])
+        else:
+            dist.barrier()
