@@ -207,7 +207,11 @@ struct TcCfg {
   static constexpr int OUT_BUF = TMA_STORE ? PLANES * 128 * OUT_ROW : 0;   // one staging buffer
   static constexpr int MISC = 1024 /*align*/ + 256 /*barriers*/ + BN * 8;
   static constexpr int UPS_WARPS = UPS ? 8 : 0;                            // interpolating producer warps
-  static constexpr int THREADS = 192 + 32 * UPS_WARPS;
+  // epilogue warps: two per TMEM lane quarter for tiles of >= 2 column chunks (each takes every other 32-column
+  // chunk: the accumulator of a single-wave launch drains in half the time), one per quarter otherwise
+  static constexpr int EPI_SETS = (BN >= 64 && !UPS) ? 2 : 1;
+  static constexpr int EPI_WARPS = 4 * EPI_SETS;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * UPS_WARPS;
   static constexpr int LR_BYTES = 0;
   static constexpr int NST_RAW = (227 * 1024 - MISC - 2 * OUT_BUF - RES - LR_BYTES) / STAGE;
   static constexpr int NST = NST_RAW > 8 ? 8 : NST_RAW;                    // UPS: ring of upsampled rows (multiple of 4:
@@ -238,7 +242,8 @@ struct TcMaps {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+template <int NTHREADS>
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
@@ -285,7 +290,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, CTA2 ? 8 : 4);   // one arrival per epilogue warp (of both CTAs of a pair)
+      mbar_init(bar_tempty + 8 * i, (CTA2 ? 2 : 1) * Cfg::EPI_WARPS);   // one arrival per epilogue warp (of both CTAs of a pair)
     }
     mbar_init(bar_res, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -503,12 +508,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + Cfg::EPI_WARPS) {
     // ===================== epilogue (warps 2..5 <-> TMEM lane quarters) =====================
     const int q = warp & 3;                    // a warp may only touch TMEM lanes [32*(warp%4), +32)
     const int r = q * 32 + lane;               // accumulator row = pixel within the tile
     const int xx = r % p.BW, yy = (r / p.BW) % p.BH, ni = r / (p.BW * p.BH);
-    const int et = threadIdx.x - 64;           // 0..127
+    const int et = threadIdx.x - 64;           // 0 .. 32 * EPI_WARPS - 1
+    const int eset = (warp - 2) >> 2;          // which of the EPI_SETS warps of this lane quarter
     // sub-box of warp q for the bulk stores = pixels 32q .. 32q+31 of the tile (box dims chosen on the host to match)
     const int sub_x = (q * 32) % p.BW, sub_y = ((q * 32) / p.BW) % p.BH, sub_n = (q * 32) / (p.BW * p.BH);
     int last_n0 = -1;
@@ -519,12 +525,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
       const int img0 = grp * p.BNI, y0 = ty * p.BH, x0 = tx * p.BW, n0 = nt * BN;
       if (n0 != last_n0) {
-        epi_bar();                               // nobody still reads the previous scale/shift
-        for (int j = et; j < BN; j += 128) {
+        epi_bar<32 * Cfg::EPI_WARPS>();          // nobody still reads the previous scale/shift
+        for (int j = et; j < BN; j += 32 * Cfg::EPI_WARPS) {
           s_scale[j] = (p.scale ? __ldg(&p.scale[n0 + j]) : 1.f) * p.wscale;
           s_shift[j] = p.shift ? __ldg(&p.shift[n0 + j]) : 0.f;
         }
-        epi_bar();
+        epi_bar<32 * Cfg::EPI_WARPS>();
         last_n0 = n0;
       }
       const uint32_t buf = i & 1;
@@ -538,7 +544,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       const size_t pix = ((size_t)(ok ? img : 0) * p.H + (y0 + yy)) * p.W + (x0 + xx);
       const size_t off = pix * p.cout + n0;
 #pragma unroll 1
-      for (int cb = 0; cb < BN; cb += 32) {
+      for (int cb = 32 * eset; cb < BN; cb += 32 * Cfg::EPI_SETS) {
         uint32_t v[32];
         tmem_ld32_issue(tmem + ((uint32_t)(q * 32) << 16) + buf * Cfg::ACC_COLS + cb, v);
         if (Cfg::STACK) {                        // second column block (hi*Wlo) of the stacked accumulator
@@ -551,7 +557,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         } else {
           tmem_ld_wait();
         }
-        if (cb + 32 >= BN) {                     // accumulator fully read: hand it back to the MMA warp
+        if (cb + 32 * Cfg::EPI_SETS >= BN) {     // this warp's share of the accumulator is read: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -606,8 +612,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           // one thread write it with a bulk tensor store; two staging buffers alternate
           // Each epilogue warp stages and stores its own 32 pixels (a sub-box of the tile): no CTA-wide barrier,
           // the four warps drain the accumulator independently.
-          const uint32_t sbuf = chunk_ctr & 1;
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          // two staging buffers: alternating per chunk (one warp per quarter) or one per warp set
+          const uint32_t sbuf = Cfg::EPI_SETS == 2 ? (uint32_t)eset : (chunk_ctr & 1);
+          if (lane == 0) {
+            if (Cfg::EPI_SETS == 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          }
           __syncwarp();                                      // this warp's slice of staging buffer `sbuf` is free again
           if (stamp) p.dbg_buf[i * 8 + 4] = clock64();
           uint8_t* dst = stage_out_ptr + sbuf * Cfg::OUT_BUF;
@@ -675,7 +685,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         }
       }
     }
-    if (TMA_STORE && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (TMA_STORE && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   } else if (UPS) {
     // ===================== interpolating producers (warps 6..13) =====================
     // thread = (low-res column x, 8-channel chunk ch): it owns pixels X = 2x, 2x+1 of every upsampled row.
@@ -685,7 +695,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     // share them, so a new low-res row is fetched only every second row.
     constexpr int NT = 32 * Cfg::UPS_WARPS, C8 = Cfg::KC / 8;
     static_assert(!UPS || (NT == 64 * C8), "one producer thread per (low-res column, 8-channel chunk)");
-    const int pt = threadIdx.x - 192;
+    const int pt = threadIdx.x - (64 + 32 * Cfg::EPI_WARPS);
     const int x = pt / C8, ch = pt % C8;
     const int lh = p.H >> 1, lw = p.W >> 1;
     const __half* src_hi = reinterpret_cast<const __half*>(p.ups_src);
