@@ -178,6 +178,12 @@ int ofb_attention_f32(const void* q, const void* kv, int B, int N, int heads, in
 int ofb_attention_qkv_f32(const void* qkv, int B, int N, int heads, int head_dim,
                           void* out, int fmt, void* stream);
 
+/* The same heads on the tensor pipe (split-half format only): x_planes = split-half planes of (imgs,h,128,32),
+ * wgt_split = split-half planes of the (16,3,3,32) filter bank [pred; weight_pred; 14 zero rows] scaled by
+ * 1 / wgt_unscale (ofb_split_f16).  Rolling-row tcgen05 kernel, see csrc/conv_tc.cu (conv_tc_heads). */
+int ofb_heads_tc_f16(const void* x_planes, int imgs, int h, int w, const void* wgt_split, float wgt_unscale,
+                     float b_pred, float b_conf, int confidence, float* pred_out, float* conf_out, void* stream);
+
 /* Heads: pred / weight_pred 3x3 convs + relu / sigmoid / product,
  * spherical_model_iterative.py:371-374.  x (imgs,h,w,32); w_pred,w_conf (3,3,32);
  * pred_out = relu(pred) * (confidence ? sigmoid(conf) : 1); conf_out = sigmoid(conf)

@@ -62,6 +62,7 @@ _SIGNATURES = {
     "ofb_layernorm_f32": (_I, [_P, _P, _P, _I, _I, C.c_float, _P, _I, _I, _P]),
     "ofb_attention_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "ofb_attention_qkv_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _P]),
+    "ofb_heads_tc_f16": (_I, [_P, _I, _I, _I, _P, C.c_float, C.c_float, C.c_float, _I, _P, _P, _P]),
     "ofb_heads_f32": (_I, [_P, _I, _I, _I, _P, C.c_float, _P, C.c_float, _I, _P, _P, _I, _P]),
     "ofb_absrel_partial": (_I, [_P, _P, _P, C.c_size_t, C.c_float, _P, _P]),
     "ofb_depth_metrics_partial": (_I, [_P, _P, _P, C.c_size_t, C.c_float, _P, _P]),

@@ -39,6 +39,7 @@ struct TcParams {
   int dbg;               // timing experiments only (results are wrong):
                          // 32 skip the fused-upsample interpolation, 64 skip the epilogue math and stores,
                          // 128 skip only the global stores of the epilogue
+  float* heads_pred; float* heads_conf; float heads_bp, heads_bc;   // UPS == 2: the two heads' outputs and biases
   long long* dbg_buf;    // dbg & 16: clock stamps of the epilogue warp 2 of CTA 0: [tile][8]
   int group64;           // accumulate the three split-half products in the cta_group::2 column grouping (see the MMA warp)
 };
@@ -192,21 +193,24 @@ __device__ __forceinline__ float act_fn(float v, int act) {
 // shared-memory reads of the B operand per SM are halved - the mid layers are bound by exactly that.
 // Accumulator columns (per CTA, 128 lanes = its own 128 pixels): [0,64) hi*Whi[0:64] + lo*Whi[0:64],
 // [64,128) hi*Wlo[64:128] + lo*Whi[64:128], [128,192) hi*Whi[64:128], [192,256) hi*Wlo[0:64].
-template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR, bool BRES = false, bool UPS = false, bool CTA2 = false>
+template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR, bool BRES = false, int UPS = 0, bool CTA2 = false>
 struct TcCfg {
   static constexpr int PLANES = MODE == MODE_F16X3 ? 2 : 1;
   static constexpr int ES = MODE == MODE_F16X3 ? 2 : 4;
   static constexpr int KC_ = ROW_BYTES / ES;
   static constexpr int A_BYTES = (KHR ? 192 : 128) * ROW_BYTES;           // capacity; KHR boxes are <= 192 rows
   static constexpr int B_BYTES = (KHR ? 3 : 1) * (CTA2 ? BN / 2 : BN) * ROW_BYTES;
-  static constexpr int UPS_PX = 130;                                       // UPS: pixels per ring row (one zero column each side)
-  static constexpr int UPS_PLANE = UPS_PX * ROW_BYTES;                     // UPS: bytes of one upsampled row, one plane
+  // UPS == 1: rolling rows of the 2x-upsampled input, interpolated by producer warps (de_conv4_0)
+  // UPS == 2: rolling rows of a full-resolution input, one TMA box per row and plane, epilogue = the two heads
+  static constexpr int UPS_PX = 130;                                       // pixels per ring row (one zero column each side)
+  static constexpr int UPS_PITCH = UPS == 2 ? 136 : UPS_PX;                // ring rows per slot (TMA destinations are 512-byte aligned)
+  static constexpr int UPS_PLANE = UPS_PITCH * ROW_BYTES;                  // bytes of one ring slot, one plane
   static constexpr int STAGE = UPS ? UPS_PLANE * PLANES : (A_BYTES + (BRES ? 0 : B_BYTES)) * PLANES;
   static constexpr int RES = BRES ? 3 * PLANES * B_BYTES : 0;               // resident weights (all 3 kw)
   static constexpr int OUT_ROW = 32 * ES;                                  // bytes per staged row (32 columns)
   static constexpr int OUT_BUF = TMA_STORE ? PLANES * 128 * OUT_ROW : 0;   // one staging buffer
   static constexpr int MISC = 1024 /*align*/ + 256 /*barriers*/ + BN * 8;
-  static constexpr int UPS_WARPS = UPS ? 8 : 0;                            // interpolating producer warps
+  static constexpr int UPS_WARPS = UPS == 1 ? 8 : 0;                       // interpolating producer warps
   // epilogue warps: two per TMEM lane quarter for tiles of >= 2 column chunks (each takes every other 32-column
   // chunk: the accumulator of a single-wave launch drains in half the time), one per quarter otherwise
   static constexpr int EPI_SETS = (BN >= 64 && !UPS) ? 2 : 1;
@@ -229,6 +233,7 @@ struct TcCfg {
   static constexpr int SMEM = NST * STAGE + 2 * OUT_BUF + RES + LR_BYTES + MISC;
   static_assert(NST >= 2 && NST <= NST_RAW, "pipeline needs at least two stages that fit in shared memory");
   static_assert(!UPS || (KHR && BRES && MODE == MODE_F16X3 && ROW_BYTES == 64 && NST == 8), "UPS is a variant of the resident-filter kh-reuse kernel");
+  static_assert(UPS != 2 || (BN == 16 && !TMA_STORE), "the heads kernel computes 2 (padded to 16) output channels and stores them itself");
   static_assert(!CTA2 || (BN == 128 && MODE == MODE_F16X3 && !KHR && !BRES && !UPS), "CTA2 is a variant of the plain 128-wide F16X3 kernel");
 };
 
@@ -252,7 +257,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
 // Persistent kernel: each CTA walks tiles t = blockIdx.x, +gridDim.x, ...; the smem ring and its
 // phases run continuously across tiles, and two TMEM accumulator buffers let the MMA warp start
 // tile i+1 while the epilogue warps drain tile i.
-template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR, bool BRES = false, bool UPS = false, bool CTA2 = false>
+template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR, bool BRES = false, int UPS = 0, bool CTA2 = false>
 __global__ void __launch_bounds__((TcCfg<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES, UPS, CTA2>::THREADS), 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   using Cfg = TcCfg<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES, UPS, CTA2>;
@@ -285,7 +290,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < Cfg::NST; ++i) {
-      mbar_init(bars + 8 * i, UPS ? Cfg::UPS_WARPS : 1);     // full: the TMA thread, or one arrival per producer warp
+      mbar_init(bars + 8 * i, UPS == 1 ? Cfg::UPS_WARPS : 1);     // full: the TMA thread, or one arrival per producer warp
       mbar_init(bars + 8 * (Cfg::NST + i), 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -294,7 +299,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     }
     mbar_init(bar_res, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (!UPS) tma_prefetch_desc(&maps.a[0][0]);
+    if (UPS != 1) tma_prefetch_desc(&maps.a[0][0]);
     tma_prefetch_desc(&maps.b[0]);
     if (TMA_STORE) tma_prefetch_desc(&maps.o[0]);
   }
@@ -329,6 +334,28 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           tma_load_4d(res_b + kw * Cfg::PLANES * Cfg::B_BYTES, &maps.b[0], bar_res, 0, 0, 0, kw);
       }
       __syncwarp();
+    }
+    if (UPS == 2) {
+      // rolling rows: one box {32 channels, 130 pixels from x = -1, 1 row} per plane and produced row; rows -1
+      // and H and the two border columns are out of bounds = zero-filled by TMA = the conv padding
+      uint32_t pc = 0;
+      int g = ups_r0;
+      while (g < ups_r1) {
+        const int img = g / p.H, ys = g - img * p.H;
+        const int ye = min(p.H, ys + (ups_r1 - g));
+        for (int Y = ys - 1; Y <= ye; ++Y, ++pc) {
+          const uint32_t slot = pc % Cfg::NST;
+          mbar_wait(bars + 8 * (Cfg::NST + slot), ((pc / Cfg::NST) & 1) ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(bars + 8 * slot, (uint32_t)(Cfg::PLANES * Cfg::UPS_PX * ROW_BYTES));
+#pragma unroll
+            for (int pl = 0; pl < Cfg::PLANES; ++pl)
+              tma_load_4d(base + (uint32_t)((pl * Cfg::NST + slot) * Cfg::UPS_PLANE), &maps.a[0][pl], bars + 8 * slot, 0, -1, Y, img);
+          }
+          __syncwarp();
+        }
+        g += ye - ys;
+      }
     }
     // (no divisions per K-step; ring stage / phase advanced incrementally)
     uint32_t st = 0, ph = 0;
@@ -421,7 +448,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
               for (int kh = 0; kh < 3; ++kh) {
-                const uint32_t row = ((pb + kh) % Cfg::NST) * Cfg::UPS_PX + kw;          // first ring row of this tap
+                const uint32_t row = ((pb + kh) % Cfg::NST) * Cfg::UPS_PITCH + kw;       // first ring row of this tap
                 const uint32_t a0 = base + row * ROW_BYTES, b0 = res_b + (uint32_t)((kw * Cfg::PLANES * 3 + kh * 2) * BN * ROW_BYTES);
                 const uint64_t a_hi = dconst | ((a0 >> 4) & 0x3FFF), a_lo = dconst | (((a0 + Cfg::NST * Cfg::UPS_PLANE) >> 4) & 0x3FFF);
                 const uint64_t b_st = dconst | ((b0 >> 4) & 0x3FFF);
@@ -544,6 +571,25 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       const size_t pix = ((size_t)(ok ? img : 0) * p.H + (y0 + yy)) * p.W + (x0 + xx);
       const size_t off = pix * p.cout + n0;
 #pragma unroll 1
+      if (UPS == 2) {
+        // heads: accumulator columns [0,16) = hi*Whi + lo*Whi, [16,32) = hi*Wlo; channel 0 = pred, 1 = weight_pred
+        // (spherical_model_iterative.py:371-374: relu / sigmoid / product)
+        uint32_t v[32];
+        tmem_ld32_issue(tmem + ((uint32_t)(q * 32) << 16) + buf * Cfg::ACC_COLS, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        if ((p.dbg & 64) || !ok) continue;
+        float pr = fmaxf((__uint_as_float(v[0]) + __uint_as_float(v[16])) * p.wscale + p.heads_bp, 0.f);
+        if (p.heads_conf) {
+          const float cf = 1.f / (1.f + expf(-((__uint_as_float(v[1]) + __uint_as_float(v[17])) * p.wscale + p.heads_bc)));
+          pr *= cf;
+          p.heads_conf[pix] = cf;
+        }
+        p.heads_pred[pix] = pr;
+        continue;
+      }
       for (int cb = 32 * eset; cb < BN; cb += 32 * Cfg::EPI_SETS) {
         uint32_t v[32];
         tmem_ld32_issue(tmem + ((uint32_t)(q * 32) << 16) + buf * Cfg::ACC_COLS + cb, v);
@@ -686,7 +732,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       }
     }
     if (TMA_STORE && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-  } else if (UPS) {
+  } else if (UPS == 1) {
     // ===================== interpolating producers (warps 6..13) =====================
     // thread = (low-res column x, 8-channel chunk ch): it owns pixels X = 2x, 2x+1 of every upsampled row.
     // F.interpolate(scale 2, bilinear, align_corners=False): row Y = 2y+dy blends low-res rows y-1+dy, y+dy
@@ -694,7 +740,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     // x 8 channels per thread) is cached in registers for the two rows in use: consecutive upsampled rows
     // share them, so a new low-res row is fetched only every second row.
     constexpr int NT = 32 * Cfg::UPS_WARPS, C8 = Cfg::KC / 8;
-    static_assert(!UPS || (NT == 64 * C8), "one producer thread per (low-res column, 8-channel chunk)");
+    static_assert(UPS != 1 || (NT == 64 * C8), "one producer thread per (low-res column, 8-channel chunk)");
     const int pt = threadIdx.x - (64 + 32 * Cfg::EPI_WARPS);
     const int x = pt / C8, ch = pt % C8;
     const int lh = p.H >> 1, lw = p.W >> 1;
@@ -708,7 +754,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     // zero columns X = -1 and X = 128 of every ring row, once (the slots keep their layout)
     if (pt < Cfg::NST * 2 * C8) {
       const int slot = pt / (2 * C8), side = (pt / C8) & 1, c = pt % C8;
-      const uint32_t r = slot * Cfg::UPS_PX + (side ? Cfg::UPS_PX - 1 : 0);
+      const uint32_t r = slot * Cfg::UPS_PITCH + (side ? Cfg::UPS_PX - 1 : 0);
       const uint32_t off = r * ROW_BYTES + ((c ^ ((r >> 1) & 3)) << 4);
       *reinterpret_cast<uint4*>(ring_hi + off) = make_uint4(0u, 0u, 0u, 0u);
       *reinterpret_cast<uint4*>(ring_lo + off) = make_uint4(0u, 0u, 0u, 0u);
@@ -789,7 +835,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         }
 #pragma unroll
         for (int px = 0; px < 2; ++px) {
-          const uint32_t r = slot * Cfg::UPS_PX + 1 + 2 * x + px;
+          const uint32_t r = slot * Cfg::UPS_PITCH + 1 + 2 * x + px;
           const uint32_t off = r * ROW_BYTES + ((ch ^ ((r >> 1) & 3)) << 4);
           *reinterpret_cast<uint4*>(ring_hi + off) = hi4[px];
           *reinterpret_cast<uint4*>(ring_lo + off) = lo4[px];
@@ -903,7 +949,7 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR, bool BRES = false, bool UPS = false, bool CTA2 = false>
+template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR, bool BRES = false, int UPS = 0, bool CTA2 = false>
 static int launch_tc(const TcMaps& maps, const TcParams& p, cudaStream_t s) {
   using Cfg = TcCfg<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES, UPS, CTA2>;
   static bool attr = false;
@@ -1067,6 +1113,44 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
   }
   if (row_bytes == 128) return launch_bn<MODE_TF32, 128>(bn, false, false, maps, p, s);
   return launch_bn<MODE_TF32, 64>(bn, false, false, maps, p, s);
+}
+
+// ------------------------------------------------------------------ heads on tensor cores
+// pred / weight_pred (3x3, 32 -> 1 each) as ONE 3x3 conv with 16 output channels (0 = pred, 1 = weight_pred,
+// 2..15 zero) on the rolling-row kernel: a CTA walks a contiguous range of 128-pixel image rows, the TMA
+// producer adds one input row per output row to a ring in shared memory (1.02 instead of 1.27 x the input
+// through L2, no index arithmetic), all nine taps read it through row-shifted descriptors, and the epilogue
+// applies relu / sigmoid / product and writes the two float32 patch maps.  x: split-half (n, h, 128, 32).
+int conv_tc_heads(const void* x, int n, int h, int w, const void* wgt_split, float wgt_unscale, float b_pred,
+                  float b_conf, int confidence, float* pred_out, float* conf_out, cudaStream_t s) {
+  OFB_CHECK(x && wgt_split && pred_out && (!confidence || conf_out), "heads_tc: null pointer");
+  OFB_CHECK(w == 128 && h >= 1, "heads_tc: rows must be 128 pixels wide (got %d)", w);
+  TcParams p{};
+  p.n_img = n; p.H = h; p.W = w; p.c0 = 32; p.c1 = 0; p.cout = 16; p.k = 3; p.pad = 1; p.stride = 1;
+  p.taps = 9; p.kdiv = 3; p.sx = p.sy = 1; p.padx = p.pady = 1;
+  p.BW = 128; p.BH = 1; p.BNI = 1; p.tiles_x = 1; p.tiles_y = h;
+  p.wscale = wgt_unscale; p.act = OFB_ACT_NONE;
+  p.tiles_n = 1; p.total_tiles = n * h;
+  p.heads_pred = pred_out; p.heads_conf = confidence ? conf_out : nullptr; p.heads_bp = b_pred; p.heads_bc = b_conf;
+  p.dbg = g_dbg;
+  p.dbg_buf = (g_dbg & 16) ? conv_tc_debug_buffer() : nullptr;
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const size_t plane = (size_t)n * h * w * 32;               // halves per plane
+  for (int pl = 0; pl < 2; ++pl) {
+    cuuint64_t dims[4] = {32, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint32_t box[4] = {32u, 130u, 1u, 1u};
+    if (make_map(&maps.a[0][pl], true, 4, (char*)x + pl * plane * 2, dims, box, 64)) return -1;
+    maps.a[1][pl] = maps.a[0][pl];
+  }
+  {  // weights: (2*16, kh, kw, 32) = stacked [Whi; Wlo]; one box = {32 channels, 32 rows, all 3 kh, one kw}
+    cuuint64_t dims[4] = {32, 32, 3, 3};
+    cuuint64_t bstr[3] = {(cuuint64_t)9 * 32 * 2, (cuuint64_t)3 * 32 * 2, (cuuint64_t)32 * 2};
+    cuuint32_t box[4] = {32u, 32u, 3u, 1u};
+    if (make_map(&maps.b[0], true, 4, (char*)wgt_split, dims, box, 64, 1, bstr)) return -1;
+    maps.b[1] = maps.b[0];
+  }
+  return launch_tc<16, MODE_F16X3, 64, false, true, true, 2>(maps, p, s);
 }
 
 // ------------------------------------------------------------------ stem on tensor cores

@@ -36,6 +36,8 @@ void conv_tc_set_pdl(bool on);
 void conv_tc_set_store128(bool on);
 void conv_tc_set_cta2(bool on);
 void conv_tc_set_debug(int v);
+int conv_tc_heads(const void* x, int n, int h, int w, const void* wgt_split, float wgt_unscale, float b_pred,
+                  float b_conf, int confidence, float* pred_out, float* conf_out, cudaStream_t s);
 void conv_tc_set_fill_div(int v);
 long long* conv_tc_debug_buffer();
 void conv_tc_set_direct32(bool on);
@@ -80,6 +82,8 @@ struct ofb_handle {
   int pos_patches = 0;
   ConvW down;
   float *pred_w = nullptr, *conf_w = nullptr;
+  ConvW heads16;                   // both heads as one 16-channel 3x3 conv (0 = pred, 1 = weight_pred) for the tcgen05 engine
+  int heads_tc = 1;                // run the heads on the tensor pipe (split-half format, 128-pixel rows)
   float pred_b = 0.f, conf_b = 0.f;
   Mlp mlp[2]{};
   std::vector<void*> owned;        // device allocations for weights
@@ -291,6 +295,20 @@ static int load_all(ofb_handle* h, const TMap& m, bool single) {
   ConvW hp, hc;
   if (pack_conv(h, m, "pred.weight", &hp) || pack_conv(h, m, "weight_pred.weight", &hc)) return -1;
   h->pred_w = hp.w; h->conf_w = hc.w;
+  {  // (16,32,3,3): rows 0/1 = pred / weight_pred, the rest zero
+    const ofb_tensor_desc *tp = find(m, "pred.weight"), *tc = find(m, "weight_pred.weight");
+    if (!tp || !tc) return -1;
+    OFB_CHECK(numel(tp) == 288 && numel(tc) == 288, "load_weights: head filters must be (1,32,3,3,1)");
+    std::vector<float> cat(16 * 288, 0.f);
+    memcpy(cat.data(), tp->data, 288 * sizeof(float));
+    memcpy(cat.data() + 288, tc->data, 288 * sizeof(float));
+    ofb_tensor_desc fused{};
+    std::string nm = "heads16.weight";
+    fused.name = nm.c_str(); fused.data = cat.data(); fused.ndim = 4;
+    fused.shape[0] = 16; fused.shape[1] = 32; fused.shape[2] = 3; fused.shape[3] = 3;
+    TMap one; one[nm] = &fused;
+    if (pack_conv(h, one, nm, &h->heads16)) return -1;
+  }
   const ofb_tensor_desc *pb = find(m, "pred.bias"), *cb = find(m, "weight_pred.bias");
   if (!pb || !cb) return -1;
   h->pred_b = pb->data[0]; h->conf_b = cb->data[0];
@@ -566,7 +584,9 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
 
     // heads + ERP merge (:371-380)
     { Prof pr(h, s, "heads", 0.0, 4.0*((double)imgs*P*P*34));
-    if (ofb_heads_f32(b.d40, imgs, P, P, h->pred_w, h->pred_b, h->conf_w, h->conf_b, confidence, b.pred, b.conf, F, vs)) return -1; }
+    if (h->heads_tc && F == OFB_FMT_SPLIT16 && h->engine != OFB_ENGINE_SIMT && P == 128) {
+      if (conv_tc_heads(b.d40, imgs, P, P, h->heads16.ws, h->heads16.unscale, h->pred_b, h->conf_b, confidence, b.pred, b.conf, s)) return -1;
+    } else if (ofb_heads_f32(b.d40, imgs, P, P, h->pred_w, h->pred_b, h->conf_w, h->conf_b, confidence, b.pred, b.conf, F, vs)) return -1; }
     float* out = outs[it] + out_off;
     if (confidence) {
       { Prof pr(h, s, "blend_conf", 0.0, 4.0*((double)imgs*P*P*2 + (double)Bc*He*We));
@@ -602,6 +622,13 @@ extern "C" int64_t ofb_launch_count(int reset) {
 extern "C" int ofb_set_device(int device) {
   OFB_CUDA(cudaSetDevice(device));
   return 0;
+}
+
+extern "C" int ofb_heads_tc_f16(const void* x_planes, int imgs, int h, int w, const void* wgt_split, float wgt_unscale,
+                                float b_pred, float b_conf, int confidence, float* pred_out, float* conf_out,
+                                void* stream) {
+  return conv_tc_heads(x_planes, imgs, h, w, wgt_split, wgt_unscale, b_pred, b_conf, confidence, pred_out, conf_out,
+                       (cudaStream_t)stream);
 }
 
 extern "C" int ofb_stem_tc_f16(const void* patches, int n, int h, int w, const void* wgt_split, float wgt_unscale,
@@ -668,6 +695,7 @@ extern "C" int ofb_set_option(ofb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "chunk")) h->chunk = value;
   else if (!strcmp(key, "dedup")) h->dedup = value;
   else if (!strcmp(key, "fuse_ups")) h->fuse_ups = value;
+  else if (!strcmp(key, "heads_tc")) h->heads_tc = value;
   else if (!strcmp(key, "pdl")) conv_tc_set_pdl(value != 0);     // process-wide: programmatic dependent launch
   else if (!strcmp(key, "store128")) conv_tc_set_store128(value != 0);
   else if (!strcmp(key, "tc_debug")) conv_tc_set_debug(value);         // timing experiments only (wrong results)

@@ -182,3 +182,34 @@ def test_conv_fused_upsample_rejected_by_cuda_core_engine():
     w = o.ohwi(rand(32, 32, 3, 3, seed=2)).to(DEV)
     with pytest.raises(_lib.OfbError):
         o.conv_fmt(x, w, 3, 1, 1, engine=_lib.ENGINE_SIMT, in_fmt=_lib.FMT_SPLIT16, out_fmt=_lib.FMT_SPLIT16, ups2x=1)
+
+
+@pytest.mark.parametrize("n,h,confidence", [(1, 128, True), (3, 128, False), (150, 16, True)])
+def test_heads_on_tensor_cores_match_torch_cpu(n, h, confidence):
+    """pred / weight_pred heads (spherical_model_iterative.py:371-374) as one 16-channel conv on the rolling-row
+    tcgen05 kernel (ofb_heads_tc_f16): against torch-CPU fp32.  n=1 gives every CTA one row (both halo rows
+    re-loaded per row), n=3 makes CTA ranges cross image boundaries, n=150 wraps the row ring many times."""
+    o = ops()
+    x = F.relu(rand(n, 32, h, 128, seed=21))
+    wp, wc = rand(1, 32, 3, 3, seed=22, scale=0.1), rand(1, 32, 3, 3, seed=23, scale=0.1)
+    bp, bc = 0.7, -0.3
+    pred = F.relu(F.conv2d(x, wp, torch.tensor([bp]), 1, 1))
+    conf = torch.sigmoid(F.conv2d(x, wc, torch.tensor([bc]), 1, 1))
+    w16 = torch.zeros(16, 3, 3, 32)
+    w16[0], w16[1] = o.ohwi(wp)[0], o.ohwi(wc)[0]
+    w16 = w16.to(DEV)
+    mul = o.weight_scale(w16)
+    ws, xs = o.split16(w16, mul), o.split16(o.nhwc(x).to(DEV))
+    gp = torch.full((n, h, 128), -1.0, device=DEV)
+    gc = torch.full((n, h, 128), -1.0, device=DEV)
+    _lib.check(_lib.lib().ofb_heads_tc_f16(_lib.ptr(xs), n, h, 128, _lib.ptr(ws), 1.0 / mul, bp, bc, int(confidence),
+                                            _lib.ptr(gp), _lib.ptr(gc), _lib.stream_of(torch.device(DEV))))
+    torch.cuda.synchronize()
+    want = (pred * conf)[:, 0] if confidence else pred[:, 0]
+    err = (gp.cpu() - want).abs()
+    print(f"[parity] heads_tc n={n} h={h} conf={confidence}: max_abs_err={err.max().item():.3e} ref_absmax={want.abs().max().item():.3e}")
+    assert (err <= 2e-5 + 2e-5 * want.abs()).all()
+    if confidence:
+        assert ((gc.cpu() - conf[:, 0]).abs() <= 2e-5).all()
+    else:
+        assert (gc == -1.0).all()          # conf_out untouched
