@@ -928,6 +928,8 @@ static bool g_direct32 = false;  // BN = 32 split-half tiles store straight from
 void conv_tc_set_direct32(bool on) { g_direct32 = on; }
 static int g_fill_div = 2;      // shrink the N tile while fewer than num_sms / g_fill_div tiles exist
 void conv_tc_set_fill_div(int v) { g_fill_div = v > 0 ? v : 2; }
+static int g_sm_share = 1;      // persistent grids use num_sms / g_sm_share CTAs (two concurrent forward lanes share the GPU)
+void conv_tc_set_sm_share(int div) { g_sm_share = div >= 1 ? div : 1; }
 static int g_dbg = 0;           // TcParams::dbg (timing experiments)
 static long long* g_dbg_buf = nullptr;
 void conv_tc_set_debug(int v) { g_dbg = v; }
@@ -958,7 +960,7 @@ static int launch_tc(const TcMaps& maps, const TcParams& p, cudaStream_t s) {
     attr = true;
   }
   // persistent: one CTA per SM (CTA2: one CTA pair per TPC, total_tiles counts pair-tiles)
-  const int units = CTA2 ? num_sms() / 2 : num_sms();
+  const int units = (CTA2 ? num_sms() / 2 : num_sms()) / g_sm_share;
   int grid = (p.total_tiles < units ? p.total_tiles : units) * (CTA2 ? 2 : 1);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;

@@ -36,6 +36,7 @@ void conv_tc_set_pdl(bool on);
 void conv_tc_set_store128(bool on);
 void conv_tc_set_cta2(bool on);
 void conv_tc_set_debug(int v);
+void conv_tc_set_sm_share(int div);
 int conv_tc_heads(const void* x, int n, int h, int w, const void* wgt_split, float wgt_unscale, float b_pred,
                   float b_conf, int confidence, float* pred_out, float* conf_out, cudaStream_t s);
 void conv_tc_set_fill_div(int v);
@@ -88,12 +89,19 @@ struct ofb_handle {
   Mlp mlp[2]{};
   std::vector<void*> owned;        // device allocations for weights
   // workspace
-  float* ws = nullptr; size_t ws_floats = 0; size_t ws_used = 0;
+  // Two "lanes" (option lanes=2, off by default): a batch of >= 4 panoramas is split in two halves that run
+  // concurrently on two streams (each with its own workspace) so that the latency-bound token path of one half
+  // overlaps the convolutions of the other.  Measured on B200: 1561 vs 1898 panoramas/s at 8 per step, 1945 vs
+  // 2136 at 32 - the halves' persistent kernels compete for the L2 fabric and for SMs instead of interleaving.
+  struct Lane { float* ws = nullptr; size_t ws_floats = 0; bool patches_zeroed = false; int patches_imgs = 0; };
+  Lane lane[2];
+  int cur = 0;                     // lane whose launches are being enqueued (host-side state)
+  int lanes = 1;
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int engine = OFB_ENGINE_AUTO, chunk = 0, dedup = 1;
   int fuse_ups = 1;                // fold the last decoder upsample into de_conv4_0's operand producer
   int fmt = OFB_FMT_SPLIT16;       // activation storage inside the network
-  bool patches_zeroed = false;      // row pads of the stem-layout patch buffer are zero
-  int patches_imgs = 0;
   std::map<std::string, Act> acts;
   // optional per-launch timing (ofb_profile_enable)
   bool profile = false;
@@ -326,7 +334,7 @@ struct Plan {
   float* take(size_t n) {
     size_t a = (off + 63) & ~(size_t)63;   // 256-byte alignment
     off = a + n;
-    return h->ws ? h->ws + a : nullptr;
+    return h->lane[h->cur].ws ? h->lane[h->cur].ws + a : nullptr;
   }
 };
 
@@ -364,16 +372,16 @@ static size_t plan_buffers(ofb_handle* h, int imgs, int P, Buffers* b) {
 
 static int ensure_workspace(ofb_handle* h, int imgs, int P, Buffers* b) {
   Buffers tmp;
-  float* saved = h->ws;
-  h->ws = nullptr;
+  float* saved = h->lane[h->cur].ws;
+  h->lane[h->cur].ws = nullptr;
   size_t need = plan_buffers(h, imgs, P, &tmp);
-  h->ws = saved;
-  if (need > h->ws_floats) {
-    if (h->ws) cudaFree(h->ws);
-    h->ws = nullptr; h->ws_floats = 0;
-    OFB_CUDA(cudaMalloc(&h->ws, need * sizeof(float)));
-    h->ws_floats = need;
-    h->patches_zeroed = false;
+  h->lane[h->cur].ws = saved;
+  if (need > h->lane[h->cur].ws_floats) {
+    if (h->lane[h->cur].ws) cudaFree(h->lane[h->cur].ws);
+    h->lane[h->cur].ws = nullptr; h->lane[h->cur].ws_floats = 0;
+    OFB_CUDA(cudaMalloc(&h->lane[h->cur].ws, need * sizeof(float)));
+    h->lane[h->cur].ws_floats = need;
+    h->lane[h->cur].patches_zeroed = false;
   }
   plan_buffers(h, imgs, P, b);
   return 0;
@@ -496,10 +504,10 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
       // equi2pers(rgb, P) -> patches; stem; pool; layer1 (spherical_model_iterative.py:315,322-324)
       const ConvW& st = h->conv["stem"];
       const bool stem_tc_path = F == OFB_FMT_SPLIT16 && h->engine != OFB_ENGINE_SIMT;
-      if (stem_tc_path && (!h->patches_zeroed || h->patches_imgs != imgs)) {
+      if (stem_tc_path && (!h->lane[h->cur].patches_zeroed || h->lane[h->cur].patches_imgs != imgs)) {
         // the stem layout's row pads must read as zero; the interior is rewritten by every forward
         OFB_CUDA(cudaMemsetAsync(b.patches, 0, (size_t)imgs * P * (P + 8) * 4 * sizeof(float), s));
-        h->patches_zeroed = true; h->patches_imgs = imgs;
+        h->lane[h->cur].patches_zeroed = true; h->lane[h->cur].patches_imgs = imgs;
       }
       { Prof pr(h, s, "e2p_rgb", 0.0, 4.0*((double)Bc*3*He*We + (double)imgs*P*P*4));
       if (ofb_equi2pers_f32(rgb, Bc, 3, He, We, g.grid_hi, N, P, P, b.patches,
@@ -657,7 +665,11 @@ extern "C" int ofb_destroy(ofb_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   free_weights(h);
-  if (h->ws) cudaFree(h->ws);
+  for (int l = 0; l < 2; ++l)
+    if (h->lane[l].ws) cudaFree(h->lane[l].ws);
+  if (h->aux) cudaStreamDestroy(h->aux);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
   return 0;
 }
@@ -690,8 +702,9 @@ extern "C" int ofb_load_weights(ofb_handle* h, const ofb_tensor_desc* tensors, i
 
 extern "C" int ofb_set_option(ofb_handle* h, const char* key, int value) {
   OFB_CHECK(h && key, "set_option: null pointer");
-  h->patches_zeroed = false;
+  h->lane[0].patches_zeroed = h->lane[1].patches_zeroed = false;
   if (!strcmp(key, "engine")) h->engine = value;
+  else if (!strcmp(key, "lanes")) h->lanes = value >= 2 ? 2 : 1;
   else if (!strcmp(key, "chunk")) h->chunk = value;
   else if (!strcmp(key, "dedup")) h->dedup = value;
   else if (!strcmp(key, "fuse_ups")) h->fuse_ups = value;
@@ -722,13 +735,45 @@ extern "C" int ofb_forward_f32(ofb_handle* h, const float* rgb, int B, int iters
   int N = h->geo.n_patch;
   int chunk = h->chunk > 0 ? h->chunk : (576 / N > 0 ? 576 / N : 1);
   size_t plane = (size_t)h->geo.erp_h * h->geo.erp_w;
-  for (int b0 = 0; b0 < B; b0 += chunk) {
-    int Bc = B - b0 < chunk ? B - b0 : chunk;
-    if (forward_chunk(h, rgb + (size_t)b0 * 3 * plane, Bc, iters, confidence, out_depth, (size_t)b0 * plane,
-                      (cudaStream_t)stream))
-      return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  // panoramas [lo, hi) on lane `l`, in chunks
+  auto run_lane = [&](int l, int lo, int hi, cudaStream_t ls) -> int {
+    h->cur = l;
+    for (int b0 = lo; b0 < hi; b0 += chunk) {
+      int Bc = hi - b0 < chunk ? hi - b0 : chunk;
+      if (forward_chunk(h, rgb + (size_t)b0 * 3 * plane, Bc, iters, confidence, out_depth, (size_t)b0 * plane, ls)) return -1;
+    }
+    return 0;
+  };
+  const bool two = h->lanes == 2 && B >= 4 && !h->profile;
+  if (!two) {
+    int rc = run_lane(0, 0, B, s);
+    h->cur = 0;
+    return rc;
   }
-  return 0;
+  if (!h->aux) {
+    OFB_CUDA(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
+    OFB_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    OFB_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  }
+  // both lanes' workspaces exist before anything is enqueued (an allocation must not interleave with a capture)
+  const int half = (B + 1) / 2;
+  for (int l = 0; l < 2; ++l) {
+    h->cur = l;
+    Buffers tmp;
+    int nb = l == 0 ? half : B - half;
+    if (ensure_workspace(h, (nb < chunk ? nb : chunk) * N, h->geo.patch, &tmp)) { h->cur = 0; return -1; }
+  }
+  OFB_CUDA(cudaEventRecord(h->ev_fork, s));
+  OFB_CUDA(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
+  conv_tc_set_sm_share(2);                 // persistent grids take half of the SMs each: the two lanes run side by side
+  int rc = run_lane(0, 0, half, s);
+  if (!rc) rc = run_lane(1, half, B, h->aux);
+  conv_tc_set_sm_share(1);
+  h->cur = 0;
+  OFB_CUDA(cudaEventRecord(h->ev_join, h->aux));
+  OFB_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
+  return rc;
 }
 
 // timing experiments: copies the clock stamps recorded with tc_debug & 16 (512 x 8 int64) to the host

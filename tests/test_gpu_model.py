@@ -146,7 +146,19 @@ def test_batch_invariance_chunking_dedup_and_graph(fmt):
         full = net(rgb, iter=2, confidence=True)
         assert torch.equal(full[1], base[1]), "re-using the iteration-invariant stem must not change results"
         net.set_option("dedup", 1)
+        # option lanes=2: the batch runs as two concurrent halves on two streams; must agree bit for bit
+        net.set_option("lanes", 2)
+        two_lanes = net(rgb, iter=2, confidence=True)
+        net.set_option("lanes", 1)
+        assert torch.equal(two_lanes[0], base[0]) and torch.equal(two_lanes[1], base[1])
         if FORMATS[fmt] == 1:
+            # the heads run on the tensor pipe; the CUDA-core heads kernel must agree to rounding
+            net.set_option("heads_tc", 0)
+            cc = net(rgb, iter=2, confidence=True)
+            net.set_option("heads_tc", 1)
+            d = ((cc[1] - base[1]).abs() / base[1].abs().clamp_min(1e-6)).max().item()
+            print(f"[parity] tensor-core vs CUDA-core heads: depth max rel diff {d:.3e}")
+            assert d <= 2e-5
             # the last decoder upsample is folded into de_conv4_0's operand producer; unfused must agree
             net.set_option("fuse_ups", 0)
             unfused = net(rgb, iter=2, confidence=True)
