@@ -232,8 +232,12 @@ int ofb_load_weights(ofb_handle* h, const ofb_tensor_desc* tensors, int count, i
 int ofb_forward_f32(ofb_handle* h, const float* rgb, int B, int iters, int confidence,
                     float* const* out_depth, void* stream);
 
-/* Engine knobs: conv engine (OFB_ENGINE_*), panoramas per internal chunk (0 = auto),
- * reuse of the iteration-invariant stem/layer1 across iterations (1 = on, default). */
+/* Engine knobs (key, value): "engine" conv engine (OFB_ENGINE_*), "chunk" panoramas per internal chunk
+ * (0 = auto), "dedup" reuse of the iteration-invariant stem/layer1 across iterations (default 1), "format"
+ * activation storage (OFB_FMT_*), "fuse_ups" fold the last decoder upsample into de_conv4_0 (default 1),
+ * "heads_tc" heads on the tensor pipe (default 1), "lanes" 2 = two concurrent half-batches on two streams
+ * (default 1), "cta2" / "pdl" / "store128" / "fill_div" / "direct32" tcgen05 launch variants (process-wide);
+ * "tc_debug" / "dbg_blocks" switch parts of the pipeline OFF for timing experiments (results are wrong). */
 int ofb_set_option(ofb_handle* h, const char* key, int value);
 
 /* Copies a named intermediate of the last forward (last chunk, last iteration) into
@@ -252,6 +256,10 @@ int ofb_profile_report(ofb_handle* h, char* buf, int capacity);
 
 /* Kernel launches issued by this library on the calling thread since the last reset. */
 int64_t ofb_launch_count(int reset);
+
+/* Timing experiments: copies the clock stamps an epilogue warp of CTA 0 recorded while "tc_debug" & 16
+ * was set (512 tiles x 8 int64) to host_dst (tools/probe_tail.py). */
+int ofb_debug_stamps(long long* host_dst);
 
 #ifdef __cplusplus
 }

@@ -84,6 +84,7 @@ struct ofb_handle {
   ConvW down;
   float *pred_w = nullptr, *conf_w = nullptr;
   ConvW heads16;                   // both heads as one 16-channel 3x3 conv (0 = pred, 1 = weight_pred) for the tcgen05 engine
+  int dbg_blocks = 6;              // timing experiments only: number of transformer blocks executed
   int heads_tc = 1;                // run the heads on the tensor pipe (split-half format, 128-pixel rows)
   float pred_b = 0.f, conf_b = 0.f;
   Mlp mlp[2]{};
@@ -549,7 +550,7 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
     if (ofb_token_pack_f32(b.down, h->pos_emb, imgs, N, b.tok, F, vs)) return -1; }
     float* x = b.tok;
     float* y = b.tok2;
-    for (int i = 0; i < 6; ++i) {   // Transformer_Block, model/blocks.py:84-88
+    for (int i = 0; i < h->dbg_blocks; ++i) {   // Transformer_Block, model/blocks.py:84-88 (dbg_blocks = 6)
       Block& B = h->blk[i];
       { Prof pr(h, s, "layernorm", 0.0, 4.0*((double)imgs*1024));
       if (ofb_layernorm_f32(x, B.n1g, B.n1b, imgs, 512, 1e-5f, b.ln, F, F, vs)) return -1; }
@@ -709,6 +710,7 @@ extern "C" int ofb_set_option(ofb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "dedup")) h->dedup = value;
   else if (!strcmp(key, "fuse_ups")) h->fuse_ups = value;
   else if (!strcmp(key, "heads_tc")) h->heads_tc = value;
+  else if (!strcmp(key, "dbg_blocks")) h->dbg_blocks = value < 0 ? 0 : (value > 6 ? 6 : value);   // timing experiments (wrong results)
   else if (!strcmp(key, "pdl")) conv_tc_set_pdl(value != 0);     // process-wide: programmatic dependent launch
   else if (!strcmp(key, "store128")) conv_tc_set_store128(value != 0);
   else if (!strcmp(key, "tc_debug")) conv_tc_set_debug(value);         // timing experiments only (wrong results)

@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int n_mma, int mode
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int stg = j >> 1, kk = (j & 1) * 2 + ((i >> 3) & 1);
-          const uint64_t ad = umma_desc<128>(a0 + stg * 192 * 128 + (uint32_t)(a_rows ? (j % 3) * 32 * 128 : 0)) + 2 * kk;
+          // a_rows >= 0: every MMA's A tile starts a_rows * (j % 3) rows into the stage (row-shifted descriptors)
+          const uint64_t ad = umma_desc<128>(a0 + stg * 192 * 128 + (uint32_t)((j % 3) * a_rows * 128)) + 2 * kk;
           const uint64_t bd = umma_desc<128>(b0 + stg * 256 * 128) + 2 * kk;
           if (mode == 1 && (j & 1)) tc_mma(tmem + 256, ad, bd, id_h, 1);
           else tc_mma(tmem, ad, bd, id_n, 1);
@@ -225,7 +226,7 @@ int main() {
         if (mode == 1 && N == 16) continue;
         long long h[2];
         for (int rep = 0; rep < 2; ++rep) {
-          rate_kernel<<<grid, 128, smem>>>(N, n_mma, mode, 1, d_out);
+          rate_kernel<<<grid, 128, smem>>>(N, n_mma, mode, 32, d_out);
           CK(cudaDeviceSynchronize());
         }
         CK(cudaMemcpy(h, d_out, 16, cudaMemcpyDeviceToHost));
@@ -233,6 +234,16 @@ int main() {
                mode ? " (alternating N, N/2)" : "", (double)h[0] / n_mma, (double)h[1] / n_mma);
       }
   }
+  for (int sh : {0, 1, 2, 3, 4, 8, 16, 32})
+    for (int N : {16, 32, 64}) {
+      long long h[2];
+      for (int rep = 0; rep < 2; ++rep) {
+        rate_kernel<<<148, 128, smem>>>(N, n_mma, 0, sh, d_out);
+        CK(cudaDeviceSynchronize());
+      }
+      CK(cudaMemcpy(h, d_out, 16, cudaMemcpyDeviceToHost));
+      printf("row shift %2d x (0,1,2) N=%3d: %.1f clk/MMA\n", sh, N, (double)h[1] / n_mma);
+    }
   run_shift<128>();
   run_shift<64>();
   return 0;
