@@ -74,6 +74,7 @@ _SIGNATURES = {
     "ofb_set_option": (_I, [_P, C.c_char_p, _I]),
     "ofb_get_activation": (C.c_int64, [_P, C.c_char_p, _P, C.c_int64, C.POINTER(_I * 4), _P]),
     "ofb_launch_count": (C.c_int64, [_I]),
+    "ofb_debug_stamps": (_I, [_P]),
     "ofb_profile_enable": (_I, [_P, _I]),
     "ofb_profile_report": (_I, [_P, C.c_char_p, _I]),
 }

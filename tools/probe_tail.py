@@ -80,8 +80,8 @@ for (nm, n, hw, c0, c1, cout, ups) in []:
 
 # ---- clock stamps of epilogue warp 2 of CTA 0
 import numpy as np
-L.ofb_debug_stamps.restype = C.c_int
-L.ofb_debug_stamps.argtypes = [C.c_void_p]
+
+
 opt("direct32", 0)
 for (nm, n, hw, c0, c1, cout, ups) in shapes[:3]:
     d, keep = make(n, hw, c0, c1, cout, ups)
