@@ -928,6 +928,10 @@ static bool g_direct32 = false;  // BN = 32 split-half tiles store straight from
 void conv_tc_set_direct32(bool on) { g_direct32 = on; }
 static int g_fill_div = 2;      // shrink the N tile while fewer than num_sms / g_fill_div tiles exist
 void conv_tc_set_fill_div(int v) { g_fill_div = v > 0 ? v : 2; }
+static bool g_khr_row64 = false;// 64-byte K rows for the Cout = 64 kh-reuse layers (4 ring stages instead of 2)
+void conv_tc_set_khr_row64(bool on) { g_khr_row64 = on; }
+static int g_khr_bw = 16;       // tile width of the kh-reuse kernels (16 or 32)
+void conv_tc_set_khr_bw(int v) { g_khr_bw = v == 32 ? 32 : 16; }
 static int g_sm_share = 1;      // persistent grids use num_sms / g_sm_share CTAs (two concurrent forward lanes share the GPU)
 void conv_tc_set_sm_share(int div) { g_sm_share = div >= 1 ? div : 1; }
 static int g_dbg = 0;           // TcParams::dbg (timing experiments)
@@ -1024,6 +1028,9 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
   // channels per K-step: a 128-byte row when every source allows it, else a 64-byte row
   int row_bytes = 128;
   if ((d->c0 * es) % 128 || (c1 * es) % 128) row_bytes = 64;
+  // experiment (option khr_row64, off): kh-reuse layers with 64 output channels have 96 KB stages = a 2-stage
+  // ring; 64-byte rows give 4 stages of half the size, but measured 3-10 % slower (TMA on 64-byte rows)
+  if (g_khr_row64 && split && d->k == 3 && d->stride == 1 && d->cout == 64 && d->w >= 16 && d->h >= 8) row_bytes = 64;
   const int kc = row_bytes / es;
   OFB_CHECK(d->c0 % kc == 0 && c1 % kc == 0, "conv_tc: channel counts (%d,%d) not divisible by %d", d->c0, c1, kc);
   TcParams p{};
@@ -1050,7 +1057,8 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
   while (!khr && bn > 32 && (long long)groups * p.tiles_x * p.tiles_y * (d->cout / bn) < num_sms() / g_fill_div) bn >>= 1;
   int groups_k = groups;
   if (khr) {
-    p.BW = ow < 32 ? ow : 32; p.BH = 128 / p.BW; p.BNI = 1;
+    // 16 x 8 pixel tiles: the halo box is 16 x 10 = 1.25 x the tile (32 x 4 tiles: 32 x 6 = 1.5 x)
+    p.BW = ow < g_khr_bw ? ow : g_khr_bw; p.BH = 128 / p.BW; p.BNI = 1;
     p.tiles_x = ow / p.BW; p.tiles_y = oh / p.BH;
     groups_k = d->n;
   }

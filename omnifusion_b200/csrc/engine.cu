@@ -36,6 +36,8 @@ void conv_tc_set_pdl(bool on);
 void conv_tc_set_store128(bool on);
 void conv_tc_set_cta2(bool on);
 void conv_tc_set_debug(int v);
+void conv_tc_set_khr_bw(int v);
+void conv_tc_set_khr_row64(bool on);
 void conv_tc_set_sm_share(int div);
 int conv_tc_heads(const void* x, int n, int h, int w, const void* wgt_split, float wgt_unscale, float b_pred,
                   float b_conf, int confidence, float* pred_out, float* conf_out, cudaStream_t s);
@@ -710,6 +712,8 @@ extern "C" int ofb_set_option(ofb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "dedup")) h->dedup = value;
   else if (!strcmp(key, "fuse_ups")) h->fuse_ups = value;
   else if (!strcmp(key, "heads_tc")) h->heads_tc = value;
+  else if (!strcmp(key, "khr_row64")) conv_tc_set_khr_row64(value != 0);   // process-wide
+  else if (!strcmp(key, "khr_bw")) conv_tc_set_khr_bw(value);            // process-wide: tile width of the kh-reuse kernels
   else if (!strcmp(key, "dbg_blocks")) h->dbg_blocks = value < 0 ? 0 : (value > 6 ? 6 : value);   // timing experiments (wrong results)
   else if (!strcmp(key, "pdl")) conv_tc_set_pdl(value != 0);     // process-wide: programmatic dependent launch
   else if (!strcmp(key, "store128")) conv_tc_set_store128(value != 0);

@@ -1,3 +1,5 @@
-timeout 600 python bench.py --batch 8 --erp 1024x2048 --nrows 5 --steps 5 --warmup 3 --skip-cpu-baseline > gpurun_out/cfg3.json 2>gpurun_out/cfg3.err
-timeout 600 python bench.py --batch 16 --erp 512x1024 --nrows 6 --steps 5 --warmup 3 --skip-cpu-baseline > gpurun_out/cfg4.json 2>gpurun_out/cfg4.err
-timeout 600 python bench.py --batch 1 --steps 10 --warmup 3 --skip-cpu-baseline > gpurun_out/b1.json 2>gpurun_out/b1.err
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/tests.log
+for b in 8 32; do
+timeout 300 python bench.py --batch $b --steps 10 --warmup 3 --skip-cpu-baseline > gpurun_out/new_${b}.json 2>>gpurun_out/ab.err
+timeout 300 python bench.py --batch $b --steps 10 --warmup 3 --skip-cpu-baseline --opt khr_row64=0 > gpurun_out/new_${b}_r128.json 2>>gpurun_out/ab.err
+done
