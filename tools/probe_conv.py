@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Timing experiments on the tcgen05 conv engine (not a test, not a benchmark line): runs one layer shape
-with parts of the pipeline disabled (TcParams::dbg) to see which resource bounds it."""
+with the CTA pairing and parts of the epilogue switched off (TcParams::dbg) to see what bounds it."""
 import ctypes as C
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -51,20 +51,16 @@ def time_conv(d, iters=30):
 
 
 shapes = [(144, 8, 256, 256), (144, 16, 128, 128), (144, 4, 512, 512), (576, 8, 256, 256)]
-names = {0: "full", 1: "no lo*Whi MMA", 2: "no stacked MMA", 3: "no MMA", 4: "no B loads", 8: "no A loads",
-         12: "no loads", 15: "nothing"}
-opt("store128", 0)
 for (n, hw, cin, cout) in shapes:
     d, keep = make(n, hw, cin, cout)
     fl = 2.0 * n * hw * hw * cout * 9 * cin
+    row = []
     for cta2 in (0, 1):
         opt("cta2", cta2)
-        row = []
-        for dbg in (0, 1, 2, 3, 4, 8, 12, 15):
+        for dbg, nm in ((0, "full"), (64, "no epilogue math/stores"), (128, "no global stores")):
             opt("tc_debug", dbg)
             us = time_conv(d)
-            row.append(f"{names[dbg]}={us:.1f}us")
-        opt("tc_debug", 0)
-        print(f"n={n} {hw}x{hw} c{cin}->o{cout} cta2={cta2} ({fl / 1e9:.1f} GFLOP): " + "  ".join(row), flush=True)
-
-opt("tc_debug", 0)
+            row.append(f"cta2={cta2} {nm}={us:.1f}us ({fl / us / 1e6:.0f} TFLOP/s)" if dbg == 0 else f"cta2={cta2} {nm}={us:.1f}us")
+    opt("tc_debug", 0)
+    opt("cta2", 1)
+    print(f"n={n} {hw}x{hw} c{cin}->o{cout} ({fl / 1e9:.1f} GFLOP): " + "  ".join(row), flush=True)
