@@ -118,6 +118,10 @@ typedef struct {
   int in_fmt, out_fmt;
   const void* wgt_split; float wgt_unscale;
   int ups2x;
+  int ksplit;        /* > 1 (tcgen05 engine, split-half 1x1 layers only): K is split over `ksplit` CTAs per tile; the
+                        raw float32 partial sums go to `partial` (ksplit, n*h*w, cout) and scale / shift / residual /
+                        act / out are NOT applied - ofb_splitk_finish_ln_f32 finishes the layer */
+  float* partial;
 } ofb_conv_desc;
 int ofb_conv_f32(const ofb_conv_desc* d, void* stream);
 
@@ -168,6 +172,13 @@ int ofb_token_pack_f32(const void* down, const float* pos_emb, int imgs, int N,
 /* nn.LayerNorm over the last dim (model/blocks.py:76,81; encoder_norm eps 1e-6). */
 int ofb_layernorm_f32(const void* x, const float* gamma, const float* beta, int rows, int dim,
                       float eps, void* y, int in_fmt, int out_fmt, void* stream);
+
+/* Finish of a split-K linear with 512 outputs + the LayerNorm that follows it in a Transformer_Block
+ * (model/blocks.py:84-88): x_out = residual + bias + wscale * sum_s partial[s] (split-half planes, rows x 512),
+ * ln_out = LayerNorm(x_out; gamma, beta, eps) in format ln_fmt.  residual / x_out are split-half planes. */
+int ofb_splitk_finish_ln_f32(const float* partial, int ksplit, float wscale, const float* bias,
+                             const void* residual, int rows, int dim, void* x_out, const float* gamma,
+                             const float* beta, float eps, void* ln_out, int ln_fmt, void* stream);
 
 /* Attention core, model/blocks.py:50-62: q (rows,512), kv (rows,1024) [k | v],
  * rows = B*N, heads of 128; softmax(q k^T / sqrt(128)) v -> out (rows,512). */

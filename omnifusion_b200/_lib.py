@@ -28,7 +28,7 @@ class ConvDesc(C.Structure):
                 ("scale", C.c_void_p), ("shift", C.c_void_p), ("residual", C.c_void_p),
                 ("act", C.c_int), ("out", C.c_void_p), ("engine", C.c_int),
                 ("in_fmt", C.c_int), ("out_fmt", C.c_int), ("wgt_split", C.c_void_p), ("wgt_unscale", C.c_float),
-                ("ups2x", C.c_int)]
+                ("ups2x", C.c_int), ("ksplit", C.c_int), ("partial", C.c_void_p)]
 
 
 class Geometry(C.Structure):
@@ -60,6 +60,7 @@ _SIGNATURES = {
     "ofb_point_embed_f32": (_I, [_P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "ofb_token_pack_f32": (_I, [_P, _P, _I, _I, _P, _I, _P]),
     "ofb_layernorm_f32": (_I, [_P, _P, _P, _I, _I, C.c_float, _P, _I, _I, _P]),
+    "ofb_splitk_finish_ln_f32": (_I, [_P, _I, C.c_float, _P, _P, _I, _I, _P, _P, _P, C.c_float, _P, _I, _P]),
     "ofb_attention_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "ofb_attention_qkv_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _P]),
     "ofb_heads_tc_f16": (_I, [_P, _I, _I, _I, _P, C.c_float, C.c_float, C.c_float, _I, _P, _P, _P]),

@@ -39,6 +39,9 @@ struct TcParams {
   int dbg;               // timing experiments only (results are wrong):
                          // 32 skip the fused-upsample interpolation, 64 skip the epilogue math and stores,
                          // 128 skip only the global stores of the epilogue
+  int ksplit;            // split-K (1x1 / linear layers only): tile index = ((m tile * tiles_n + n tile) * ksplit + split);
+  float* partial;        // each split writes its raw float32 accumulators to partial[split][pixel][cout] (ofb_splitk_finish_ln_f32 reduces)
+  long long m_total;     // pixels per split plane of `partial`
   float* heads_pred; float* heads_conf; float heads_bp, heads_bc;   // UPS == 2: the two heads' outputs and biases
   long long* dbg_buf;    // dbg & 16: clock stamps of the epilogue warp 2 of CTA 0: [tile][8]
   int group64;           // accumulate the three split-half products in the cta_group::2 column grouping (see the MMA warp)
@@ -285,7 +288,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   const int ups_r0 = UPS ? min((int)blockIdx.x * ups_per, p.total_tiles) : 0, ups_r1 = UPS ? min(ups_r0 + ups_per, p.total_tiles) : 0;
   const int cin = p.c0 + p.c1;
   const int cchunks = cin / Cfg::KC;
-  const int ksteps = (KHR ? 3 : p.taps) * cchunks;
+  const int ksteps = ((KHR ? 3 : p.taps) * cchunks) / p.ksplit;      // K-steps of one tile (of one split)
   const int tiles_per_group = p.tiles_x * p.tiles_y;
 
   if (warp == 0 && lane == 0) {
@@ -364,17 +367,20 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     const uint32_t a_bytes = KHR ? (uint32_t)((p.BH + 2) * p.BW * ROW_BYTES) : (uint32_t)Cfg::A_BYTES;
     const uint32_t tx = (uint32_t)Cfg::PLANES * ((ld_a ? a_bytes : 0u) + (ld_b ? (uint32_t)Cfg::B_BYTES : 0u));
     for (int t = tile0; !UPS && t < p.total_tiles; t += tile_step) {
-      const int nt = t % p.tiles_n, mt = CTA2 ? 2 * (t / p.tiles_n) + (int)rank : t / p.tiles_n;
+      const int sp = t % p.ksplit, tq = t / p.ksplit;            // split-K slice (ksplit == 1: tq == t)
+      const int nt = tq % p.tiles_n, mt = CTA2 ? 2 * (tq / p.tiles_n) + (int)rank : tq / p.tiles_n;
       const int grp = mt / tiles_per_group, trem = mt - grp * tiles_per_group;
       const int ty = trem / p.tiles_x, tx_ = trem - ty * p.tiles_x;
       const int img0 = grp * p.BNI, y0 = ty * p.BH, x0 = tx_ * p.BW, n0 = nt * BN;
+      // split-K exists for single-tap layers only: the slice is a range of channel chunks
+      const int cq_begin = p.ksplit > 1 ? sp * ksteps : 0, cq_end = p.ksplit > 1 ? cq_begin + ksteps : cchunks;
       int kh = 0, kw = 0;
       for (int tap = 0; tap < ntap; ++tap) {
         // KHR: `tap` is kw; the box carries rows y0-1 .. y0+BH, the weights all three kh
         const int cx = KHR ? x0 + tap - 1 : x0 * p.sx + kw - p.padx;
         const int cy = KHR ? y0 - 1 : y0 * p.sy + kh - p.pady;
         const int wk = tap * cin;
-        for (int cq = 0; cq < cchunks; ++cq) {
+        for (int cq = cq_begin; cq < cq_end; ++cq) {
           int c = cq * Cfg::KC;
           int src = 0;
           if (c >= p.c0) { src = 1; c -= p.c0; }
@@ -480,7 +486,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         // 128 output channels, channels [0,64) accumulate hi*Whi + lo*Whi in one column and hi*Wlo in the other;
         // channels [64,128) accumulate hi*Wlo + lo*Whi in one column and hi*Whi in the other (that is what the
         // cta_group::2 operand split produces); the epilogue adds the two columns.
-        const bool upper = !CTA2 && BN < 128 && p.group64 && (((t % p.tiles_n) * BN) & 64) != 0;
+        const bool upper = !CTA2 && BN < 128 && p.group64 && ((((t / p.ksplit) % p.tiles_n) * BN) & 64) != 0;
         const uint32_t acc_lo = acc + (upper ? BN : 0);           // where lo*Whi accumulates
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(bars + 8 * st, ph);
@@ -547,7 +553,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     int last_n0 = -1;
     uint32_t i = 0, chunk_ctr = 0;
     for (int t = UPS ? ups_r0 : tile0; t < (UPS ? ups_r1 : p.total_tiles); t += UPS ? 1 : tile_step, ++i) {
-      const int nt = t % p.tiles_n, mt = CTA2 ? 2 * (t / p.tiles_n) + (int)rank : t / p.tiles_n;
+      const int sp = t % p.ksplit, tq = t / p.ksplit;
+      const int nt = tq % p.tiles_n, mt = CTA2 ? 2 * (tq / p.tiles_n) + (int)rank : tq / p.tiles_n;
       const int grp = mt / tiles_per_group, trem = mt - grp * tiles_per_group;
       const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
       const int img0 = grp * p.BNI, y0 = ty * p.BH, x0 = tx * p.BW, n0 = nt * BN;
@@ -613,6 +620,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         }
         if (stamp) p.dbg_buf[i * 8 + 2] = clock64();
         if (p.dbg & 64) continue;
+        if (p.ksplit > 1) {                      // split-K: raw partial sums, reduced (+ bias, residual, LayerNorm) by the finish kernel
+          if (ok) {
+            float* dst = p.partial + ((size_t)sp * p.m_total + pix) * p.cout + n0 + cb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              st4(dst + j, make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+          }
+          continue;
+        }
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * s_scale[cb + j] + s_shift[cb + j];
@@ -1046,6 +1062,10 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
   p.dbg = g_dbg;
   p.dbg_buf = (g_dbg & 16) ? conv_tc_debug_buffer() : nullptr;
   p.group64 = g_cta2 ? 1 : 0;
+  const int S = d->ksplit > 1 ? d->ksplit : 1;
+  OFB_CHECK(S == 1 || (split && d->k == 1 && d->stride == 1 && !d->ups2x && d->partial && (cin / kc) % S == 0),
+            "conv_tc: split-K needs a split-half 1x1 layer, a partial buffer and %d K-chunks divisible by %d", cin / kc, S);
+  p.ksplit = S; p.partial = d->partial; p.m_total = (long long)d->n * oh * ow;
   const int groups = (d->n + p.BNI - 1) / p.BNI;
   // kh-reuse tiling for the narrow 3x3 layers: 32x4 / 16x8 pixel tiles inside one image.  Decided from the
   // layer shape only, never from the batch size, so results stay batch-invariant (it accumulates the taps
@@ -1054,7 +1074,7 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
   // widest N tile unless that leaves most SMs without a tile
   int bn = d->cout >= 128 ? 128 : d->cout;
   // (only for really small problems such as the token linears: narrow tiles re-read the A tile more often)
-  while (!khr && bn > 32 && (long long)groups * p.tiles_x * p.tiles_y * (d->cout / bn) < num_sms() / g_fill_div) bn >>= 1;
+  while (!khr && bn > 32 && (long long)groups * p.tiles_x * p.tiles_y * (d->cout / bn) * S < num_sms() / g_fill_div) bn >>= 1;
   int groups_k = groups;
   if (khr) {
     // 16 x 8 pixel tiles: the halo box is 16 x 10 = 1.25 x the tile (32 x 4 tiles: 32 x 6 = 1.5 x)
@@ -1063,9 +1083,9 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
     groups_k = d->n;
   }
   p.tiles_n = d->cout / bn;
-  p.total_tiles = groups_k * p.tiles_x * p.tiles_y * p.tiles_n;
+  p.total_tiles = groups_k * p.tiles_x * p.tiles_y * p.tiles_n * S;
   // CTA pairs (cta_group::2): two adjacent M tiles share one weight tile.  Decided from the layer shape only.
-  const bool cta2 = g_cta2 && split && bn == 128 && !khr && row_bytes == 128;
+  const bool cta2 = g_cta2 && split && bn == 128 && !khr && row_bytes == 128 && S == 1;
   if (cta2) p.total_tiles = ((groups_k * p.tiles_x * p.tiles_y + 1) / 2) * p.tiles_n;
 
   TcMaps maps;
@@ -1141,6 +1161,7 @@ int conv_tc_heads(const void* x, int n, int h, int w, const void* wgt_split, flo
   p.BW = 128; p.BH = 1; p.BNI = 1; p.tiles_x = 1; p.tiles_y = h;
   p.wscale = wgt_unscale; p.act = OFB_ACT_NONE;
   p.tiles_n = 1; p.total_tiles = n * h;
+  p.ksplit = 1;
   p.heads_pred = pred_out; p.heads_conf = confidence ? conf_out : nullptr; p.heads_bp = b_pred; p.heads_bc = b_conf;
   p.dbg = g_dbg;
   p.dbg_buf = (g_dbg & 16) ? conv_tc_debug_buffer() : nullptr;
@@ -1185,6 +1206,7 @@ int stem_tc(const void* patches, int n, int h, int w, const void* wgt_split, flo
   p.scale = scale; p.shift = shift; p.wscale = wgt_unscale; p.residual = nullptr; p.out = out; p.act = OFB_ACT_RELU;
   p.plane = (long long)n * oh * ow * 64;
   p.tiles_n = 1; p.total_tiles = n * p.tiles_y;
+  p.ksplit = 1;
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
   const size_t in_plane = (size_t)n * h * pitch * 4;         // halves per plane

@@ -87,6 +87,7 @@ struct ofb_handle {
   float *pred_w = nullptr, *conf_w = nullptr;
   ConvW heads16;                   // both heads as one 16-channel 3x3 conv (0 = pred, 1 = weight_pred) for the tcgen05 engine
   int dbg_blocks = 6;              // timing experiments only: number of transformer blocks executed
+  int splitk = 4;                  // K slices of the two 512-wide token linears on the tcgen05 engine (1 = off)
   int heads_tc = 1;                // run the heads on the tensor pipe (split-half format, 128-pixel rows)
   float pred_b = 0.f, conf_b = 0.f;
   Mlp mlp[2]{};
@@ -344,7 +345,7 @@ struct Plan {
 struct Buffers {
   float *patches, *conv1, *pool, *l1t, *l1a, *l1b, *layer1_pre, *layer1;
   float *l2t, *l2a, *l2b, *l2d, *layer2, *l3t, *l3a, *l3b, *l3d, *layer3, *l4t, *l4a, *l4b, *l4d, *layer4;
-  float *down, *tok, *ln, *q, *kv, *att, *tok2, *fc1, *enc;
+  float *down, *tok, *ln, *q, *kv, *att, *tok2, *fc1, *enc, *part;
   float *up0, *d00, *d01, *up1, *d10, *d11, *up2, *d20, *d21, *up3, *d30, *d31, *up4, *d40;
   float *pred, *conf, *depth_p;
 };
@@ -364,6 +365,7 @@ static size_t plan_buffers(ofb_handle* h, int imgs, int P, Buffers* b) {
   b->down = pl.take(I * 512); b->tok = pl.take(I * 512); b->ln = pl.take(I * 512); b->q = pl.take(I * 512);
   b->kv = pl.take(I * 1536); b->att = pl.take(I * 512); b->tok2 = pl.take(I * 512); b->fc1 = pl.take(I * 2048);
   b->enc = pl.take(I * 512);
+  b->part = pl.take(I * 512 * 4);                  // split-K partial sums of attn.proj / mlp.fc2 (4 slices)
   b->up0 = pl.take(I * p16 * p16 * 512); b->d00 = pl.take(I * p16 * p16 * 256); b->d01 = pl.take(I * p16 * p16 * 128);
   b->up1 = pl.take(I * p8 * p8 * 128); b->d10 = pl.take(I * p8 * p8 * 128); b->d11 = pl.take(I * p8 * p8 * 64);
   b->up2 = pl.take(I * p4 * p4 * 64); b->d20 = pl.take(I * p4 * p4 * 64); b->d21 = pl.take(I * p4 * p4 * 64);
@@ -445,11 +447,13 @@ static bool can_fuse_ups(ofb_handle* h, const ConvW& w, int n, int hh, int ww) {
   return conv_tc_supported(&d);
 }
 
-static int run_linear(Ctx& c, const ConvW& w, const float* in, const float* residual, int act, float* out) {
+static int run_linear(Ctx& c, const ConvW& w, const float* in, const float* residual, int act, float* out,
+                      int ksplit = 1, float* partial = nullptr) {
   ofb_conv_desc d{};
   d.in0 = in; d.c0 = w.cin; d.n = c.imgs; d.h = 1; d.w = 1;
   d.wgt = w.w; d.k = 1; d.stride = 1; d.pad = 0; d.cout = w.cout;
   d.scale = nullptr; d.shift = w.shift; d.residual = residual; d.act = act; d.out = out;
+  d.ksplit = ksplit; d.partial = partial;      // ksplit > 1: raw partial sums only (`out` just anchors the unused store maps)
   d.engine = c.h->engine;
   d.in_fmt = d.out_fmt = c.h->fmt; d.wgt_split = w.ws; d.wgt_unscale = w.unscale;
   double fl, by;
@@ -552,7 +556,30 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
     if (ofb_token_pack_f32(b.down, h->pos_emb, imgs, N, b.tok, F, vs)) return -1; }
     float* x = b.tok;
     float* y = b.tok2;
-    for (int i = 0; i < h->dbg_blocks; ++i) {   // Transformer_Block, model/blocks.py:84-88 (dbg_blocks = 6)
+    const int SK = (F == OFB_FMT_SPLIT16 && h->engine != OFB_ENGINE_SIMT) ? h->splitk : 1;
+    const int nblk = h->dbg_blocks;
+    if (SK > 1 && nblk > 0) {
+      // attn.proj and mlp.fc2 run split-K; their finish kernels add bias + residual and apply the NEXT LayerNorm
+      { Prof pr(h, s, "layernorm", 0.0, 4.0*((double)imgs*1024));
+      if (ofb_layernorm_f32(x, h->blk[0].n1g, h->blk[0].n1b, imgs, 512, 1e-5f, b.ln, F, F, vs)) return -1; }
+      for (int i = 0; i < nblk; ++i) {   // Transformer_Block, model/blocks.py:84-88
+        Block& B = h->blk[i];
+        if (run_linear(c, B.qkv, b.ln, nullptr, OFB_ACT_NONE, b.kv)) return -1;     // (imgs,1536) = [q | k | v]
+        { Prof pr(h, s, "attention", 0.0, 4.0*((double)imgs*2048));
+        if (ofb_attention_qkv_f32(b.kv, Bc, N, 4, 128, b.att, F, vs)) return -1; }
+        if (run_linear(c, B.proj, b.att, nullptr, OFB_ACT_NONE, b.kv, SK, b.part)) return -1;
+        { Prof pr(h, s, "splitk_finish_ln", 0.0, 4.0*((double)imgs*512*(SK + 3)));     // y = x + proj(att); ln = norm2(y)
+        if (ofb_splitk_finish_ln_f32(b.part, SK, B.proj.unscale, B.proj.shift, x, imgs, 512, y, B.n2g, B.n2b, 1e-5f, b.ln, F, vs)) return -1; }
+        if (run_linear(c, B.fc1, b.ln, nullptr, OFB_ACT_GELU, b.fc1)) return -1;
+        if (run_linear(c, B.fc2, b.fc1, nullptr, OFB_ACT_NONE, b.kv, SK, b.part)) return -1;
+        const bool last = i == nblk - 1;      // x = y + fc2(gelu(fc1)); then norm1 of the next block, or encoder_norm (eps 1e-6)
+        { Prof pr(h, s, "splitk_finish_ln", 0.0, 4.0*((double)imgs*512*(SK + 3)));
+        if (ofb_splitk_finish_ln_f32(b.part, SK, B.fc2.unscale, B.fc2.shift, y, imgs, 512, x,
+                                     last ? h->enc_g : h->blk[i + 1].n1g, last ? h->enc_b : h->blk[i + 1].n1b,
+                                     last ? 1e-6f : 1e-5f, last ? b.enc : b.ln, last ? OFB_FMT_F32 : F, vs)) return -1; }
+      }
+    } else {
+    for (int i = 0; i < nblk; ++i) {   // Transformer_Block, model/blocks.py:84-88 (dbg_blocks = 6)
       Block& B = h->blk[i];
       { Prof pr(h, s, "layernorm", 0.0, 4.0*((double)imgs*1024));
       if (ofb_layernorm_f32(x, B.n1g, B.n1b, imgs, 512, 1e-5f, b.ln, F, F, vs)) return -1; }
@@ -567,6 +594,7 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
     }
     { Prof pr(h, s, "layernorm", 0.0, 4.0*((double)imgs*1024));
     if (ofb_layernorm_f32(x, h->enc_g, h->enc_b, imgs, 512, 1e-6f, b.enc, F, OFB_FMT_F32, vs)) return -1; }
+    }
 
     // decoder (:337-369); the token broadcast-add (:334-335) is fused into the first upsample
     { Prof pr(h, s, "upsample2x_c512", 0.0, 4.0*5.0*(double)imgs*(P / 32)*(P / 32)*512);
@@ -712,6 +740,7 @@ extern "C" int ofb_set_option(ofb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "dedup")) h->dedup = value;
   else if (!strcmp(key, "fuse_ups")) h->fuse_ups = value;
   else if (!strcmp(key, "heads_tc")) h->heads_tc = value;
+  else if (!strcmp(key, "splitk")) h->splitk = value == 2 || value == 4 ? value : 1;
   else if (!strcmp(key, "khr_row64")) conv_tc_set_khr_row64(value != 0);   // process-wide
   else if (!strcmp(key, "khr_bw")) conv_tc_set_khr_bw(value);            // process-wide: tile width of the kh-reuse kernels
   else if (!strcmp(key, "dbg_blocks")) h->dbg_blocks = value < 0 ? 0 : (value > 6 ? 6 : value);   // timing experiments (wrong results)

@@ -305,6 +305,71 @@ __global__ void layernorm_kernel(const void* __restrict__ x, const float* __rest
   }
 }
 
+// ------------------------------------------------------ split-K finish + LayerNorm
+// The two 512-wide linears of a Transformer_Block (attn.proj, mlp.fc2; model/blocks.py:84-88) run split-K
+// on the tcgen05 engine (few token rows: the K range is what can be spread over the SMs) and leave raw
+// float32 partial sums.  One warp per row: x_new = residual + bias + wscale * sum_s partial[s] (fixed order),
+// written as the new residual stream, and LayerNorm(x_new) - the input of the next linear - in the same pass,
+// so the finish replaces the LayerNorm launch instead of adding one.
+template <bool LN_SPLIT>
+__global__ void splitk_ln_kernel(const float* __restrict__ partial, int ksplit, float wscale,
+                                 const float* __restrict__ bias, const void* __restrict__ residual, int rows,
+                                 void* __restrict__ x_out, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, void* __restrict__ ln_out) {
+  constexpr int DIM = 512, PER = DIM / 32;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const size_t plane = (size_t)rows * DIM;
+  float v[PER];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; i += 4) {
+    const int col = (i / 4) * 128 + lane * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < ksplit; ++k) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(partial + ((size_t)k * rows + row) * DIM + col));
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    const float4 r = act_ld4<true>(residual, (size_t)row * DIM + col, plane);
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) b = __ldg(reinterpret_cast<const float4*>(bias + col));
+    // same expression as the conv epilogue: acc * scale + shift, then + residual
+    float4 o;
+    o.x = (acc.x * wscale + b.x) + r.x; o.y = (acc.y * wscale + b.y) + r.y;
+    o.z = (acc.z * wscale + b.z) + r.z; o.w = (acc.w * wscale + b.w) + r.w;
+    act_st4<true>(x_out, (size_t)row * DIM + col, plane, o);
+    // LayerNorm reads what the next kernel would read back: the split-half rounded value
+    const __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn(o.x - f0.x, o.y - f0.y), l1 = __floats2half2_rn(o.z - f1.x, o.w - f1.y);
+    const float2 g0 = __half22float2(l0), g1 = __half22float2(l1);
+    v[i] = f0.x + g0.x; v[i + 1] = f0.y + g0.y; v[i + 2] = f1.x + g1.x; v[i + 3] = f1.y + g1.y;
+    s += v[i] + v[i + 1] + v[i + 2] + v[i + 3];
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / DIM;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { const float d = v[i] - mean; q += d * d; }
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float var = q / DIM + eps;
+  float rstd = rsqrtf(var);
+  rstd = rstd * (1.5f - 0.5f * var * rstd * rstd);
+#pragma unroll
+  for (int i = 0; i < PER; i += 4) {
+    const int col = (i / 4) * 128 + lane * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + col));
+    float4 o;
+    o.x = (v[i] - mean) * rstd * g.x + b.x;
+    o.y = (v[i + 1] - mean) * rstd * g.y + b.y;
+    o.z = (v[i + 2] - mean) * rstd * g.z + b.z;
+    o.w = (v[i + 3] - mean) * rstd * g.w + b.w;
+    act_st4<LN_SPLIT>(ln_out, (size_t)row * DIM + col, plane, o);
+  }
+}
+
 // ------------------------------------------------------------------ attention
 // One CTA per (panorama, head, group of ATT_RG query rows): N <= 64 tokens, head_dim 128.  K, V and the
 // group's Q rows are staged in shared memory (rows padded to 132 floats: 16-byte aligned, bank-skewed),
@@ -554,6 +619,19 @@ extern "C" int ofb_layernorm_f32(const void* x, const float* gamma, const float*
   else if (in_fmt && out_fmt) layernorm_kernel<512, true, true><<<blocks, 128, 0, s>>>(x, gamma, beta, rows, eps, y);
   else if (in_fmt) layernorm_kernel<512, true, false><<<blocks, 128, 0, s>>>(x, gamma, beta, rows, eps, y);
   else layernorm_kernel<512, false, true><<<blocks, 128, 0, s>>>(x, gamma, beta, rows, eps, y);
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ofb_splitk_finish_ln_f32(const float* partial, int ksplit, float wscale, const float* bias,
+                                        const void* residual, int rows, int dim, void* x_out, const float* gamma,
+                                        const float* beta, float eps, void* ln_out, int ln_fmt, void* stream) {
+  OFB_CHECK(partial && residual && x_out && gamma && beta && ln_out && OFB_FMT_OK(ln_fmt), "splitk_finish_ln: bad arguments");
+  OFB_CHECK(dim == 512 && ksplit >= 1 && rows > 0, "splitk_finish_ln: dim must be 512 (got %d), ksplit >= 1", dim);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int blocks = cdiv(rows, 4);
+  if (ln_fmt) splitk_ln_kernel<true><<<blocks, 128, 0, s>>>(partial, ksplit, wscale, bias, residual, rows, x_out, gamma, beta, eps, ln_out);
+  else splitk_ln_kernel<false><<<blocks, 128, 0, s>>>(partial, ksplit, wscale, bias, residual, rows, x_out, gamma, beta, eps, ln_out);
   OFB_LAUNCH_CHECK();
   return 0;
 }

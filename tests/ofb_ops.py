@@ -171,7 +171,7 @@ def weight_scale(w):
 
 
 def conv_fmt(in0, wgt, k, stride, pad, in1=None, scale=None, shift=None, residual=None, act=0, engine=0,
-             in_fmt=0, out_fmt=0, ups2x=0):
+             in_fmt=0, out_fmt=0, ups2x=0, ksplit=1):
     """conv with explicit storage formats: float32 NHWC tensors in, converted to/from split planes here.
     ups2x: in0 is the low-resolution tensor, bilinearly upsampled x2 inside the conv kernel."""
     n, h, w, c0 = in0.shape
@@ -203,5 +203,11 @@ def conv_fmt(in0, wgt, k, stride, pad, in1=None, scale=None, shift=None, residua
         torch.empty((n, oh, ow, cout), device=in0.device)
     d.act, d.out, d.engine, d.in_fmt, d.out_fmt = act, out.data_ptr(), engine, in_fmt, out_fmt
     d.ups2x = ups2x
+    if ksplit > 1:
+        # split-K: the kernel leaves raw float32 partial sums (ksplit, n*oh*ow, cout); returns them with 1/mul
+        part = torch.zeros(ksplit, n * oh * ow, cout, device=in0.device)
+        d.ksplit, d.partial = ksplit, part.data_ptr()
+        ck(L().ofb_conv_f32(C.byref(d), _st(in0)))
+        return part, 1.0 / mul
     ck(L().ofb_conv_f32(C.byref(d), _st(in0)))
     return merge16(out, (n, oh, ow, cout)) if out_fmt == 1 else out

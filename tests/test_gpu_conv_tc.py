@@ -213,3 +213,36 @@ def test_heads_on_tensor_cores_match_torch_cpu(n, h, confidence):
         assert ((gc.cpu() - conf[:, 0]).abs() <= 2e-5).all()
     else:
         assert (gc == -1.0).all()          # conf_out untouched
+
+
+@pytest.mark.parametrize("rows,cin,ksplit", [(144, 2048, 4), (18, 512, 4), (576, 512, 2)])
+def test_splitk_linear_and_finish_layernorm(rows, cin, ksplit):
+    """attn.proj / mlp.fc2 of a Transformer_Block (model/blocks.py:84-88) as a split-K linear on the tcgen05 engine
+    (ofb_conv_desc.ksplit) + ofb_splitk_finish_ln_f32 (bias + residual + the following LayerNorm), against
+    torch-CPU fp32."""
+    o = ops()
+    x = rand(rows, cin, seed=31)
+    w = rand(512, cin, seed=32, scale=(1.0 / cin) ** 0.5)
+    bias, res = rand(512, seed=33, scale=0.1), rand(rows, 512, seed=34)
+    gamma, beta = 0.5 + torch.rand(512, generator=torch.Generator().manual_seed(35)), rand(512, seed=36, scale=0.1)
+    want_x = res + F.linear(x, w, bias)
+    want_ln = F.layer_norm(want_x, (512,), gamma, beta, 1e-5)
+    xd = x.view(rows, 1, 1, cin).to(DEV)
+    wd = w.view(512, 1, 1, cin).to(DEV)
+    part, unscale = o.conv_fmt(xd, wd, 1, 1, 0, engine=_lib.ENGINE_TC, in_fmt=_lib.FMT_SPLIT16,
+                               out_fmt=_lib.FMT_SPLIT16, ksplit=ksplit)
+    resd = o.split16(res.to(DEV))
+    bias_d, gamma_d, beta_d = bias.to(DEV), gamma.to(DEV), beta.to(DEV)      # kept alive across the launches
+    x_out = torch.empty(2 * rows * 512, dtype=torch.float16, device=DEV)
+    for ln_fmt in (1, 0):
+        ln_out = torch.empty(2 * rows * 512, dtype=torch.float16, device=DEV) if ln_fmt else torch.empty(rows, 512, device=DEV)
+        _lib.check(_lib.lib().ofb_splitk_finish_ln_f32(_lib.ptr(part), ksplit, unscale, _lib.ptr(bias_d), _lib.ptr(resd),
+                                                        rows, 512, _lib.ptr(x_out), _lib.ptr(gamma_d),
+                                                        _lib.ptr(beta_d), 1e-5, _lib.ptr(ln_out), ln_fmt,
+                                                        _lib.stream_of(torch.device(DEV))))
+        torch.cuda.synchronize()
+        got_x = o.merge16(x_out, (rows, 512)).cpu()
+        got_ln = (o.merge16(ln_out, (rows, 512)) if ln_fmt else ln_out).cpu()
+        ex, el = (got_x - want_x).abs().max().item(), (got_ln - want_ln).abs().max().item()
+        print(f"[parity] split-K linear rows={rows} K={cin} S={ksplit} ln_fmt={ln_fmt}: x max_abs_err={ex:.3e} ln max_abs_err={el:.3e}")
+        assert ex <= 2e-5 and el <= 5e-5
