@@ -203,6 +203,10 @@ int ofb_heads_f32(const void* x, int imgs, int h, int w,
                   const float* w_pred, float b_pred, const float* w_conf, float b_conf,
                   int confidence, float* pred_out, float* conf_out, int in_fmt, void* stream);
 
+/* Loader-side input conversion, dataset_loader_stanford.py:52,79 (rgb.astype(float32) / 255, HWC -> CHW; channel
+ * order untouched): src (B,H,W,C) uint8 device -> dst (B,C,H,W) float32, bit-identical to the numpy expression. */
+int ofb_u8hwc_to_f32chw(const uint8_t* src, int B, int H, int W, int C, float* dst, void* stream);
+
 /* Abs-Rel partial sums, metrics.py:7-9: out[0] += sum(|p*scale-g|/g over mask), out[1] += count.
  * `out` must be zeroed by the caller. */
 int ofb_absrel_partial(const float* pred, const float* gt, const uint8_t* mask, size_t n,

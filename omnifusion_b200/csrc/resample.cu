@@ -388,6 +388,27 @@ extern "C" int ofb_blend_conf_f32(const float* pred_w, const float* conf, int B,
   return 0;
 }
 
+// ------------------------------------------------------------------ loader-side input conversion
+// dataset_loader_stanford.py:52,79: rgb.astype(np.float32) / 255 and transpose(2,0,1) of the decoded uint8
+// panorama (cv2 channel order kept, as the reference keeps it).  One thread per pixel; the division is the IEEE
+// float32 division numpy performs, so the result is bit-identical.
+__global__ void u8hwc_to_f32chw_kernel(const uint8_t* __restrict__ src, size_t pixels_per_img, int C, size_t total,
+                                       float* __restrict__ dst) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const size_t b = i / pixels_per_img, px = i - b * pixels_per_img;
+  for (int c = 0; c < C; ++c)
+    dst[(b * C + c) * pixels_per_img + px] = __fdiv_rn((float)src[i * C + c], 255.f);
+}
+
+extern "C" int ofb_u8hwc_to_f32chw(const uint8_t* src, int B, int H, int W, int C, float* dst, void* stream) {
+  OFB_CHECK(src && dst && B > 0 && H > 0 && W > 0 && C >= 1 && C <= 4, "u8hwc_to_f32chw: bad arguments");
+  const size_t ppi = (size_t)H * W, total = ppi * B;
+  u8hwc_to_f32chw_kernel<<<(unsigned)cdiv((long long)total, 256), 256, 0, (cudaStream_t)stream>>>(src, ppi, C, total, dst);
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int ofb_absrel_partial(const float* pred, const float* gt, const uint8_t* mask, size_t n,
                                   float scale, double* out, void* stream) {
   OFB_CHECK(pred && gt && mask && out, "absrel: null pointer");

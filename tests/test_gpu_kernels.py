@@ -292,3 +292,18 @@ def test_depth_metrics_match_oracle_eval():
         assert got["n"] == ref["n"]
         for k in metrics.METRIC_NAMES:
             assert abs(got[k] - ref[k]) <= 2e-6 * max(1.0, abs(ref[k])), (k, got[k], ref[k])
+
+
+def test_rgb_u8_to_input_is_bit_identical_to_the_loader_expression():
+    """dataset_loader_stanford.py:52,79: rgb.astype(np.float32) / 255, transpose(2,0,1)."""
+    import numpy as np
+    from omnifusion_b200.preprocess import rgb_u8_to_input
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, size=(2, 37, 53, 3), dtype=np.uint8)
+    img[0, 0, 0] = (0, 255, 254)
+    want = np.stack([(im.astype(np.float32) / 255).transpose(2, 0, 1) for im in img])
+    got = rgb_u8_to_input(torch.from_numpy(img).to(DEV)).cpu().numpy()
+    assert got.dtype == np.float32 and got.shape == (2, 3, 37, 53)
+    assert np.array_equal(got, want)
+    with pytest.raises(Exception):
+        rgb_u8_to_input(torch.from_numpy(img))          # CPU tensor: no CPU path
