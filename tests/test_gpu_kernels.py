@@ -307,3 +307,16 @@ def test_rgb_u8_to_input_is_bit_identical_to_the_loader_expression():
     assert np.array_equal(got, want)
     with pytest.raises(Exception):
         rgb_u8_to_input(torch.from_numpy(img))          # CPU tensor: no CPU path
+
+
+def test_depth_to_points_matches_the_reference_expression():
+    """test.py:208-218: xyz rays (util.py:159-174) * depth, predictions above 8 m zeroed for the export."""
+    from omnifusion_b200.pointcloud import depth_to_points, erp_rays
+    depth = 0.1 + 9.9 * torch.rand(2, 1, 16, 32, generator=torch.Generator().manual_seed(3))
+    rays = torch.from_numpy(erp_rays(16, 32))
+    want = rays.unsqueeze(0) * depth.reshape(2, 16 * 32, 1)
+    got = depth_to_points(depth.to(DEV))
+    assert torch.equal(got.cpu(), want)
+    clipped = depth.clone()
+    clipped[clipped > 8] = 0
+    assert torch.equal(depth_to_points(depth.to(DEV), max_depth=8).cpu(), rays.unsqueeze(0) * clipped.reshape(2, -1, 1))

@@ -1,4 +1,5 @@
 """Host-built geometry tables of the product vs the oracle's dense tables (bit-exact)."""
+import numpy as np
 import pytest
 import torch
 
@@ -51,3 +52,15 @@ def test_blend_table_chunking_invariant():
     b = tables.blend_table(FOV, 4, 16, (40, 80), rows_per_chunk=64)
     for k in ("rowptr", "idx", "w"):
         assert torch.equal(a[k], b[k])
+
+
+def test_pointcloud_rays_match_reference_golden(golden_dir):
+    """omnifusion_b200.pointcloud.erp_rays vs the reference's coords2uv / uv2xyz (util.py:159-174) run on the
+    meshgrid of test.py:210-213 (tests/golden/make_golden_pointcloud.py)."""
+    import os
+    from omnifusion_b200.pointcloud import erp_rays
+    g = np.load(os.path.join(golden_dir, "pointcloud_rays.npz"))
+    for key in g.files:
+        h, w = (int(v) for v in key.split("_")[1].split("x"))
+        got = erp_rays(h, w)
+        assert got.dtype == np.float32 and np.array_equal(got, g[key]), key
