@@ -89,6 +89,23 @@ def test_iterative_forward_matches_oracle_with_stages(confidence, fmt):
     assert ((tok - t1["tokens"]).abs().max() / t1["tokens"].abs().max()).item() <= stage_tol
 
 
+def test_nrows3_forward_matches_oracle_including_uncovered_pixels():
+    """nrows=3 (10 patches): the only layout that leaves ERP pixels uncovered; the reference returns
+    0 there (pers2equi_v3.py:189-196 with all weights zero, spherical_model_iterative.py:376-378)."""
+    net = model("iterative", 3)
+    sd = synthetic_state_dict("iterative", 10, 0)
+    rgb = urand(2, 3, 64, 128, seed=77)
+    ref = om.forward_iterative(sd, rgb, 2, True, nrows=3)
+    with torch.no_grad():
+        got = net(rgb.to(DEV), iter=2, confidence=True)
+    for i, (g, r) in enumerate(zip(got, ref)):
+        e = max_rel(g.cpu(), r)
+        print(f"[parity] nrows=3 iter{i}: max_rel={e:.3e}; uncovered pixels {(r == 0).sum().item()}")
+        assert e <= REL_TOL
+        assert torch.equal(g.cpu() == 0, r == 0)
+    assert (ref[-1] == 0).any()
+
+
 def test_single_stage_forward_matches_oracle():
     net = model("single", 4)
     sd = synthetic_state_dict("single", 18, 0)
