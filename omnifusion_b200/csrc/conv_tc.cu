@@ -1,19 +1,23 @@
-// tcgen05 / TMEM / TMA implicit-GEMM convolution engine (sm_100a), stride 1, k in {1,3}.
+// tcgen05 / TMEM / TMA implicit-GEMM convolution engine (sm_100a): every 3x3 / 1x1 conv (stride 1 and 2), every
+// nn.Linear, the 7x7 stem and the two heads of the OmniFusion network.
 //
-// GEMM view: M = output pixels (CTA tile = 128 pixels = a TMA box of BNI images x BH rows x BW
-// columns), N = cout (CTA tile BN <= 128), K = taps x channels.  For every filter tap the
-// producer issues one 4-D TMA load of the *shifted* activation box (out-of-bounds rows/columns
-// are zero-filled by TMA = the conv padding) and one 2-D load of the matching K-slice of the
-// OHWI weights; both land in shared memory in the K-major 128B/64B-swizzled layout that
-// tcgen05.mma consumes directly.  One elected thread issues the MMAs, accumulating in TMEM;
-// four epilogue warps read TMEM back (tcgen05.ld), apply scale/shift/residual/activation and
-// store.  Pipeline: NST-stage smem ring with full/empty mbarriers; MMA completion is
-// signalled with tcgen05.commit.
+// GEMM view: M = output pixels (CTA tile = 128 pixels = a TMA box of BNI images x BH rows x BW columns), N = cout
+// (CTA tile BN <= 128), K = taps x channels.  For every filter tap the producer warp issues one 4-D TMA load of
+// the *shifted* activation box (out-of-bounds rows/columns are zero-filled by TMA = the conv padding; traversal
+// strides = the conv stride) and one load of the matching K-slice of the OHWI weights; both land in shared memory
+// in the K-major 128B/64B-swizzled layout that tcgen05.mma consumes directly.  The MMA warp accumulates in TMEM
+// (two accumulator buffers: tile i+1 runs while the epilogue drains tile i); epilogue warps read TMEM back
+// (tcgen05.ld), apply scale/shift/residual/activation, convert to the storage format and store through staged
+// bulk tensor stores.  Persistent CTAs, NST-stage smem ring with full/empty mbarriers, tcgen05.commit frees stages.
+// The producer and MMA warps run warp-uniformly and predicate only the instruction issue on elect.sync.
 //
-// Two operand modes:
-//   TF32   : float32 tensors, one kind::tf32 MMA per K-step (TF32 accuracy).
-//   F16X3  : split-half planes (value = hi + lo, both fp16), three kind::f16 MMAs per K-step
-//            (hi*hi + lo*hi + hi*lo) accumulated in fp32 - ~22-bit operands, fp32-level result.
+// Operand modes:
+//   TF32   : float32 tensors, one kind::tf32 MMA per K-step (TF32 accuracy; cross-check only).
+//   F16X3  : split-half planes (value = hi + lo, both fp16): hi * [Whi; Wlo] as ONE MMA against the stacked weight
+//            tile plus lo * Whi, accumulated in fp32 - ~22-bit operands, fp32-level result.
+// Variants (template flags, see TcCfg): KHR kh-reuse boxes for narrow 3x3 layers, BRES resident filter, UPS rolling
+// rows (1: fused 2x upsample with interpolating producer warps, 2: TMA-fed rows + heads epilogue), CTA2
+// cta_group::2 CTA pairs for the 128-wide tiles; split-K for the token linears (TcParams::ksplit).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
