@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OFB_VERSION 100
+#define OFB_VERSION 101
 
 typedef struct ofb_handle ofb_handle;
 
