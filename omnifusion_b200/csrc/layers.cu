@@ -108,14 +108,15 @@ template <bool SPLIT>
 __global__ void maxpool_kernel(const void* __restrict__ in, int n, int h, int w, int c4,
                                void* __restrict__ out) {
   int oh_n = h / 2, ow_n = w / 2;
-  size_t total = (size_t)n * oh_n * ow_n * c4;
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  // 32-bit index arithmetic (the host checks total < 2^31): 64-bit div/mod costs ~100 instructions each
+  const uint32_t total = (uint32_t)n * oh_n * ow_n * c4;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  int c = (int)(i % c4);
-  size_t r = i / c4;
-  int ow = (int)(r % ow_n); r /= ow_n;
-  int oh = (int)(r % oh_n);
-  int img = (int)(r / oh_n);
+  const int c = (int)(i % (uint32_t)c4);
+  uint32_t r = i / (uint32_t)c4;
+  const int ow = (int)(r % (uint32_t)ow_n); r /= (uint32_t)ow_n;
+  const int oh = (int)(r % (uint32_t)oh_n);
+  const int img = (int)(r / (uint32_t)oh_n);
   float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
   const size_t in_plane = (size_t)n * h * w * c4 * 4;
 #pragma unroll
@@ -130,7 +131,7 @@ __global__ void maxpool_kernel(const void* __restrict__ in, int n, int h, int w,
       m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
     }
   }
-  act_st4<SPLIT>(out, i * 4, total * 4, m);
+  act_st4<SPLIT>(out, (size_t)i * 4, (size_t)total * 4, m);
 }
 
 // ------------------------------------------------------------------- upsample
@@ -143,14 +144,14 @@ __global__ void maxpool_kernel(const void* __restrict__ in, int n, int h, int w,
 template <bool SPLIT>
 __global__ void upsample2x_kernel(const void* __restrict__ in, const float* __restrict__ img_bias,
                                   int n, int h, int w, int c8, void* __restrict__ out) {
-  size_t total = (size_t)n * h * w * c8;
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const uint32_t total = (uint32_t)n * h * w * c8;       // 32-bit index arithmetic, see maxpool_kernel
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  int c = (int)(i % c8);
-  size_t r = i / c8;
-  int x = (int)(r % w); r /= w;
-  int y = (int)(r % h);
-  int img = (int)(r / h);
+  const int c = (int)(i % (uint32_t)c8);
+  uint32_t r = i / (uint32_t)c8;
+  const int x = (int)(r % (uint32_t)w); r /= (uint32_t)w;
+  const int y = (int)(r % (uint32_t)h);
+  const int img = (int)(r / (uint32_t)h);
   const size_t in_plane = (size_t)n * h * w * c8 * 8, out_plane = in_plane * 4;
   const int ys[3] = {max(y - 1, 0), y, min(y + 1, h - 1)};
   const int xs[3] = {max(x - 1, 0), x, min(x + 1, w - 1)};
@@ -219,8 +220,9 @@ point_embed_kernel(const float* __restrict__ pts, int N, int cin, int p,
     if (!live) i = total - 1;
     const int g = (int)(i & 15);
     const size_t pix = i >> 4;
-    const int xy = (int)(pix % (p * p));
-    const int img = (int)(pix / (p * p));
+    const uint32_t pp = (uint32_t)(p * p), pix32 = (uint32_t)pix;     // 32-bit div/mod (host checks the range)
+    const int xy = (int)(pix32 % pp);
+    const int img = (int)(pix32 / pp);
     const int n = img % N;
     const float dsc = depth ? __ldg(&depth[pix]) : 1.f;
     float a = 0.f;
@@ -569,6 +571,7 @@ extern "C" int ofb_stem_f32(const float* in, int n, int h, int w, const float* w
 extern "C" int ofb_maxpool3x3s2_f32(const void* in, int n, int h, int w, int c, void* out, int fmt, void* stream) {
   OFB_CHECK(in && out && c % 4 == 0 && h % 2 == 0 && w % 2 == 0 && OFB_FMT_OK(fmt), "maxpool: bad arguments");
   size_t total = (size_t)n * (h / 2) * (w / 2) * (c / 4);
+  OFB_CHECK(total < (1ull << 31), "maxpool: %zu output vectors exceed the 32-bit index range (process fewer images per call)", total);
   if (fmt) maxpool_kernel<true><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, n, h, w, c / 4, out);
   else maxpool_kernel<false><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, n, h, w, c / 4, out);
   OFB_LAUNCH_CHECK();
@@ -579,6 +582,7 @@ extern "C" int ofb_upsample2x_f32(const void* in, const float* img_bias, int n, 
                                   void* out, int fmt, void* stream) {
   OFB_CHECK(in && out && c % 8 == 0 && OFB_FMT_OK(fmt), "upsample2x: bad arguments");
   size_t total = (size_t)n * h * w * (c / 8);
+  OFB_CHECK(total < (1ull << 31), "upsample2x: %zu input vectors exceed the 32-bit index range (process fewer images per call)", total);
   if (fmt) upsample2x_kernel<true><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, img_bias, n, h, w, c / 8, out);
   else upsample2x_kernel<false><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, img_bias, n, h, w, c / 8, out);
   OFB_LAUNCH_CHECK();
@@ -591,6 +595,7 @@ extern "C" int ofb_point_embed_f32(const float* pts, int N, int cin, int p, cons
                                    void* stream) {
   OFB_CHECK(pts && w1 && s1 && t1 && w2 && s2 && t2 && out && OFB_FMT_OK(fmt), "point_embed: bad arguments");
   OFB_CHECK(cin >= 1 && cin <= 5, "point_embed: cin must be <= 5 (got %d)", cin);
+  OFB_CHECK((size_t)imgs * p * p < (1ull << 31), "point_embed: too many pixels for the 32-bit index range");
   size_t total = (size_t)imgs * p * p * 16;
   const int blocks = (int)(cdiv(total, 256) < 148 * 8 ? cdiv(total, 256) : 148 * 8);
   if (fmt) point_embed_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(pts, N, cin, p, depth, imgs, w1, s1, t1, w2, s2, t2, base, out);
