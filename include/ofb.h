@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OFB_VERSION 101
+#define OFB_VERSION 102
 
 typedef struct ofb_handle ofb_handle;
 
@@ -207,6 +207,24 @@ int ofb_heads_f32(const void* x, int imgs, int h, int w,
  * order untouched): src (B,H,W,C) uint8 device -> dst (B,C,H,W) float32, bit-identical to the numpy expression. */
 int ofb_u8hwc_to_f32chw(const uint8_t* src, int B, int H, int W, int C, float* dst, void* stream);
 
+/* cv2.resize(img, (W/factor, H/factor), interpolation=cv2.INTER_AREA) of the decoded uint8 panorama for integer
+ * scale factors (dataset_loader_stanford.py:92-96): src (B,H,W,C) -> dst (B,H/factor,W/factor,C), both uint8 device;
+ * bit-identical to OpenCV (mean of the factor x factor block, rounded to nearest even). */
+int ofb_area_resize_u8(const uint8_t* src, int B, int H, int W, int C, int factor, uint8_t* dst, void* stream);
+
+/* Lower median (torch.median) of x[mask != 0] by four radix-select passes; no host synchronisation.  state: device
+ * scratch of >= 1027 uint32 (zeroed by the call); out: 1 float (NaN when the mask is empty).  x 16-byte aligned. */
+int ofb_masked_median_f32(const float* x, const uint8_t* mask, size_t n, void* state, float* out, void* stream);
+
+/* Median scaling of test.py:161-162: out3 = [median(gt[mask]) / median(pred[mask]), median(gt), median(pred)]. */
+int ofb_median_scale_f32(const float* pred, const float* gt, const uint8_t* mask, size_t n, void* state,
+                         float* out3, void* stream);
+
+/* Point cloud of test.py:205-218: pts (B,He*We,3) = rays (He*We,3) * depth (B,1,He,We); depths above max_depth are
+ * zeroed first when max_depth > 0 (test.py:208).  rays: util.py:159-174 coords2uv / uv2xyz, built on the host. */
+int ofb_depth_to_points_f32(const float* depth, const float* rays, int B, int He, int We, float max_depth,
+                            float* pts, void* stream);
+
 /* Abs-Rel partial sums, metrics.py:7-9: out[0] += sum(|p*scale-g|/g over mask), out[1] += count.
  * `out` must be zeroed by the caller. */
 int ofb_absrel_partial(const float* pred, const float* gt, const uint8_t* mask, size_t n,
@@ -217,6 +235,10 @@ int ofb_absrel_partial(const float* pred, const float* gt, const uint8_t* mask, 
  *  n(delta<1.25^2), n(delta<1.25^3), n] over mask, with p = pred*scale.  `out` zeroed by the caller. */
 int ofb_depth_metrics_partial(const float* pred, const float* gt, const uint8_t* mask, size_t n,
                               float scale, double* out, void* stream);
+/* Same with the scale read from device memory (*scale_dev, e.g. out3[0] of ofb_median_scale_f32): the whole
+ * evaluation step stays on the stream without a device-to-host round trip. */
+int ofb_depth_metrics_partial_ds(const float* pred, const float* gt, const uint8_t* mask, size_t n,
+                                 const float* scale_dev, double* out, void* stream);
 
 /* ------------------------------------------------------------------- engine */
 
@@ -247,11 +269,16 @@ int ofb_load_weights(ofb_handle* h, const ofb_tensor_desc* tensors, int count, i
 int ofb_forward_f32(ofb_handle* h, const float* rgb, int B, int iters, int confidence,
                     float* const* out_depth, void* stream);
 
+/* Bumped every time the engine (re)allocates its workspace arena (a forward with more images than any before).  A
+ * CUDA graph captured around ofb_forward_f32 replays launches into the arena it was captured with: compare this value
+ * with the one read at capture time and re-capture when it changed. */
+long long ofb_workspace_generation(ofb_handle* h);
+
 /* Engine knobs (key, value): "engine" conv engine (OFB_ENGINE_*), "chunk" panoramas per internal chunk
  * (0 = auto), "dedup" reuse of the iteration-invariant stem/layer1 across iterations (default 1), "format"
  * activation storage (OFB_FMT_*), "fuse_ups" fold the last decoder upsample into de_conv4_0 (default 1),
  * "heads_tc" heads on the tensor pipe (default 1), "lanes" 2 = two concurrent half-batches on two streams
- * (default 1), "cta2" / "pdl" / "store128" / "fill_div" / "direct32" tcgen05 launch variants (process-wide);
+ * (default 1), "cta2" / "pdl" / "store128" / "fill_div" / "direct32" / "khr_bw" / "khr_row64" tcgen05 launch variants (per handle);
  * "tc_debug" / "dbg_blocks" switch parts of the pipeline OFF for timing experiments (results are wrong). */
 int ofb_set_option(ofb_handle* h, const char* key, int value);
 
@@ -268,6 +295,11 @@ int64_t ofb_get_activation(ofb_handle* h, const char* name, float* dst, int64_t 
  * number of bytes written and clears the records. */
 int ofb_profile_enable(ofb_handle* h, int on);
 int ofb_profile_report(ofb_handle* h, char* buf, int capacity);
+
+/* Test hook: which instantiation of the tcgen05 conv kernel the calling thread's last ofb_conv_f32 / engine conv
+ * selected: "cta2" (cta_group::2 CTA pairs), "khr" (kh-reuse boxes), "ups" (rolling-row fused upsample), "splitk",
+ * "plain". */
+const char* ofb_last_conv_variant(void);
 
 /* Kernel launches issued by this library on the calling thread since the last reset. */
 int64_t ofb_launch_count(int reset);

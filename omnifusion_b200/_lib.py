@@ -68,6 +68,11 @@ _SIGNATURES = {
     "ofb_u8hwc_to_f32chw": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "ofb_absrel_partial": (_I, [_P, _P, _P, C.c_size_t, C.c_float, _P, _P]),
     "ofb_depth_metrics_partial": (_I, [_P, _P, _P, C.c_size_t, C.c_float, _P, _P]),
+    "ofb_depth_metrics_partial_ds": (_I, [_P, _P, _P, C.c_size_t, _P, _P, _P]),
+    "ofb_area_resize_u8": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "ofb_masked_median_f32": (_I, [_P, _P, C.c_size_t, _P, _P, _P]),
+    "ofb_median_scale_f32": (_I, [_P, _P, _P, C.c_size_t, _P, _P, _P]),
+    "ofb_depth_to_points_f32": (_I, [_P, _P, _I, _I, _I, C.c_float, _P, _P]),
     "ofb_create": (_I, [_I, C.POINTER(_P)]),
     "ofb_destroy": (_I, [_P]),
     "ofb_set_geometry": (_I, [_P, C.POINTER(Geometry)]),
@@ -76,6 +81,8 @@ _SIGNATURES = {
     "ofb_set_option": (_I, [_P, C.c_char_p, _I]),
     "ofb_get_activation": (C.c_int64, [_P, C.c_char_p, _P, C.c_int64, C.POINTER(_I * 4), _P]),
     "ofb_launch_count": (C.c_int64, [_I]),
+    "ofb_workspace_generation": (C.c_longlong, [_P]),
+    "ofb_last_conv_variant": (C.c_char_p, []),
     "ofb_debug_stamps": (_I, [_P]),
     "ofb_profile_enable": (_I, [_P, _I]),
     "ofb_profile_report": (_I, [_P, C.c_char_p, _I]),

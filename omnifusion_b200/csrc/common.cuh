@@ -42,6 +42,29 @@ void count_launch(int n = 1);
     }                                                                            \
   } while (0)
 
+// tcgen05 launch variants (csrc/conv_tc.cu), owned by an engine handle: "cta2" / "pdl" / "store128" / "fill_div" /
+// "direct32" / "khr_bw" / "khr_row64" of ofb_set_option, plus sm_share (two-lane forwards) and the timing-experiment
+// switches (dbg).
+struct TcOptions {
+  bool pdl = true;        // programmatic dependent launch
+  bool store128 = true;   // bulk-tensor-store epilogue also for the 128-wide tiles
+  bool cta2 = true;       // cta_group::2 CTA pairs for the 128-wide split-half tiles
+  bool direct32 = false;  // BN = 32 split-half tiles store straight from registers
+  bool khr_row64 = false; // 64-byte K rows for the Cout = 64 kh-reuse layers
+  int fill_div = 2;       // shrink the N tile while fewer than num_sms / fill_div tiles exist
+  int khr_bw = 16;        // tile width of the kh-reuse kernels (16 or 32)
+  int sm_share = 1;       // persistent grids use num_sms / sm_share CTAs
+  int dbg = 0;            // TcParams::dbg (timing experiments; results are wrong)
+};
+const TcOptions& tc_opts();
+struct TcOptScope {
+  const TcOptions* prev;
+  explicit TcOptScope(const TcOptions* o);
+  ~TcOptScope();
+  TcOptScope(const TcOptScope&) = delete;
+  TcOptScope& operator=(const TcOptScope&) = delete;
+};
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }

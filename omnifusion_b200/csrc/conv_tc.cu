@@ -940,57 +940,60 @@ bool conv_tc_supported(const ofb_conv_desc* d) {
   return true;
 }
 
-static bool g_pdl = true;      // programmatic dependent launch for the tensor-core kernels
-static bool g_store128 = true;  // bulk-tensor-store epilogue also for the 128-wide tiles
-static bool g_cta2 = true;      // cta_group::2 CTA pairs for the 128-wide split-half tiles
-void conv_tc_set_cta2(bool on) { g_cta2 = on; }
-static bool g_direct32 = false;  // BN = 32 split-half tiles store straight from registers instead of bulk tensor stores
-void conv_tc_set_direct32(bool on) { g_direct32 = on; }
-static int g_fill_div = 2;      // shrink the N tile while fewer than num_sms / g_fill_div tiles exist
-void conv_tc_set_fill_div(int v) { g_fill_div = v > 0 ? v : 2; }
-static bool g_khr_row64 = false;// 64-byte K rows for the Cout = 64 kh-reuse layers (4 ring stages instead of 2)
-void conv_tc_set_khr_row64(bool on) { g_khr_row64 = on; }
-static int g_khr_bw = 16;       // tile width of the kh-reuse kernels (16 or 32)
-void conv_tc_set_khr_bw(int v) { g_khr_bw = v == 32 ? 32 : 16; }
-static int g_sm_share = 1;      // persistent grids use num_sms / g_sm_share CTAs (two concurrent forward lanes share the GPU)
-void conv_tc_set_sm_share(int div) { g_sm_share = div >= 1 ? div : 1; }
-static int g_dbg = 0;           // TcParams::dbg (timing experiments)
+// Launch variants are per engine handle (TcOptions, common.cuh): the engine installs its handle's options for the
+// duration of a forward (TcOptScope); operator calls made directly through the C ABI use the defaults.
+static thread_local const TcOptions* t_opts = nullptr;
+static const TcOptions k_default_opts{};
+const TcOptions& tc_opts() { return t_opts ? *t_opts : k_default_opts; }
+TcOptScope::TcOptScope(const TcOptions* o) : prev(t_opts) { t_opts = o; }
+TcOptScope::~TcOptScope() { t_opts = prev; }
+
 static long long* g_dbg_buf = nullptr;
-void conv_tc_set_debug(int v) { g_dbg = v; }
 long long* conv_tc_debug_buffer() {
   if (!g_dbg_buf) cudaMalloc(&g_dbg_buf, 512 * 8 * sizeof(long long));
   return g_dbg_buf;
 }
-void conv_tc_set_pdl(bool on) { g_pdl = on; }
-void conv_tc_set_store128(bool on) { g_store128 = on; }
 
+// which instantiation the calling thread's last conv_tc() selected (tests assert that a shape really reaches the
+// kernel they mean to cover): ofb_last_conv_variant()
+static thread_local char t_variant[64] = "";
+const char* conv_tc_last_variant() { return t_variant; }
+
+// per-device state: SM count, and whether a kernel instantiation has had its dynamic-shared-memory opt-in applied
+// on that device (function attributes are per device)
+constexpr int kMaxDevices = 64;
+static int cur_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
 static int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[kMaxDevices] = {0};
+  const int dev = cur_device();
+  if (!n[dev]) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
   }
-  return n;
+  return n[dev];
 }
 
 template <int BN, int MODE, int ROW_BYTES, bool TMA_STORE, bool KHR, bool BRES = false, int UPS = 0, bool CTA2 = false>
 static int launch_tc(const TcMaps& maps, const TcParams& p, cudaStream_t s) {
   using Cfg = TcCfg<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES, UPS, CTA2>;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[kMaxDevices] = {false};
+  const int dev = cur_device();
+  if (!attr[dev]) {
     OFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MODE, ROW_BYTES, TMA_STORE, KHR, BRES, UPS, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    attr = true;
+    attr[dev] = true;
   }
   // persistent: one CTA per SM (CTA2: one CTA pair per TPC, total_tiles counts pair-tiles)
-  const int units = (CTA2 ? num_sms() / 2 : num_sms()) / g_sm_share;
+  const int units = (CTA2 ? num_sms() / 2 : num_sms()) / tc_opts().sm_share;
   int grid = (p.total_tiles < units ? p.total_tiles : units) * (CTA2 ? 2 : 1);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;
   cudaLaunchAttribute attrs[2];
   int na = 0;
-  if (g_pdl) {
+  if (tc_opts().pdl) {
     attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attrs[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
@@ -1010,19 +1013,19 @@ template <int MODE, int ROW_BYTES>
 static int launch_bn(int bn, bool khr, bool cta2, const TcMaps& maps, const TcParams& p, cudaStream_t s) {
   if (bn == 128 && cta2) {
     if (MODE == MODE_F16X3 && ROW_BYTES == 128) {
-      if (g_store128) return launch_tc<128, MODE_F16X3, 128, true, false, false, false, true>(maps, p, s);
+      if (tc_opts().store128) return launch_tc<128, MODE_F16X3, 128, true, false, false, false, true>(maps, p, s);
       return launch_tc<128, MODE_F16X3, 128, false, false, false, false, true>(maps, p, s);
     }
     OFB_CHECK(false, "conv_tc: CTA pairs need split-half operands with 128-byte rows");
   }
   if (bn == 128) {
-    if (g_store128) return launch_tc<128, MODE, ROW_BYTES, true, false>(maps, p, s);
+    if (tc_opts().store128) return launch_tc<128, MODE, ROW_BYTES, true, false>(maps, p, s);
     return launch_tc<128, MODE, ROW_BYTES, false, false>(maps, p, s);
   }
   if (MODE == MODE_F16X3 && khr) {
     if (p.ups_src) {
       if (ROW_BYTES == 64) {
-        if (g_direct32) return launch_tc<32, MODE_F16X3, 64, false, true, true, true>(maps, p, s);
+        if (tc_opts().direct32) return launch_tc<32, MODE_F16X3, 64, false, true, true, true>(maps, p, s);
         return launch_tc<32, MODE_F16X3, 64, true, true, true, true>(maps, p, s);
       }
       OFB_CHECK(false, "conv_tc: fused upsample needs 64-byte rows");
@@ -1030,10 +1033,10 @@ static int launch_bn(int bn, bool khr, bool cta2, const TcMaps& maps, const TcPa
     if (bn == 64) return launch_tc<64, MODE_F16X3, ROW_BYTES, true, true>(maps, p, s);
     // 32 -> 32 channels: the whole filter stays resident in shared memory
     if (ROW_BYTES == 64 && p.c0 + p.c1 == 32 && p.cout == 32) {
-      if (g_direct32) return launch_tc<32, MODE_F16X3, 64, false, true, true>(maps, p, s);
+      if (tc_opts().direct32) return launch_tc<32, MODE_F16X3, 64, false, true, true>(maps, p, s);
       return launch_tc<32, MODE_F16X3, 64, true, true, true>(maps, p, s);
     }
-    if (g_direct32) return launch_tc<32, MODE_F16X3, ROW_BYTES, false, true>(maps, p, s);
+    if (tc_opts().direct32) return launch_tc<32, MODE_F16X3, ROW_BYTES, false, true>(maps, p, s);
     return launch_tc<32, MODE_F16X3, ROW_BYTES, true, true>(maps, p, s);
   }
   if (bn == 64) return launch_tc<64, MODE, ROW_BYTES, true, false>(maps, p, s);
@@ -1050,7 +1053,7 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
   if ((d->c0 * es) % 128 || (c1 * es) % 128) row_bytes = 64;
   // experiment (option khr_row64, off): kh-reuse layers with 64 output channels have 96 KB stages = a 2-stage
   // ring; 64-byte rows give 4 stages of half the size, but measured 3-10 % slower (TMA on 64-byte rows)
-  if (g_khr_row64 && split && d->k == 3 && d->stride == 1 && d->cout == 64 && d->w >= 16 && d->h >= 8) row_bytes = 64;
+  if (tc_opts().khr_row64 && split && d->k == 3 && d->stride == 1 && d->cout == 64 && d->w >= 16 && d->h >= 8) row_bytes = 64;
   const int kc = row_bytes / es;
   OFB_CHECK(d->c0 % kc == 0 && c1 % kc == 0, "conv_tc: channel counts (%d,%d) not divisible by %d", d->c0, c1, kc);
   TcParams p{};
@@ -1063,9 +1066,9 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
   p.scale = d->scale; p.shift = d->shift; p.wscale = split ? d->wgt_unscale : 1.f;
   p.residual = d->residual; p.out = d->out; p.act = d->act;
   p.plane = (long long)d->n * oh * ow * d->cout;
-  p.dbg = g_dbg;
-  p.dbg_buf = (g_dbg & 16) ? conv_tc_debug_buffer() : nullptr;
-  p.group64 = g_cta2 ? 1 : 0;
+  p.dbg = tc_opts().dbg;
+  p.dbg_buf = (tc_opts().dbg & 16) ? conv_tc_debug_buffer() : nullptr;
+  p.group64 = tc_opts().cta2 ? 1 : 0;
   const int S = d->ksplit > 1 ? d->ksplit : 1;
   OFB_CHECK(S == 1 || (split && d->k == 1 && d->stride == 1 && !d->ups2x && d->partial && (cin / kc) % S == 0),
             "conv_tc: split-K needs a split-half 1x1 layer, a partial buffer and %d K-chunks divisible by %d", cin / kc, S);
@@ -1078,18 +1081,18 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
   // widest N tile unless that leaves most SMs without a tile
   int bn = d->cout >= 128 ? 128 : d->cout;
   // (only for really small problems such as the token linears: narrow tiles re-read the A tile more often)
-  while (!khr && bn > 32 && (long long)groups * p.tiles_x * p.tiles_y * (d->cout / bn) * S < num_sms() / g_fill_div) bn >>= 1;
+  while (!khr && bn > 32 && (long long)groups * p.tiles_x * p.tiles_y * (d->cout / bn) * S < num_sms() / tc_opts().fill_div) bn >>= 1;
   int groups_k = groups;
   if (khr) {
     // 16 x 8 pixel tiles: the halo box is 16 x 10 = 1.25 x the tile (32 x 4 tiles: 32 x 6 = 1.5 x)
-    p.BW = ow < g_khr_bw ? ow : g_khr_bw; p.BH = 128 / p.BW; p.BNI = 1;
+    p.BW = ow < tc_opts().khr_bw ? ow : tc_opts().khr_bw; p.BH = 128 / p.BW; p.BNI = 1;
     p.tiles_x = ow / p.BW; p.tiles_y = oh / p.BH;
     groups_k = d->n;
   }
   p.tiles_n = d->cout / bn;
   p.total_tiles = groups_k * p.tiles_x * p.tiles_y * p.tiles_n * S;
   // CTA pairs (cta_group::2): two adjacent M tiles share one weight tile.  Decided from the layer shape only.
-  const bool cta2 = g_cta2 && split && bn == 128 && !khr && row_bytes == 128 && S == 1;
+  const bool cta2 = tc_opts().cta2 && split && bn == 128 && !khr && row_bytes == 128 && S == 1;
   if (cta2) p.total_tiles = ((groups_k * p.tiles_x * p.tiles_y + 1) / 2) * p.tiles_n;
 
   TcMaps maps;
@@ -1131,7 +1134,7 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
       if (make_map(&maps.b[pl], split, 2, a, dims, box, row_bytes)) return -1;
     }
   }
-  if (bn < 128 || g_store128) {      // output tensor maps for the bulk-store epilogue: box = 32 columns x the pixel box
+  if (bn < 128 || tc_opts().store128) {      // output tensor maps for the bulk-store epilogue: box = 32 columns x the pixel box
     cuuint64_t dims[4] = {(cuuint64_t)d->cout, (cuuint64_t)ow, (cuuint64_t)oh, (cuuint64_t)d->n};
     // one store per epilogue warp: 32 consecutive pixels of the tile
     const int sbw = p.BW < 32 ? p.BW : 32, sbh = 32 / sbw < p.BH ? 32 / sbw : p.BH, sbn = 32 / (sbw * sbh);
@@ -1141,6 +1144,7 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
       if (make_map(&maps.o[pl], split, 4, a, dims, box, 32 * es)) return -1;
     }
   }
+  snprintf(t_variant, sizeof(t_variant), "%s", cta2 ? "cta2" : (d->ups2x ? "ups" : (khr ? "khr" : (S > 1 ? "splitk" : "plain"))));
   if (split) {
     if (row_bytes == 128) return launch_bn<MODE_F16X3, 128>(bn, khr, cta2, maps, p, s);
     return launch_bn<MODE_F16X3, 64>(bn, khr, false, maps, p, s);
@@ -1167,8 +1171,8 @@ int conv_tc_heads(const void* x, int n, int h, int w, const void* wgt_split, flo
   p.tiles_n = 1; p.total_tiles = n * h;
   p.ksplit = 1;
   p.heads_pred = pred_out; p.heads_conf = confidence ? conf_out : nullptr; p.heads_bp = b_pred; p.heads_bc = b_conf;
-  p.dbg = g_dbg;
-  p.dbg_buf = (g_dbg & 16) ? conv_tc_debug_buffer() : nullptr;
+  p.dbg = tc_opts().dbg;
+  p.dbg_buf = (tc_opts().dbg & 16) ? conv_tc_debug_buffer() : nullptr;
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
   const size_t plane = (size_t)n * h * w * 32;               // halves per plane

@@ -32,18 +32,10 @@ int stem_tc(const void* patches, int n, int h, int w, const void* wgt_split, flo
             const float* shift, void* out, cudaStream_t s);
 int conv_tc(const ofb_conv_desc* d, cudaStream_t s);
 bool conv_tc_supported(const ofb_conv_desc* d);
-void conv_tc_set_pdl(bool on);
-void conv_tc_set_store128(bool on);
-void conv_tc_set_cta2(bool on);
-void conv_tc_set_debug(int v);
-void conv_tc_set_khr_bw(int v);
-void conv_tc_set_khr_row64(bool on);
-void conv_tc_set_sm_share(int div);
 int conv_tc_heads(const void* x, int n, int h, int w, const void* wgt_split, float wgt_unscale, float b_pred,
                   float b_conf, int confidence, float* pred_out, float* conf_out, cudaStream_t s);
-void conv_tc_set_fill_div(int v);
 long long* conv_tc_debug_buffer();
-void conv_tc_set_direct32(bool on);
+const char* conv_tc_last_variant();
 
 int conv_dispatch(const ofb_conv_desc* d, cudaStream_t s) {
   OFB_CHECK(d && d->in0 && (d->wgt || d->wgt_split) && d->out, "conv: null pointer");
@@ -97,10 +89,13 @@ struct ofb_handle {
   // concurrently on two streams (each with its own workspace) so that the latency-bound token path of one half
   // overlaps the convolutions of the other.  Measured on B200: 1561 vs 1898 panoramas/s at 8 per step, 1945 vs
   // 2136 at 32 - the halves' persistent kernels compete for the L2 fabric and for SMs instead of interleaving.
-  struct Lane { float* ws = nullptr; size_t ws_floats = 0; bool patches_zeroed = false; int patches_imgs = 0; };
+  struct Lane { float* ws = nullptr; size_t ws_floats = 0; };
   Lane lane[2];
   int cur = 0;                     // lane whose launches are being enqueued (host-side state)
   int lanes = 1;
+  TcOptions tc;                    // tcgen05 launch variants of THIS handle (installed for the duration of a forward)
+  long long ws_generation = 0;     // bumped whenever a workspace arena is (re)allocated: captured CUDA graphs that
+                                   // replay launches into the old arena must be dropped (ofb_workspace_generation)
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int engine = OFB_ENGINE_AUTO, chunk = 0, dedup = 1;
@@ -112,6 +107,11 @@ struct ofb_handle {
   struct Rec { std::string name; double flops, bytes; cudaEvent_t e0, e1; };
   std::vector<Rec> recs;
 };
+
+static void drop_profile_records(ofb_handle* h) {
+  for (auto& r : h->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  h->recs.clear();
+}
 
 namespace ofb {
 
@@ -163,8 +163,8 @@ static int pack_conv(ofb_handle* h, const TMap& m, const std::string& wname, Con
   cw->unscale = ldexpf(1.f, -e);
   OFB_CUDA(cudaMalloc(&cw->ws, p.size() * 4));
   h->owned.push_back(cw->ws);
+  // (legacy default stream: ordered after the synchronous upload above; load_all synchronises once at the end)
   if (ofb_split_f16(cw->w, p.size(), ldexpf(1.f, e), cw->ws, nullptr)) return -1;
-  OFB_CUDA(cudaStreamSynchronize(nullptr));
   return 0;
 }
 
@@ -257,7 +257,6 @@ static int load_all(ofb_handle* h, const TMap& m, bool single) {
     OFB_CUDA(cudaMalloc(&stem.ws, q.size() * 4));
     h->owned.push_back(stem.ws);
     if (ofb_split_f16(tmp, q.size(), ldexpf(1.f, ex), stem.ws, nullptr)) return -1;
-    OFB_CUDA(cudaStreamSynchronize(nullptr));
   }
   if (pack_bn(h, m, "bn1", 64, 1e-5f, &stem.scale, &stem.shift)) return -1;
   h->conv["stem"] = stem;
@@ -386,7 +385,7 @@ static int ensure_workspace(ofb_handle* h, int imgs, int P, Buffers* b) {
     h->lane[h->cur].ws = nullptr; h->lane[h->cur].ws_floats = 0;
     OFB_CUDA(cudaMalloc(&h->lane[h->cur].ws, need * sizeof(float)));
     h->lane[h->cur].ws_floats = need;
-    h->lane[h->cur].patches_zeroed = false;
+    ++h->ws_generation;
   }
   plan_buffers(h, imgs, P, b);
   return 0;
@@ -511,10 +510,17 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
       // equi2pers(rgb, P) -> patches; stem; pool; layer1 (spherical_model_iterative.py:315,322-324)
       const ConvW& st = h->conv["stem"];
       const bool stem_tc_path = F == OFB_FMT_SPLIT16 && h->engine != OFB_ENGINE_SIMT;
-      if (stem_tc_path && (!h->lane[h->cur].patches_zeroed || h->lane[h->cur].patches_imgs != imgs)) {
-        // the stem layout's row pads must read as zero; the interior is rewritten by every forward
-        OFB_CUDA(cudaMemsetAsync(b.patches, 0, (size_t)imgs * P * (P + 8) * 4 * sizeof(float), s));
-        h->lane[h->cur].patches_zeroed = true; h->lane[h->cur].patches_imgs = imgs;
+      if (stem_tc_path) {
+        // The stem layout's 4-pixel row pads must read as zero and e2p never writes them.  They are re-zeroed by
+        // EVERY forward, inside the stream-ordered (and therefore graph-captured) region: the arena is re-planned
+        // per batch size, so another forward may have put live data where this one's pads are.  The right pad of
+        // row r and the left pad of row r+1 are one contiguous 64-byte span (rows of both planes are back to
+        // back), so the pads are one strided 2-D memset plus the first and the last 32 bytes.
+        const size_t pitch = (size_t)(P + 8) * 4 * sizeof(__half), rows = (size_t)2 * imgs * P;
+        char* pp = reinterpret_cast<char*>(b.patches);
+        OFB_CUDA(cudaMemsetAsync(pp, 0, 32, s));
+        OFB_CUDA(cudaMemset2DAsync(pp + pitch - 32, pitch, 0, 64, rows - 1, s));
+        OFB_CUDA(cudaMemsetAsync(pp + rows * pitch - 32, 0, 32, s));
       }
       { Prof pr(h, s, "e2p_rgb", 0.0, 4.0*((double)Bc*3*He*We + (double)imgs*P*P*4));
       if (ofb_equi2pers_f32(rgb, Bc, 3, He, We, g.grid_hi, N, P, P, b.patches,
@@ -696,6 +702,7 @@ extern "C" int ofb_destroy(ofb_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   free_weights(h);
+  drop_profile_records(h);
   for (int l = 0; l < 2; ++l)
     if (h->lane[l].ws) cudaFree(h->lane[l].ws);
   if (h->aux) cudaStreamDestroy(h->aux);
@@ -727,13 +734,13 @@ extern "C" int ofb_load_weights(ofb_handle* h, const ofb_tensor_desc* tensors, i
   }
   h->single = single_stage != 0;
   if (load_all(h, m, h->single)) { free_weights(h); return -1; }
+  OFB_CUDA(cudaStreamSynchronize(nullptr));      // all split-half conversions of the checkpoint
   h->has_weights = true;
   return 0;
 }
 
 extern "C" int ofb_set_option(ofb_handle* h, const char* key, int value) {
   OFB_CHECK(h && key, "set_option: null pointer");
-  h->lane[0].patches_zeroed = h->lane[1].patches_zeroed = false;
   if (!strcmp(key, "engine")) h->engine = value;
   else if (!strcmp(key, "lanes")) h->lanes = value >= 2 ? 2 : 1;
   else if (!strcmp(key, "chunk")) h->chunk = value;
@@ -741,15 +748,15 @@ extern "C" int ofb_set_option(ofb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "fuse_ups")) h->fuse_ups = value;
   else if (!strcmp(key, "heads_tc")) h->heads_tc = value;
   else if (!strcmp(key, "splitk")) h->splitk = value == 2 || value == 4 ? value : 1;
-  else if (!strcmp(key, "khr_row64")) conv_tc_set_khr_row64(value != 0);   // process-wide
-  else if (!strcmp(key, "khr_bw")) conv_tc_set_khr_bw(value);            // process-wide: tile width of the kh-reuse kernels
+  else if (!strcmp(key, "khr_row64")) h->tc.khr_row64 = value != 0;
+  else if (!strcmp(key, "khr_bw")) h->tc.khr_bw = value == 32 ? 32 : 16;    // tile width of the kh-reuse kernels
   else if (!strcmp(key, "dbg_blocks")) h->dbg_blocks = value < 0 ? 0 : (value > 6 ? 6 : value);   // timing experiments (wrong results)
-  else if (!strcmp(key, "pdl")) conv_tc_set_pdl(value != 0);     // process-wide: programmatic dependent launch
-  else if (!strcmp(key, "store128")) conv_tc_set_store128(value != 0);
-  else if (!strcmp(key, "tc_debug")) conv_tc_set_debug(value);         // timing experiments only (wrong results)
-  else if (!strcmp(key, "fill_div")) conv_tc_set_fill_div(value);   // process-wide: N-tile shrink threshold (experiments)
-  else if (!strcmp(key, "direct32")) conv_tc_set_direct32(value != 0);   // process-wide (experiments)
-  else if (!strcmp(key, "cta2")) conv_tc_set_cta2(value != 0);          // process-wide: cta_group::2 CTA pairs
+  else if (!strcmp(key, "pdl")) h->tc.pdl = value != 0;       // programmatic dependent launch
+  else if (!strcmp(key, "store128")) h->tc.store128 = value != 0;
+  else if (!strcmp(key, "tc_debug")) h->tc.dbg = value;               // timing experiments only (wrong results)
+  else if (!strcmp(key, "fill_div")) h->tc.fill_div = value > 0 ? value : 2;   // N-tile shrink threshold (experiments)
+  else if (!strcmp(key, "direct32")) h->tc.direct32 = value != 0;        // (experiments)
+  else if (!strcmp(key, "cta2")) h->tc.cta2 = value != 0;               // cta_group::2 CTA pairs
   else if (!strcmp(key, "format")) {
     OFB_CHECK(value == OFB_FMT_F32 || value == OFB_FMT_SPLIT16, "set_option: format must be 0 (float32) or 1 (split-half)");
     h->fmt = value;
@@ -766,6 +773,7 @@ extern "C" int ofb_forward_f32(ofb_handle* h, const float* rgb, int B, int iters
   OFB_CHECK(B > 0 && iters >= 1, "forward: bad batch/iters");
   OFB_CHECK(!h->single || iters == 1, "forward: the single-stage model runs exactly one iteration");
   OFB_CUDA(cudaSetDevice(h->device));
+  TcOptScope opt_scope(&h->tc);
   for (int i = 0; i < iters; ++i) OFB_CHECK(out_depth[i], "forward: out_depth[%d] is null", i);
   int N = h->geo.n_patch;
   int chunk = h->chunk > 0 ? h->chunk : (576 / N > 0 ? 576 / N : 1);
@@ -801,10 +809,10 @@ extern "C" int ofb_forward_f32(ofb_handle* h, const float* rgb, int B, int iters
   }
   OFB_CUDA(cudaEventRecord(h->ev_fork, s));
   OFB_CUDA(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
-  conv_tc_set_sm_share(2);                 // persistent grids take half of the SMs each: the two lanes run side by side
+  h->tc.sm_share = 2;                      // persistent grids take half of the SMs each: the two lanes run side by side
   int rc = run_lane(0, 0, half, s);
   if (!rc) rc = run_lane(1, half, B, h->aux);
-  conv_tc_set_sm_share(1);
+  h->tc.sm_share = 1;
   h->cur = 0;
   OFB_CUDA(cudaEventRecord(h->ev_join, h->aux));
   OFB_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
@@ -821,8 +829,12 @@ extern "C" int ofb_debug_stamps(long long* host_dst) {
 extern "C" int ofb_profile_enable(ofb_handle* h, int on) {
   OFB_CHECK(h, "profile_enable: null handle");
   h->profile = on != 0;
+  if (!on) drop_profile_records(h);     // records nobody asked a report for
   return 0;
 }
+
+extern "C" long long ofb_workspace_generation(ofb_handle* h) { return h ? h->ws_generation : -1; }
+extern "C" const char* ofb_last_conv_variant(void) { return conv_tc_last_variant(); }
 
 extern "C" int ofb_profile_report(ofb_handle* h, char* buf, int capacity) {
   OFB_CHECK(h && buf && capacity > 0, "profile_report: bad arguments");

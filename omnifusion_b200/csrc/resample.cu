@@ -246,7 +246,8 @@ __global__ void absrel_kernel(const float* __restrict__ pred, const float* __res
 // out = [sum |p-g|/g, sum (p-g)^2/g, sum (p-g)^2, sum (log p - log g)^2, n_log, n(d<1.25), n(d<1.25^2), n(d<1.25^3), n]
 __global__ void depth_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
                                      const uint8_t* __restrict__ mask, size_t n, float scale,
-                                     double* __restrict__ out) {
+                                     const float* __restrict__ scale_dev, double* __restrict__ out) {
+  if (scale_dev) scale = __ldg(scale_dev);
   double acc[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) acc[k] = 0.0;
@@ -298,7 +299,18 @@ extern "C" int ofb_depth_metrics_partial(const float* pred, const float* gt, con
   int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  depth_metrics_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pred, gt, mask, n, scale, out);
+  depth_metrics_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pred, gt, mask, n, scale, nullptr, out);
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ofb_depth_metrics_partial_ds(const float* pred, const float* gt, const uint8_t* mask, size_t n,
+                                            const float* scale_dev, double* out, void* stream) {
+  OFB_CHECK(pred && gt && mask && out && scale_dev, "depth_metrics: null pointer");
+  int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  depth_metrics_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pred, gt, mask, n, 1.f, scale_dev, out);
   OFB_LAUNCH_CHECK();
   return 0;
 }

@@ -61,11 +61,17 @@ class SphericalFusionBase(nn.Module):
         self._keepalive = None
         self._options = {}
         self._graphs = {}
+        self._tensor_list = None       # cached list of checkpoint tensors (rebuilt after load_state_dict / .to())
 
     # ------------------------------------------------------------------ plumbing
     def load_state_dict(self, state_dict, strict=True, **kw):
         """Accepts reference checkpoints, including DataParallel's ``module.`` prefix (test.py:107-110)."""
+        self._tensor_list = None
         return super().load_state_dict(strip_module_prefix(OrderedDict(state_dict)), strict=strict, **kw)
+
+    def _apply(self, fn, *a, **k):
+        self._tensor_list = None        # .to() / .cuda() / .float() may replace parameter storage
+        return super()._apply(fn, *a, **k)
 
     def set_option(self, key, value):
         """Engine knobs: 'engine' (0 auto / 1 CUDA-core / 2 tcgen05), 'chunk', 'dedup'."""
@@ -91,14 +97,19 @@ class SphericalFusionBase(nn.Module):
         _lib.check(_lib.lib().ofb_create(idx, C.byref(h)))
         self._handle, self._handle_device = h, device
         self._weights_key = self._geometry_key = None
+        self._graphs.clear()            # graphs captured with the old handle replay launches into freed memory
         for k, v in self._options.items():
             _lib.check(_lib.lib().ofb_set_option(h, k.encode(), v))
 
     def _ensure_weights(self):
-        tensors = OrderedDict(self.state_dict())
-        key = tuple((k, v.data_ptr(), v._version) for k, v in tensors.items())
+        """Re-packs the checkpoint on the device when any tensor changed.  The change check is one
+        (data_ptr, version) pair per tensor over a cached tensor list - no state_dict() rebuild per forward."""
+        if self._tensor_list is None:
+            self._tensor_list = list(self.state_dict().items())
+        key = tuple((v.data_ptr(), v._version) for _, v in self._tensor_list)
         if key == self._weights_key:
             return
+        tensors = OrderedDict(self._tensor_list)
         host = [(k, v.detach().to("cpu", torch.float32).contiguous()) for k, v in tensors.items()
                 if not k.endswith("num_batches_tracked")]
         descs = (_lib.TensorDesc * len(host))()
@@ -156,7 +167,16 @@ class SphericalFusionBase(nn.Module):
     def forward_graphed(self, rgb, iters=1, confidence=False):
         """Same as forward, replayed from a CUDA graph captured for this (shape, iters, confidence).
         The returned tensors are the graph's static outputs and are overwritten by the next call."""
+        if self.training:
+            raise RuntimeError("omnifusion_b200 implements inference only: call .eval() first")
         key = (tuple(rgb.shape), str(rgb.device), iters, bool(confidence))
+        if self._handle is not None and self._handle_device == rgb.device:
+            # anything that invalidates captured launches drops the graphs: new weights (load_state_dict,
+            # in-place edits), and a workspace arena re-allocated by a larger eager forward in between
+            self._ensure_weights()
+            gen = _lib.lib().ofb_workspace_generation(self._handle)
+            if any(e[3] != gen for e in self._graphs.values()):
+                self._graphs.clear()
         ent = self._graphs.get(key)
         if ent is None:
             static_in = rgb.clone()
@@ -166,12 +186,15 @@ class SphericalFusionBase(nn.Module):
                 for _ in range(2):                       # warm-up: workspace + tables allocated
                     self._run(static_in, iters, confidence)
             torch.cuda.current_stream(rgb.device).wait_stream(side)
+            gen = _lib.lib().ofb_workspace_generation(self._handle)
+            if any(e[3] != gen for e in self._graphs.values()):
+                self._graphs.clear()                     # the warm-up grew the arena under older graphs
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 static_out = self._run(static_in, iters, confidence)
-            ent = (graph, static_in, static_out)
+            ent = (graph, static_in, static_out, gen)
             self._graphs[key] = ent
-        graph, static_in, static_out = ent
+        graph, static_in, static_out, _ = ent
         static_in.copy_(rgb, non_blocking=True)
         graph.replay()
         return static_out

@@ -18,9 +18,8 @@ def init_from_env(backend=None):
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-            # NCCL_DEBUG=VERSION/INFO prints to stdout; callers (bench.py) own stdout for one JSON line
-            if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
-                os.environ["NCCL_DEBUG"] = "WARN"
+            # NCCL_DEBUG is left exactly as the launcher set it (its log is how the rank count is verified);
+            # bench.py keeps its single JSON line clean by diverting fd 1 itself
             dist.init_process_group(backend=backend, rank=rank, world_size=world,
                                     device_id=torch.device("cuda", local))
         else:

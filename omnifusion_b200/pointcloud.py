@@ -1,6 +1,6 @@
 """Point cloud of an ERP depth map, the compute part of the reference's export (test.py:205-218 with
 util.py:159-174 coords2uv / uv2xyz): one unit ray per ERP pixel (host numpy table, the reference's exact op
-order) scaled by the predicted depth on the device.  Writing the PLY file is left to the caller (ply.py)."""
+order) scaled by the predicted depth by a libofb kernel.  Writing the PLY file is left to the caller (ply.py)."""
 import numpy as np
 import torch
 
@@ -25,13 +25,26 @@ def erp_rays(h, w):
     return xyz
 
 
+_rays_cache = {}
+
+
 def depth_to_points(depth, max_depth=None):
-    """depth (B,1,H,W) float32 CUDA -> (B, H*W, 3) points = ray * depth (test.py:216-218).  max_depth: the
-    reference zeroes predictions above 8 m before visualising them (test.py:208)."""
+    """depth (B,1,H,W) float32 CUDA -> (B, H*W, 3) points = ray * depth (test.py:216-218) in one kernel
+    (ofb_depth_to_points_f32).  max_depth: the reference zeroes predictions above 8 m before visualising them
+    (test.py:208)."""
     depth = _lib.require_cuda(depth, "depth")
-    b, _, h, w = depth.shape
-    rays = torch.from_numpy(erp_rays(h, w)).to(depth.device)
-    d = depth.reshape(b, h * w, 1)
-    if max_depth is not None:
-        d = torch.where(d > max_depth, torch.zeros_like(d), d)
-    return rays.unsqueeze(0) * d
+    b, c, h, w = depth.shape
+    if c != 1:
+        raise ValueError(f"depth must be (B,1,H,W), got {tuple(depth.shape)}")
+    key = (h, w, str(depth.device))
+    rays = _rays_cache.get(key)
+    if rays is None:
+        rays = torch.from_numpy(erp_rays(h, w)).to(depth.device)
+        _rays_cache.clear()
+        _rays_cache[key] = rays
+    pts = torch.empty(b, h * w, 3, dtype=torch.float32, device=depth.device)
+    _lib.use_device(depth.device)
+    _lib.check(_lib.lib().ofb_depth_to_points_f32(_lib.ptr(depth), _lib.ptr(rays), b, h, w,
+                                                  float(max_depth) if max_depth is not None else 0.0,
+                                                  _lib.ptr(pts), _lib.stream_of(depth.device)))
+    return pts

@@ -211,3 +211,7 @@ def conv_fmt(in0, wgt, k, stride, pad, in1=None, scale=None, shift=None, residua
         return part, 1.0 / mul
     ck(L().ofb_conv_f32(C.byref(d), _st(in0)))
     return merge16(out, (n, oh, ow, cout)) if out_fmt == 1 else out
+
+
+def last_conv_variant():
+    return L().ofb_last_conv_variant().decode()

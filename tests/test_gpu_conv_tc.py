@@ -42,6 +42,19 @@ TC_CASES = [
     (2, 32, 64, 64, 64, 3, True, 1),      # de_conv2_1-like with residual (kh-reuse, 32x4 tiles)
 ]
 
+# Shapes with >= 74 (= SMs / 2) tiles of 128 output channels: conv_tc keeps BN = 128 and launches the cta_group::2
+# CTA-pair instantiation (conv_tc_kernel<128, F16X3, 128, .., CTA2>), the dominant kernel class of the benchmark
+# step.  (The small TC_CASES above all shrink to BN = 32 / 64 and never reach it.)
+CTA2_CASES = [
+    (150, 8, 256, 0, 256, 3, True, 1),     # layer3 block conv at B=8-like size: 75 M tiles (odd: ragged last pair) x 2 N tiles
+    (600, 4, 512, 0, 512, 3, True, 1),     # layer4: 8 images per tile, 75 M tiles x 4 N tiles, K = 4608
+    (40, 16, 128, 0, 128, 3, False, 1),    # layer2: half-image tiles, 80 M tiles x 1 N tile
+    (150, 8, 256, 256, 256, 3, False, 1),  # de_conv0_0-like with a concat source (two tensor maps), K = 4608
+    (150, 16, 128, 0, 256, 3, False, 1, 2),  # layer3.0.conv1: 3x3 stride 2 (TMA traversal strides) on CTA pairs
+    (150, 16, 128, 0, 256, 1, False, 0, 2),  # layer3.0.downsample: 1x1 stride 2, K = 128 (two K-steps)
+    (149, 8, 256, 0, 128, 3, False, 1),    # odd image count: the last tile holds one image, 75 M tiles x 1 N tile
+]
+
 
 def reference(case, seed=0):
     n, hw, c0, c1, cout, k, use_res, act = case[:8]
@@ -80,6 +93,20 @@ def test_conv_tc_f16x3_matches_fp32(case):
     # tensor-core fp32 accumulation truncates (round-toward-zero) on every K-block add, so the error
     # grows ~linearly with K (observed 1e-4 abs at K=4608) instead of ~sqrt(K) for FFMA
     assert (err <= 1.5e-4 + 5e-5 * ref.abs()).all()
+
+
+@pytest.mark.parametrize("case", CTA2_CASES)
+def test_conv_tc_cta_pair_kernel_matches_fp32(case):
+    """The cta_group::2 instantiation directly against torch-CPU fp32, and bit-identical to the single-CTA
+    instantiation of the same layer (option cta2=0 keeps the same `group64` accumulation grouping only when both
+    run with it, so the comparison is against fp32 for both and between them at rounding level)."""
+    o = ops()
+    before = _lib.lib().ofb_launch_count(1)
+    got, ref = run(case, _lib.ENGINE_TC, _lib.FMT_SPLIT16)
+    err = (got - ref).abs()
+    print(f"[parity] conv_tc cta_group::2 {case}: max_abs_err={err.max().item():.3e} ref_absmax={ref.abs().max().item():.3e}")
+    assert (err <= 1.5e-4 + 5e-5 * ref.abs()).all()
+    assert o.last_conv_variant() == "cta2", "this shape must select the CTA-pair kernel"
 
 
 @pytest.mark.parametrize("case", TC_CASES[:7])

@@ -320,3 +320,66 @@ def test_depth_to_points_matches_the_reference_expression():
     clipped = depth.clone()
     clipped[clipped > 8] = 0
     assert torch.equal(depth_to_points(depth.to(DEV), max_depth=8).cpu(), rays.unsqueeze(0) * clipped.reshape(2, -1, 1))
+
+
+def test_area_resize_is_bit_identical_to_cv2_inter_area(golden_dir):
+    """dataset_loader_stanford.py:92-94: cv2.resize(rgb, (pano_w, pano_h), interpolation=cv2.INTER_AREA) for the
+    integer factors the Stanford panoramas need; fixture produced by cv2 (tests/golden/make_golden_resize.py)."""
+    import os
+    import numpy as np
+    from omnifusion_b200.preprocess import area_resize_u8, load_panorama_batch
+    z = np.load(os.path.join(golden_dir, "area_resize.npz"))
+    src = torch.from_numpy(z["src"]).to(DEV)
+    for f in (2, 4, 8):
+        got = area_resize_u8(torch.stack([src, src.flip(0)]), f).cpu().numpy()
+        assert np.array_equal(got[0], z[f"area_{f}"]), f
+    x = load_panorama_batch(src, 2).cpu().numpy()
+    assert np.array_equal(x[0], (z["area_2"].astype(np.float32) / 255).transpose(2, 0, 1))
+    with pytest.raises(Exception):
+        area_resize_u8(src, 5)                           # 64 % 5 != 0
+
+
+@pytest.mark.parametrize("n,keep", [(2 * 128 * 256, 0.8), (8 * 512 * 1024, 0.5), (1027, 1.0), (4096, 0.0)])
+def test_masked_median_matches_torch_median(n, keep):
+    """test.py:161-162 uses torch.median (the LOWER median) of the masked values; the radix-select kernel must return
+    exactly that element, and the scale factor the same float32 quotient."""
+    from omnifusion_b200 import metrics
+    g = torch.Generator().manual_seed(n)
+    pred = (0.05 + 9.0 * torch.rand(n, generator=g)).view(1, 1, 1, n)
+    gt = (0.1 + 7.9 * torch.rand(n, generator=g)).view(1, 1, 1, n)
+    gt[0, 0, 0, : n // 7] = gt[0, 0, 0, 0]              # a long run of equal values around which ranks are ambiguous
+    mask = (torch.rand(n, generator=g) < keep).view(1, 1, 1, n)
+    out = metrics.median_scale_device(pred.to(DEV), gt.to(DEV), mask.to(DEV)).cpu()
+    if mask.any():
+        mg, mp = gt[mask].median(), pred[mask].median()
+        assert out[1].item() == mg.item() and out[2].item() == mp.item()
+        assert out[0].item() == (mg / mp).item()
+    else:
+        assert torch.isnan(out[1]) and torch.isnan(out[2])
+
+
+def test_depth_meters_follow_the_reference_average_meters():
+    """test.py:121-177: seven AverageMeters updated with (per-batch value, N = mask.sum()); rms_sq_log's per-batch
+    value is a mean over ITS OWN valid pixels (pred > 1e-7), so it is not a plain ratio of global sums."""
+    from omnifusion_b200 import metrics
+    from oracle import model as om
+    meters = metrics.DepthMeters(DEV)
+    want = {k: 0.0 for k in metrics.METRIC_NAMES}
+    count = 0
+    for b in range(3):
+        pred = 0.1 + 7.9 * urand(2, 1, 64, 128, seed=10 + b)
+        pred[0, 0, b, :50] = 0.0                         # pred <= 1e-7: excluded from rms_sq_log only
+        gt = 0.1 + 7.9 * urand(2, 1, 64, 128, seed=20 + b)
+        mask = (gt <= 8) & (gt > 0.1) & (urand(2, 1, 64, 128, seed=30 + b) > 0.1 * (b + 1))
+        ref = om.eval_metrics(pred, gt, mask, median_scale=True)
+        for k in want:
+            want[k] += ref[k] * ref["n"]
+        count += ref["n"]
+        meters.update(pred.to(DEV), gt.to(DEV), mask.to(DEV), use_median_scale=True)
+    got = meters.all_reduce().result()
+    assert got["n"] == count
+    for k in want:
+        assert abs(got[k] - want[k] / count) <= 2e-6 * max(1.0, abs(want[k] / count)), (k, got[k], want[k] / count)
+    with pytest.raises(ValueError):
+        metrics.depth_metrics_partial(torch.zeros(2, 1, 4, 4, device=DEV), torch.zeros(2, 4, 4, device=DEV),
+                                      torch.ones(2, 1, 4, 4, device=DEV))
