@@ -4,6 +4,8 @@ panoramas/sec, 512x1024 ERP, nrows=4, 2-iteration, confidence-blended).
 
     python bench.py --gpus N --steps K --warmup W          # ours (one process per GPU via torchrun for N>1)
     python bench.py --impl reference ...                   # the reference's CPU path (oracle port), host cores
+    python bench.py --impl torch_gpu ...                   # the kernels to beat: the same network through
+                                                           # cuDNN / cuBLAS (TF32 on and off), never the headline
 
 A "step" is one forward of one batch (default 8 panoramas per GPU = BASELINE configs[1]).
 Prints ONE JSON line on rank 0.
@@ -30,7 +32,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"])
     ap.add_argument("--batch", type=int, default=8, help="panoramas per GPU per step")
     ap.add_argument("--erp", default="512x1024")
     ap.add_argument("--nrows", type=int, default=4)
@@ -88,29 +90,38 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "power_w_max": max(float(r[3]) for r in self.rows)}
 
 
-def oracle_timing(args, he, we, steps):
+def oracle_timing(args, he, we, steps, rgb=None):
     """The reference's CPU path (oracle port: torch-CPU fp32, all host threads) on a bounded sample:
-    B=1 panoramas of the same workload; returns (panoramas/s, cores, description)."""
+    B=1 panoramas of the same workload; returns (panoramas/s, cores, description, final depth of the sample)."""
     from omnifusion_b200.checkpoint import synthetic_state_dict
     from oracle import model as om
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = synthetic_state_dict("iterative", NUM_PATCHES[args.nrows], 0)
-    rgb = torch.rand(1, 3, he, we, generator=torch.Generator().manual_seed(123))
-    om.forward_iterative(sd, rgb, args.iters, bool(args.confidence), nrows=args.nrows)     # builds the tap table
+    if rgb is None:
+        rgb = torch.rand(1, 3, he, we, generator=torch.Generator().manual_seed(123))
+    out = om.forward_iterative(sd, rgb, args.iters, bool(args.confidence), nrows=args.nrows)     # builds the tap table
     t0 = time.perf_counter()
     for _ in range(steps):
-        om.forward_iterative(sd, rgb, args.iters, bool(args.confidence), nrows=args.nrows)
+        out = om.forward_iterative(sd, rgb, args.iters, bool(args.confidence), nrows=args.nrows)
     dt = time.perf_counter() - t0
     return steps / dt, cores, (f"{steps} forwards of B=1 ({he}x{we} ERP, nrows={args.nrows}, {args.iters}-iter, "
                                f"confidence={args.confidence}) after 1 warm-up that builds the tap table; "
-                               f"torch-CPU fp32 oracle port, {cores} threads")
+                               f"torch-CPU fp32 oracle port, {cores} threads"), out[-1]
+
+
+def baseline_config_name(args, he, we):
+    """Which BASELINE.json configuration this command line is (per-GPU view), or 'custom'."""
+    key = (args.batch, he, we, args.nrows, args.iters)
+    return {(8, 512, 1024, 4, 2): "BASELINE configs[1]", (32, 512, 1024, 4, 2): "BASELINE configs[2]",
+            (8, 1024, 2048, 5, 2): "BASELINE configs[3] (8 per GPU of batch 64)",
+            (16, 512, 1024, 6, 2): "BASELINE configs[4] (16 per GPU of batch 128)"}.get(key, "custom")
 
 
 def config_dict(args, he, we, world):
     n = NUM_PATCHES[args.nrows]
     return {"workload": f"batch={args.batch}/GPU, {he}x{we} ERP, fov=80, nrows={args.nrows} ({n} patches of 128x128), "
-                        f"{args.iters}-iter iterative model, confidence={args.confidence} (BASELINE configs[1])",
+                        f"{args.iters}-iter iterative model, confidence={args.confidence} ({baseline_config_name(args, he, we)})",
             "batch_per_gpu": args.batch, "global_batch": args.batch * world, "erp": [he, we], "nrows": args.nrows,
             "patches": n, "iters": args.iters, "confidence": bool(args.confidence),
             "parallelism": f"dp{world} (panorama shards, no data-path collective)",
@@ -124,15 +135,108 @@ def run_reference(args):
     he, we = (int(v) for v in args.erp.split("x"))
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     t0 = time.perf_counter()
-    value, cores, sample = oracle_timing(args, he, we, max(1, args.steps))
+    value, cores, sample, _ = oracle_timing(args, he, we, max(1, args.steps))
+    cfg = config_dict(args, he, we, world)
+    cfg["sample_batch"] = 1          # each timed step of this arm is ONE panorama of the workload (see cpu_baseline.sample)
     line = {"impl": "reference", "metric": "panoramas/sec", "value": value, "unit": "panoramas/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": config_dict(args, he, we, world),
+            "config": cfg,
             "cpu_baseline": {"value": value, "unit": "panoramas/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "panoramas/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
     emit(line)
+
+
+def run_torch_gpu(args):
+    """The Blackwell kernels to beat: the reference network executed by PyTorch on the GPU -
+    cuDNN convolutions (channels_last), cuBLAS linears, ATen elementwise - with TF32 allowed and not allowed, plus
+    our resamplers around it.  Never the headline arm: one JSON line per setting, "impl": "torch_gpu"."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch.nn.functional as F
+    from omnifusion_b200.checkpoint import synthetic_state_dict
+    from omnifusion_b200.equi_pers.equi2pers_v3 import equi2pers
+    from omnifusion_b200.equi_pers.pers2equi_v3 import pers2equi
+    from oracle import model as om
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    he, we = (int(v) for v in args.erp.split("x"))
+    n_patch = NUM_PATCHES[args.nrows]
+    B, K, W, iters = args.batch, args.steps, max(args.warmup, 3), args.iters
+    sd = om.strip_module_prefix(synthetic_state_dict("iterative", n_patch, 0))
+    sd = {k: (v.to(dev).contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v.to(dev)) for k, v in sd.items()}
+    rgb = torch.rand(B, 3, he, we, generator=torch.Generator().manual_seed(123)).to(dev)
+    fov, P, p4 = (80, 80), (128, 128), (32, 32)
+
+    def step():
+        patches, _, _, _ = equi2pers(rgb, fov, args.nrows, P)
+        _, xyz, _, _ = equi2pers(rgb[:, :1, :8, :16].contiguous(), fov, args.nrows, p4)
+        x = om._fold(patches).contiguous(memory_format=torch.channels_last)
+        pf = om._mlp_points(sd, "mlp_points1", xyz.contiguous())
+        pf = pf.unsqueeze(0).expand(B, -1, -1, -1, -1).reshape(B * n_patch, *pf.shape[1:])
+        out = None
+        for it in range(iters):
+            if it > 0:
+                dp, _, _, _ = equi2pers(out, fov, args.nrows, p4)
+                pts = xyz.unsqueeze(0) * om._fold(dp).reshape(B, n_patch, 1, *p4)
+                pf = om._mlp_points(sd, "mlp_points2", pts.reshape(B * n_patch, 3, *p4))
+            pred, weight, _ = om.patch_network(sd, x, pf, B)
+            pred = F.relu(pred)
+            w = torch.sigmoid(weight)
+            pred = pred * w
+            Wm = pers2equi(om._unfold(w, B).contiguous(), fov, args.nrows, P, (he, we), "weight")
+            D = pers2equi(om._unfold(pred, B).contiguous(), fov, args.nrows, P, (he, we), "pred")
+            out = D / (Wm + 1e-8 * (Wm <= 1e-8).float())
+        return out
+
+    # per-layer-class cuDNN timings (conv only, channels_last) at this batch: the classes of kernel_breakdown
+    classes = [("conv3x3s1_c64_o64_@32", 64, 64, 32, 3, 1), ("conv3x3s1_c128_o128_@16", 128, 128, 16, 3, 1),
+               ("conv3x3s1_c256_o256_@8", 256, 256, 8, 3, 1), ("conv3x3s1_c512_o512_@4", 512, 512, 4, 3, 1),
+               ("conv3x3s1_c64_o64_@64", 64, 64, 64, 3, 1), ("conv3x3s1_c128_o32_@64", 128, 32, 64, 3, 1),
+               ("conv3x3s1_c32_o32_@128", 32, 32, 128, 3, 1), ("conv3x3s1_c512_o256_@8", 512, 256, 8, 3, 1)]
+    for tf32 in (True, False):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.benchmark = True
+        with torch.no_grad():
+            for _ in range(W):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(K):
+                out = step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            per_class = []
+            for name, ci, co, hw, k, st in classes:
+                xx = torch.randn(B * n_patch, ci, hw, hw, device=dev).contiguous(memory_format=torch.channels_last)
+                ww = torch.randn(co, ci, k, k, device=dev).contiguous(memory_format=torch.channels_last)
+                for _ in range(3):
+                    F.conv2d(xx, ww, None, st, k // 2)
+                torch.cuda.synchronize()
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record()
+                for _ in range(10):
+                    F.conv2d(xx, ww, None, st, k // 2)
+                c1.record()
+                torch.cuda.synchronize()
+                us = c0.elapsed_time(c1) * 100.0
+                fl = 2.0 * B * n_patch * hw * hw * co * ci * k * k
+                per_class.append({"name": name, "us_per_launch": us, "tflops": fl / (us * 1e-6) / 1e12})
+                del xx, ww
+        value = B * K / (ms * 1e-3)
+        cfg = config_dict(args, he, we, 1)
+        emit({"impl": "torch_gpu", "metric": "panoramas/sec", "value": value, "unit": "panoramas/s", "n_gpus": 1,
+              "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "dtype": "tf32" if tf32 else "fp32",
+              "data": "synthetic", "config": cfg,
+              "setting": {"allow_tf32": tf32, "memory_format": "channels_last", "cudnn_benchmark": True,
+                          "network": "oracle port of the reference network on CUDA (cuDNN conv, cuBLAS linear, ATen "
+                                     "elementwise), eager launches", "resamplers": "libofb equi2pers / pers2equi"},
+              "cudnn_conv_classes": per_class, "result_mean": float(out.mean())})
 
 
 def parse_profile(text):
@@ -165,6 +269,8 @@ def main():
     os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "torch_gpu":
+        return run_torch_gpu(args)
 
     import ctypes as C
     from omnifusion_b200 import _lib, parallel
@@ -278,6 +384,20 @@ def main():
         clocks["sampled_over"] = "device-resident + end-to-end timed regions"
         e2e_check = float(host_out[(K - 1) & 1].mean())        # the result really reached the host
 
+        # ---- Abs-Rel (BASELINE metric clause): test.py:151-177 on the device, shards combined over NCCL ----
+        # synthetic ground truth of SURVEY 8d; every rank scores its own shard (median scaling per batch tensor, as
+        # the reference does per DataLoader batch) and ONE all-reduce(SUM) of 8 doubles combines the meters
+        from omnifusion_b200 import metrics
+        gt = (0.1 + 7.9 * torch.rand(B, 1, he, we, generator=torch.Generator().manual_seed(456 + rank))).to(dev)
+        gmask = (gt <= 8) & (gt > 0.1)
+        depth0 = fwd(dev_in[0])[-1].clone()
+        meters = metrics.DepthMeters(dev)
+        meters.update(depth0, gt, gmask, use_median_scale=True)
+        meters.all_reduce()
+        eval_all = meters.result()
+        one = metrics.compute_eval_metrics(depth0[:1].contiguous(), gt[:1].contiguous(), gmask[:1].contiguous(), True)
+        one_raw = metrics.compute_eval_metrics(depth0[:1].contiguous(), gt[:1].contiguous(), gmask[:1].contiguous(), False)
+
         # ---- per-kernel timing (CUDA events on the launch stream, eager launches) ------------
         prof_rows = []
         if rank == 0:
@@ -344,9 +464,32 @@ def main():
                                   "tflops": (r["flops"] / (r["ms"] * 1e-3) / 1e12) if r["ms"] > 0 else 0,
                                   "gbs": (r["bytes"] / (r["ms"] * 1e-3) / 1e9) if r["ms"] > 0 else 0} for r in top],
             "graph": not args.no_graph}
+    line["abs_rel"] = one["abs_rel"]
+    line["abs_rel_ref"] = None
+    line["abs_rel_detail"] = {
+        "what": "Abs-Rel (metrics.py:7-9 after the median scaling of test.py:161-162) of the CUDA depth of panorama 0 of "
+                "rank 0 on the synthetic gt = 0.1 + 7.9*rand(seed 456), mask = (gt <= 8) & (gt > 0.1); abs_rel_ref = the "
+                "same for the reference's CPU forward (oracle port) on the same panorama",
+        "without_median_scaling": one_raw["abs_rel"], "n_pixels": one["n"],
+        "all_ranks": {"abs_rel": eval_all["abs_rel"], "panoramas": B * world, "n_pixels": eval_all["n"],
+                      "how": "per-rank device meters (radix-select median + 7-metric kernel), one NCCL all-reduce(SUM) "
+                             "of 8 float64" if world > 1 else "device meters (world size 1: no collective)",
+                      "metrics": {k: eval_all[k] for k in metrics.METRIC_NAMES}}}
     if not args.skip_cpu_baseline and world == 1:
-        v, cores, sample = oracle_timing(args, he, we, args.cpu_sample_steps)
+        from oracle import model as om
+        v, cores, sample, ref_depth = oracle_timing(args, he, we, args.cpu_sample_steps, host_in[0][:1].clone())
         line["cpu_baseline"] = {"value": v, "unit": "panoramas/s", "cores": cores, "kind": "port", "sample": sample}
+        g1, m1 = gt[:1].cpu(), gmask[:1].cpu()
+        ref_m = om.eval_metrics(ref_depth, g1, m1, median_scale=True)
+        ref_raw = om.eval_metrics(ref_depth, g1, m1, median_scale=False)
+        line["abs_rel_ref"] = ref_m["abs_rel"]
+        line["abs_rel_detail"].update({
+            "abs_rel_ref_without_median_scaling": ref_raw["abs_rel"],
+            "abs_delta": abs(one["abs_rel"] - ref_m["abs_rel"]),
+            "abs_delta_without_median_scaling": abs(one_raw["abs_rel"] - ref_raw["abs_rel"]),
+            "depth_max_rel_err_vs_reference": float(((depth0[:1].cpu() - ref_depth).abs()
+                                                     / ref_depth.abs().clamp_min(1e-6)).max()),
+            "tolerance": 1e-3})
     else:
         line["cpu_baseline"] = None
     emit(line)
