@@ -81,6 +81,11 @@ int ofb_blend_conf_f32(const float* pred_w, const float* conf, int B, int N, int
                        const int32_t* rowptr, const uint32_t* idx, const float* w,
                        int He, int We, float* out, void* stream);
 
+/* The same with the two patch maps interleaved per pixel: pred_conf (B*N,Ph,Pw,2) = (relu(pred)*sigmoid(weight),
+ * sigmoid(weight)), the layout ofb_heads_tc_pairs_f16 writes; every tap is one 8-byte gather.  8-byte aligned. */
+int ofb_blend_conf_pairs_f32(const float* pred_conf, int B, int N, int Ph, int Pw, const int32_t* rowptr,
+                             const uint32_t* idx, const float* w, int He, int We, float* out, void* stream);
+
 /* ------------------------------------------------------------ network kernels */
 
 enum { OFB_ACT_NONE = 0, OFB_ACT_RELU = 1, OFB_ACT_GELU = 2 };
@@ -195,6 +200,10 @@ int ofb_attention_qkv_f32(const void* qkv, int B, int N, int heads, int head_dim
 int ofb_heads_tc_f16(const void* x_planes, int imgs, int h, int w, const void* wgt_split, float wgt_unscale,
                      float b_pred, float b_conf, int confidence, float* pred_out, float* conf_out, void* stream);
 
+/* Same (confidence on) with both outputs interleaved per pixel: pred_conf_out (imgs,h,w,2) = (pred*conf, conf). */
+int ofb_heads_tc_pairs_f16(const void* x_planes, int imgs, int h, int w, const void* wgt_split, float wgt_unscale,
+                           float b_pred, float b_conf, float* pred_conf_out, void* stream);
+
 /* Heads: pred / weight_pred 3x3 convs + relu / sigmoid / product,
  * spherical_model_iterative.py:371-374.  x (imgs,h,w,32); w_pred,w_conf (3,3,32);
  * pred_out = relu(pred) * (confidence ? sigmoid(conf) : 1); conf_out = sigmoid(conf)
@@ -307,6 +316,11 @@ int64_t ofb_launch_count(int reset);
 /* Timing experiments: copies the clock stamps an epilogue warp of CTA 0 recorded while "tc_debug" & 16
  * was set (512 tiles x 8 int64) to host_dst (tools/probe_tail.py). */
 int ofb_debug_stamps(long long* host_dst);
+/* Timing experiments: with "tc_debug" & 256 CTA 0 of every tcgen05 conv launch records eight %globaltimer stamps
+ * (kernel entry, prologue done, producer past its dependency wait, first operands landed, last MMA issued, first
+ * accumulator complete, last store issued, kernel end).  Copies up to max_slots x 8 int64 of the launches since the
+ * last call to host_dst and returns their number (tools/timeline.py). */
+int ofb_debug_timeline(long long* host_dst, int max_slots);
 
 #ifdef __cplusplus
 }

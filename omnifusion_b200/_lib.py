@@ -50,6 +50,8 @@ _SIGNATURES = {
     "ofb_equi2pers_taps": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "ofb_pers2equi_f32": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P]),
     "ofb_blend_conf_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P]),
+    "ofb_blend_conf_pairs_f32": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P]),
+    "ofb_heads_tc_pairs_f16": (_I, [_P, _I, _I, _I, _P, C.c_float, C.c_float, C.c_float, _P, _P]),
     "ofb_conv_f32": (_I, [C.POINTER(ConvDesc), _P]),
     "ofb_split_f16": (_I, [_P, C.c_size_t, C.c_float, _P, _P]),
     "ofb_merge_f16": (_I, [_P, C.c_size_t, _P, _P]),
@@ -84,6 +86,7 @@ _SIGNATURES = {
     "ofb_workspace_generation": (C.c_longlong, [_P]),
     "ofb_last_conv_variant": (C.c_char_p, []),
     "ofb_debug_stamps": (_I, [_P]),
+    "ofb_debug_timeline": (_I, [_P, _I]),
     "ofb_profile_enable": (_I, [_P, _I]),
     "ofb_profile_report": (_I, [_P, C.c_char_p, _I]),
 }

@@ -47,7 +47,13 @@ struct TcParams {
   float* partial;        // each split writes its raw float32 accumulators to partial[split][pixel][cout] (ofb_splitk_finish_ln_f32 reduces)
   long long m_total;     // pixels per split plane of `partial`
   float* heads_pred; float* heads_conf; float heads_bp, heads_bc;   // UPS == 2: the two heads' outputs and biases
+  int heads_il;          // UPS == 2: write (pred * conf, conf) as ONE float2 per pixel into heads_pred (the layout the
+                         // blend kernel gathers with one 8-byte load per tap) instead of two separate maps
   long long* dbg_buf;    // dbg & 16: clock stamps of the epilogue warp 2 of CTA 0: [tile][8]
+                         // dbg & 256: %globaltimer stamps of CTA 0 of every launch: [launch slot][8] (kTimelineSlots slots,
+                         // slot counter behind them): 0 kernel entry, 1 prologue done, 2 producer past griddepcontrol.wait,
+                         // 3 first operands landed, 4 last MMA issued, 5 first accumulator complete, 6 last store issued,
+                         // 7 kernel end
   int group64;           // accumulate the three split-half products in the cta_group::2 column grouping (see the MMA warp)
 };
 
@@ -111,6 +117,12 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 __device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+constexpr int kTimelineSlots = 1024;
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -295,6 +307,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   const int ksteps = ((KHR ? 3 : p.taps) * cchunks) / p.ksplit;      // K-steps of one tile (of one split)
   const int tiles_per_group = p.tiles_x * p.tiles_y;
 
+  const bool tl_on = (p.dbg & 256) && blockIdx.x == 0;
+  if (tl_on && threadIdx.x == 0) {
+    const unsigned long long slot = atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg_buf + kTimelineSlots * 8), 1ull);
+    tmem_slot[1] = (uint32_t)slot;
+    if (slot < kTimelineSlots) p.dbg_buf[slot * 8 + 0] = globaltimer_ns();
+  }
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < Cfg::NST; ++i) {
       mbar_init(bars + 8 * i, UPS == 1 ? Cfg::UPS_WARPS : 1);     // full: the TMA thread, or one arrival per producer warp
@@ -326,10 +344,18 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   if (CTA2) cluster_sync_all();          // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem = uniform(*tmem_slot);
+  const uint32_t tl_slot = tl_on ? uniform(tmem_slot[1]) : 0u;
+  const bool tl = tl_on && tl_slot < (uint32_t)kTimelineSlots;
+  long long* const tl_buf = p.dbg_buf + (size_t)tl_slot * 8;
+  if (tl && threadIdx.x == 0) tl_buf[1] = globaltimer_ns();
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
   // prefetch) may overlap the tail of the previous kernel in the stream; no global memory is
   // touched before this point.  Let the next kernel start its own prologue as early as possible.
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // Let the next kernel start its own prologue as early as possible.  griddepcontrol.wait (= the previous kernel in
+  // the stream has completed and its writes are visible) is executed per role, immediately before the first access
+  // to memory another kernel writes: the WEIGHTS are written once at load time, so the producer warp issues the
+  // weight loads of the first ring stages (and the resident filter) BEFORE it waits - their HBM latency overlaps the
+  // previous kernel's tail and the launch gap instead of opening every layer's pipeline.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
@@ -342,6 +368,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       }
       __syncwarp();
     }
+    if (UPS == 2) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (UPS == 2) {
       // rolling rows: one box {32 channels, 130 pixels from x = -1, 1 row} per plane and produced row; rows -1
       // and H and the two border columns are out of bounds = zero-filled by TMA = the conv padding
@@ -370,6 +397,43 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     constexpr bool ld_a = true, ld_b = !BRES;
     const uint32_t a_bytes = KHR ? (uint32_t)((p.BH + 2) * p.BW * ROW_BYTES) : (uint32_t)Cfg::A_BYTES;
     const uint32_t tx = (uint32_t)Cfg::PLANES * ((ld_a ? a_bytes : 0u) + (ld_b ? (uint32_t)Cfg::B_BYTES : 0u));
+    // weight operand of one K-step into ring stage `stg` (the transaction bytes of the whole stage, activations
+    // included, are announced by whoever calls this first for the stage)
+    auto load_b = [&](uint32_t stg, int n0, int tap, int cq) {
+      const uint32_t full = bars + 8 * stg;
+      const uint32_t sb = base + stg * Cfg::STAGE + Cfg::PLANES * Cfg::A_BYTES;
+      if (CTA2) { if (rank == 0) mbar_expect_tx(full, 2 * tx); } else mbar_expect_tx(full, tx);
+      if (KHR) {
+        // one box = {kc, stacked [Whi; Wlo] rows, all 3 kh, this kw}
+        tma_load_4d(sb, &maps.b[0], full, cq * Cfg::KC, 0, 0, tap);
+      } else {
+        const int wk = tap * cin;
+#pragma unroll
+        for (int pl = 0; pl < Cfg::PLANES; ++pl) {
+          // CTA2, rank r: [Whi rows 64r.. ; Wlo rows 64(1-r)..]
+          if (CTA2) tma_load_2d_2sm(sb + pl * Cfg::B_BYTES, &maps.b[pl], full, wk + cq * Cfg::KC,
+                                    n0 + (BN / 2) * (pl == 0 ? (int)rank : 1 - (int)rank));
+          else tma_load_2d(sb + pl * Cfg::B_BYTES, &maps.b[pl], full, wk + cq * Cfg::KC, n0);
+        }
+      }
+    };
+    // prologue: weight loads of the first ring stages, before the dependency wait (all stages are empty)
+    int pre = 0;
+    if (ld_b && !UPS) {
+      for (int t = tile0; t < p.total_tiles && pre < Cfg::NST; t += tile_step) {
+        const int sp = t % p.ksplit, tq = t / p.ksplit;
+        const int n0 = (tq % p.tiles_n) * BN;
+        const int cq_begin = p.ksplit > 1 ? sp * ksteps : 0, cq_end = p.ksplit > 1 ? cq_begin + ksteps : cchunks;
+        for (int tap = 0; tap < ntap && pre < Cfg::NST; ++tap)
+          for (int cq = cq_begin; cq < cq_end && pre < Cfg::NST; ++cq, ++pre) {
+            if (elect_one()) load_b((uint32_t)pre, n0, tap, cq);
+            __syncwarp();
+          }
+      }
+    }
+    if (!UPS) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tl && lane == 0) tl_buf[2] = globaltimer_ns();
+    int gs = 0;                       // K-steps issued so far (the first `pre` already have their weights in flight)
     for (int t = tile0; !UPS && t < p.total_tiles; t += tile_step) {
       const int sp = t % p.ksplit, tq = t / p.ksplit;            // split-K slice (ksplit == 1: tq == t)
       const int nt = tq % p.tiles_n, mt = CTA2 ? 2 * (tq / p.tiles_n) + (int)rank : tq / p.tiles_n;
@@ -383,43 +447,25 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         // KHR: `tap` is kw; the box carries rows y0-1 .. y0+BH, the weights all three kh
         const int cx = KHR ? x0 + tap - 1 : x0 * p.sx + kw - p.padx;
         const int cy = KHR ? y0 - 1 : y0 * p.sy + kh - p.pady;
-        const int wk = tap * cin;
         for (int cq = cq_begin; cq < cq_end; ++cq) {
           int c = cq * Cfg::KC;
           int src = 0;
           if (c >= p.c0) { src = 1; c -= p.c0; }
           const uint32_t full = bars + 8 * st;
           const uint32_t sa = base + st * Cfg::STAGE;
-          const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
           mbar_wait(bars + 8 * (Cfg::NST + st), ph ^ 1);
           if (elect_one()) {
-            if (KHR) {
-              mbar_expect_tx(full, tx);
+            // (CTA2: both CTAs' bytes land on the leader's barrier)
+            if (ld_b) { if (gs >= pre) load_b(st, n0, tap, cq); }
+            else mbar_expect_tx(full, tx);
 #pragma unroll
-              for (int pl = 0; pl < Cfg::PLANES; ++pl)
-                if (ld_a) tma_load_4d(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, cx, cy, img0);
-              // one box = {kc, stacked [Whi; Wlo] rows, all 3 kh, this kw}
-              if (ld_b) tma_load_4d(sb, &maps.b[0], full, cq * Cfg::KC, 0, 0, tap);
-            } else if (CTA2) {
-              if (rank == 0) mbar_expect_tx(full, 2 * tx);      // both CTAs' bytes land on the leader's barrier
-#pragma unroll
-              for (int pl = 0; pl < Cfg::PLANES; ++pl) {
-                if (ld_a) tma_load_4d_2sm(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, cx, cy, img0);
-                // rank r: [Whi rows 64r.. ; Wlo rows 64(1-r)..]
-                if (ld_b)
-                  tma_load_2d_2sm(sb + pl * Cfg::B_BYTES, &maps.b[pl], full, wk + cq * Cfg::KC,
-                                  n0 + (BN / 2) * (pl == 0 ? (int)rank : 1 - (int)rank));
-              }
-            } else {
-              mbar_expect_tx(full, tx);
-#pragma unroll
-              for (int pl = 0; pl < Cfg::PLANES; ++pl) {
-                if (ld_a) tma_load_4d(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, cx, cy, img0);
-                if (ld_b) tma_load_2d(sb + pl * Cfg::B_BYTES, &maps.b[pl], full, wk + cq * Cfg::KC, n0);
-              }
+            for (int pl = 0; pl < Cfg::PLANES; ++pl) {
+              if (CTA2) tma_load_4d_2sm(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, cx, cy, img0);
+              else tma_load_4d(sa + pl * Cfg::A_BYTES, &maps.a[src][pl], full, c, cx, cy, img0);
             }
           }
           __syncwarp();
+          ++gs;
           if (++st == Cfg::NST) { st = 0; ph ^= 1; }
         }
         if (++kw == p.kdiv) { kw = 0; ++kh; }
@@ -495,6 +541,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(bars + 8 * st, ph);
           tc_fence_after();
+          if (tl && lane == 0 && i == 0 && ks == 0) tl_buf[3] = globaltimer_ns();
           const uint32_t sa = base + st * Cfg::STAGE;
           // BRES: one K-step per kw (cin == KC), its weights sit in the resident region
           const uint32_t sb = BRES ? res_b + (uint32_t)(ks * Cfg::PLANES * Cfg::B_BYTES) : sa + Cfg::PLANES * Cfg::A_BYTES;
@@ -544,9 +591,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           if (++st == Cfg::NST) { st = 0; ph ^= 1; }
         }
       }
+      if (tl && lane == 0) tl_buf[4] = globaltimer_ns();
     }
   } else if (warp < 2 + Cfg::EPI_WARPS) {
     // ===================== epilogue (warps 2..5 <-> TMEM lane quarters) =====================
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // residual reads / output writes: after the previous kernel
     const int q = warp & 3;                    // a warp may only touch TMEM lanes [32*(warp%4), +32)
     const int r = q * 32 + lane;               // accumulator row = pixel within the tile
     const int xx = r % p.BW, yy = (r / p.BW) % p.BH, ni = r / (p.BW * p.BH);
@@ -573,14 +622,37 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       }
       const uint32_t buf = i & 1;
       const bool stamp = (p.dbg & 16) && blockIdx.x == 0 && et == 0 && i < 512;
-      if (stamp) p.dbg_buf[i * 8 + 0] = clock64();
-      mbar_wait(bar_tfull + 8 * buf, (i >> 1) & 1);
-      tc_fence_after();
-      if (stamp) p.dbg_buf[i * 8 + 1] = clock64();
       const int img = img0 + ni;
       const bool ok = img < p.n_img;
       const size_t pix = ((size_t)(ok ? img : 0) * p.H + (y0 + yy)) * p.W + (x0 + xx);
       const size_t off = pix * p.cout + n0;
+      // The residual operand of this tile is fetched BEFORE waiting for the accumulator: the epilogue warps idle
+      // during the K loop, so its L2 / HBM latency disappears behind the MMAs instead of heading the epilogue
+      // (with one tile per CTA - 8 panoramas per step - nothing else overlaps that tail).
+      constexpr int NCH = (BN + 32 * Cfg::EPI_SETS - 1) / (32 * Cfg::EPI_SETS);     // 32-column chunks per epilogue warp
+      constexpr bool RES_PRE = MODE == MODE_F16X3;
+      uint4 rpre[RES_PRE ? NCH : 1][8];
+      const bool res_pre = RES_PRE && p.residual && ok && p.ksplit == 1;
+      if (res_pre) {
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int cb = 32 * eset + ci * 32 * Cfg::EPI_SETS;
+          if (cb < BN) {
+            const __half* rhi = reinterpret_cast<const __half*>(p.residual) + off + cb;
+            const __half* rlo = rhi + p.plane;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              rpre[ci][j] = __ldg(reinterpret_cast<const uint4*>(rhi + 8 * j));
+              rpre[ci][4 + j] = __ldg(reinterpret_cast<const uint4*>(rlo + 8 * j));
+            }
+          }
+        }
+      }
+      if (stamp) p.dbg_buf[i * 8 + 0] = clock64();
+      mbar_wait(bar_tfull + 8 * buf, (i >> 1) & 1);
+      tc_fence_after();
+      if (stamp) p.dbg_buf[i * 8 + 1] = clock64();
+      if (tl && et == 0 && i == 0) tl_buf[5] = globaltimer_ns();
 #pragma unroll 1
       if (UPS == 2) {
         // heads: accumulator columns [0,16) = hi*Whi + lo*Whi, [16,32) = hi*Wlo; channel 0 = pred, 1 = weight_pred
@@ -596,12 +668,19 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         if (p.heads_conf) {
           const float cf = 1.f / (1.f + expf(-((__uint_as_float(v[1]) + __uint_as_float(v[17])) * p.wscale + p.heads_bc)));
           pr *= cf;
+          if (p.heads_il) {
+            reinterpret_cast<float2*>(p.heads_pred)[pix] = make_float2(pr, cf);
+            continue;
+          }
           p.heads_conf[pix] = cf;
         }
         p.heads_pred[pix] = pr;
         continue;
       }
-      for (int cb = 32 * eset; cb < BN; cb += 32 * Cfg::EPI_SETS) {
+#pragma unroll
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int cb = 32 * eset + ci * 32 * Cfg::EPI_SETS;
+        if (cb >= BN) break;
         uint32_t v[32];
         tmem_ld32_issue(tmem + ((uint32_t)(q * 32) << 16) + buf * Cfg::ACC_COLS + cb, v);
         if (Cfg::STACK) {                        // second column block (hi*Wlo) of the stacked accumulator
@@ -645,12 +724,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
               f[j] += tt.x; f[j + 1] += tt.y; f[j + 2] += tt.z; f[j + 3] += tt.w;
             }
           } else {
-            const __half* rhi = reinterpret_cast<const __half*>(p.residual) + off + cb;
-            const __half* rlo = rhi + p.plane;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-              uint4 a = __ldg(reinterpret_cast<const uint4*>(rhi + j));
-              uint4 b = __ldg(reinterpret_cast<const uint4*>(rlo + j));
+              const uint4 a = rpre[RES_PRE ? ci : 0][j >> 3];
+              const uint4 b = rpre[RES_PRE ? ci : 0][4 + (j >> 3)];
               const __half2* ah = reinterpret_cast<const __half2*>(&a);
               const __half2* bh = reinterpret_cast<const __half2*>(&b);
 #pragma unroll
@@ -751,6 +828,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         }
       }
     }
+    if (tl && et == 0) tl_buf[6] = globaltimer_ns();
     if (TMA_STORE && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   } else if (UPS == 1) {
     // ===================== interpolating producers (warps 6..13) =====================
@@ -759,6 +837,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     // (clamped) with weights h0, h1; same for columns.  T(r) = the horizontally blended low-res row r (2 pixels
     // x 8 channels per thread) is cached in registers for the two rows in use: consecutive upsampled rows
     // share them, so a new low-res row is fetched only every second row.
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // reads the previous layer's output
     constexpr int NT = 32 * Cfg::UPS_WARPS, C8 = Cfg::KC / 8;
     static_assert(UPS != 1 || (NT == 64 * C8), "one producer thread per (low-res column, 8-channel chunk)");
     const int pt = threadIdx.x - (64 + 32 * Cfg::EPI_WARPS);
@@ -870,6 +949,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   tc_fence_before();
   __syncthreads();
   if (CTA2) cluster_sync_all();          // the leader's MMAs read the peer's shared memory until the very end
+  if (tl && threadIdx.x == 32) tl_buf[7] = globaltimer_ns();
   if (warp == 1) {
     tc_fence_after();
     if (CTA2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
@@ -949,8 +1029,12 @@ TcOptScope::TcOptScope(const TcOptions* o) : prev(t_opts) { t_opts = o; }
 TcOptScope::~TcOptScope() { t_opts = prev; }
 
 static long long* g_dbg_buf = nullptr;
+int conv_tc_timeline_slots() { return kTimelineSlots; }
 long long* conv_tc_debug_buffer() {
-  if (!g_dbg_buf) cudaMalloc(&g_dbg_buf, 512 * 8 * sizeof(long long));
+  if (!g_dbg_buf) {
+    cudaMalloc(&g_dbg_buf, (kTimelineSlots * 8 + 8) * sizeof(long long));
+    cudaMemset(g_dbg_buf, 0, (kTimelineSlots * 8 + 8) * sizeof(long long));
+  }
   return g_dbg_buf;
 }
 
@@ -1067,7 +1151,7 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
   p.residual = d->residual; p.out = d->out; p.act = d->act;
   p.plane = (long long)d->n * oh * ow * d->cout;
   p.dbg = tc_opts().dbg;
-  p.dbg_buf = (tc_opts().dbg & 16) ? conv_tc_debug_buffer() : nullptr;
+  p.dbg_buf = (tc_opts().dbg & (16 | 256)) ? conv_tc_debug_buffer() : nullptr;
   p.group64 = tc_opts().cta2 ? 1 : 0;
   const int S = d->ksplit > 1 ? d->ksplit : 1;
   OFB_CHECK(S == 1 || (split && d->k == 1 && d->stride == 1 && !d->ups2x && d->partial && (cin / kc) % S == 0),
@@ -1160,8 +1244,10 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
 // through L2, no index arithmetic), all nine taps read it through row-shifted descriptors, and the epilogue
 // applies relu / sigmoid / product and writes the two float32 patch maps.  x: split-half (n, h, 128, 32).
 int conv_tc_heads(const void* x, int n, int h, int w, const void* wgt_split, float wgt_unscale, float b_pred,
-                  float b_conf, int confidence, float* pred_out, float* conf_out, cudaStream_t s) {
+                  float b_conf, int confidence, float* pred_out, float* conf_out, int interleaved, cudaStream_t s) {
   OFB_CHECK(x && wgt_split && pred_out && (!confidence || conf_out), "heads_tc: null pointer");
+  OFB_CHECK(!interleaved || (confidence && (reinterpret_cast<uintptr_t>(pred_out) & 7) == 0),
+            "heads_tc: the interleaved (pred*conf, conf) output needs confidence != 0 and an 8-byte aligned buffer");
   OFB_CHECK(w == 128 && h >= 1, "heads_tc: rows must be 128 pixels wide (got %d)", w);
   TcParams p{};
   p.n_img = n; p.H = h; p.W = w; p.c0 = 32; p.c1 = 0; p.cout = 16; p.k = 3; p.pad = 1; p.stride = 1;
@@ -1171,8 +1257,9 @@ int conv_tc_heads(const void* x, int n, int h, int w, const void* wgt_split, flo
   p.tiles_n = 1; p.total_tiles = n * h;
   p.ksplit = 1;
   p.heads_pred = pred_out; p.heads_conf = confidence ? conf_out : nullptr; p.heads_bp = b_pred; p.heads_bc = b_conf;
+  p.heads_il = interleaved ? 1 : 0;
   p.dbg = tc_opts().dbg;
-  p.dbg_buf = (tc_opts().dbg & 16) ? conv_tc_debug_buffer() : nullptr;
+  p.dbg_buf = (tc_opts().dbg & (16 | 256)) ? conv_tc_debug_buffer() : nullptr;
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
   const size_t plane = (size_t)n * h * w * 32;               // halves per plane

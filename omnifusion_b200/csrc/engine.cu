@@ -33,8 +33,13 @@ int stem_tc(const void* patches, int n, int h, int w, const void* wgt_split, flo
 int conv_tc(const ofb_conv_desc* d, cudaStream_t s);
 bool conv_tc_supported(const ofb_conv_desc* d);
 int conv_tc_heads(const void* x, int n, int h, int w, const void* wgt_split, float wgt_unscale, float b_pred,
-                  float b_conf, int confidence, float* pred_out, float* conf_out, cudaStream_t s);
+                  float b_conf, int confidence, float* pred_out, float* conf_out, int interleaved, cudaStream_t s);
+int blend_conf_launch(const float* pred_w, const float* conf, bool interleaved, int B, int N, int Ph, int Pw,
+                      const int32_t* rowptr, const uint32_t* idx, const float* w, int He, int We, float* out,
+                      cudaStream_t s);
+int deinterleave_launch(const float* src_pairs, size_t n, int comp, float* dst, cudaStream_t s);
 long long* conv_tc_debug_buffer();
+int conv_tc_timeline_slots();
 const char* conv_tc_last_variant();
 
 int conv_dispatch(const ofb_conv_desc* d, cudaStream_t s) {
@@ -370,7 +375,8 @@ static size_t plan_buffers(ofb_handle* h, int imgs, int P, Buffers* b) {
   b->up2 = pl.take(I * p4 * p4 * 64); b->d20 = pl.take(I * p4 * p4 * 64); b->d21 = pl.take(I * p4 * p4 * 64);
   b->up3 = pl.take(I * p2 * p2 * 64); b->d30 = pl.take(I * p2 * p2 * 64); b->d31 = pl.take(I * p2 * p2 * 32);
   b->up4 = pl.take(I * P * P * 32); b->d40 = pl.take(I * P * P * 32);
-  b->pred = pl.take(I * P * P); b->conf = pl.take(I * P * P); b->depth_p = pl.take(I * p4 * p4);
+  // head outputs: either two maps (pred | conf, back to back) or one interleaved (pred*conf, conf) pair map
+  b->pred = pl.take(2 * I * P * P); b->conf = b->pred ? b->pred + I * P * P : nullptr; b->depth_p = pl.take(I * p4 * p4);
   return pl.off;
 }
 
@@ -503,6 +509,7 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
   Ctx c{h, s, imgs};
   void* vs = (void*)s;
   const int F = h->fmt;
+  bool pairs = false;          // head outputs of the last iteration are an interleaved pair map
 
   for (int it = 0; it < iters; ++it) {
     bool reuse = it > 0 && h->dedup;
@@ -627,15 +634,18 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
       if (run_conv(c, h->conv["de_conv4_0"], b.up4, 32, nullptr, 0, P, P, 1, 1, nullptr, OFB_ACT_RELU, b.d40)) return -1;
     }
 
-    // heads + ERP merge (:371-380)
+    // heads + ERP merge (:371-380).  With the tensor-core heads and confidence the two patch maps are written as
+    // one interleaved (pred*conf, conf) pair map: every tap of the blend below is then one 8-byte gather.
+    const bool tc_heads = h->heads_tc && F == OFB_FMT_SPLIT16 && h->engine != OFB_ENGINE_SIMT && P == 128;
+    pairs = tc_heads && confidence;
     { Prof pr(h, s, "heads", 0.0, 4.0*((double)imgs*P*P*34));
-    if (h->heads_tc && F == OFB_FMT_SPLIT16 && h->engine != OFB_ENGINE_SIMT && P == 128) {
-      if (conv_tc_heads(b.d40, imgs, P, P, h->heads16.ws, h->heads16.unscale, h->pred_b, h->conf_b, confidence, b.pred, b.conf, s)) return -1;
+    if (tc_heads) {
+      if (conv_tc_heads(b.d40, imgs, P, P, h->heads16.ws, h->heads16.unscale, h->pred_b, h->conf_b, confidence, b.pred, b.conf, pairs ? 1 : 0, s)) return -1;
     } else if (ofb_heads_f32(b.d40, imgs, P, P, h->pred_w, h->pred_b, h->conf_w, h->conf_b, confidence, b.pred, b.conf, F, vs)) return -1; }
     float* out = outs[it] + out_off;
     if (confidence) {
       { Prof pr(h, s, "blend_conf", 0.0, 4.0*((double)imgs*P*P*2 + (double)Bc*He*We));
-      if (ofb_blend_conf_f32(b.pred, b.conf, Bc, N, P, P, g.blend_rowptr, g.blend_idx, g.blend_w, He, We, out, vs)) return -1; }
+      if (blend_conf_launch(b.pred, b.conf, pairs, Bc, N, P, P, g.blend_rowptr, g.blend_idx, g.blend_w, He, We, out, s)) return -1; }
     } else {
       { Prof pr(h, s, "pers2equi", 0.0, 4.0*((double)imgs*P*P + (double)Bc*He*We));
       if (ofb_pers2equi_f32(b.pred, Bc, 1, N, P, P, OFB_LAYOUT_FOLDED, g.blend_rowptr, g.blend_idx, g.blend_w, He, We, out, vs)) return -1; }
@@ -648,8 +658,8 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
   reg(h, "tokens", b.down, imgs, 4, 4, 32); reg(h, "encoded", b.enc, imgs, 1, 1, 512, 0);
   reg(h, "de_conv0_1", b.d01, imgs, P / 16, P / 16, 128); reg(h, "de_conv1_1", b.d11, imgs, P / 8, P / 8, 64);
   reg(h, "de_conv2_1", b.d21, imgs, p4, p4, 64); reg(h, "de_conv3_1", b.d31, imgs, P / 2, P / 2, 32);
-  reg(h, "de_conv4_0", b.d40, imgs, P, P, 32); reg(h, "pred_patch", b.pred, imgs, P, P, 1, 0);
-  reg(h, "conf_patch", b.conf, imgs, P, P, 1, 0);
+  reg(h, "de_conv4_0", b.d40, imgs, P, P, 32); reg(h, "pred_patch", b.pred, imgs, P, P, 1, pairs ? 2 : 0);
+  reg(h, "conf_patch", pairs ? b.pred : b.conf, imgs, P, P, 1, pairs ? 3 : 0);    // fmt 2 / 3: component 0 / 1 of a pair map
   return 0;
 }
 
@@ -672,7 +682,13 @@ extern "C" int ofb_set_device(int device) {
 extern "C" int ofb_heads_tc_f16(const void* x_planes, int imgs, int h, int w, const void* wgt_split, float wgt_unscale,
                                 float b_pred, float b_conf, int confidence, float* pred_out, float* conf_out,
                                 void* stream) {
-  return conv_tc_heads(x_planes, imgs, h, w, wgt_split, wgt_unscale, b_pred, b_conf, confidence, pred_out, conf_out,
+  return conv_tc_heads(x_planes, imgs, h, w, wgt_split, wgt_unscale, b_pred, b_conf, confidence, pred_out, conf_out, 0,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int ofb_heads_tc_pairs_f16(const void* x_planes, int imgs, int h, int w, const void* wgt_split, float wgt_unscale,
+                                      float b_pred, float b_conf, float* pred_conf_out, void* stream) {
+  return conv_tc_heads(x_planes, imgs, h, w, wgt_split, wgt_unscale, b_pred, b_conf, 1, pred_conf_out, pred_conf_out, 1,
                        (cudaStream_t)stream);
 }
 
@@ -826,6 +842,21 @@ extern "C" int ofb_debug_stamps(long long* host_dst) {
   return 0;
 }
 
+// timing experiments: %globaltimer stamps of CTA 0 of every tcgen05 conv launch since the last call ("tc_debug" & 256):
+// copies up to max_slots x 8 int64 to host_dst, resets the slot counter, returns the number of launches recorded
+extern "C" int ofb_debug_timeline(long long* host_dst, int max_slots) {
+  OFB_CUDA(cudaDeviceSynchronize());
+  const int slots = conv_tc_timeline_slots();
+  long long* buf = conv_tc_debug_buffer();
+  long long count = 0;
+  OFB_CUDA(cudaMemcpy(&count, buf + (size_t)slots * 8, sizeof(long long), cudaMemcpyDeviceToHost));
+  int n = (int)(count < slots ? count : slots);
+  if (n > max_slots) n = max_slots;
+  if (host_dst && n > 0) OFB_CUDA(cudaMemcpy(host_dst, buf, (size_t)n * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+  OFB_CUDA(cudaMemset(buf, 0, ((size_t)slots * 8 + 8) * sizeof(long long)));
+  return n;
+}
+
 extern "C" int ofb_profile_enable(ofb_handle* h, int on) {
   OFB_CHECK(h, "profile_enable: null handle");
   h->profile = on != 0;
@@ -873,6 +904,8 @@ extern "C" int64_t ofb_get_activation(ofb_handle* h, const char* name, float* ds
     OFB_CHECK(capacity >= n, "get_activation: capacity %lld < %lld", (long long)capacity, (long long)n);
     if (a.fmt == OFB_FMT_SPLIT16) {
       if (ofb_merge_f16(a.p, (size_t)n, dst, stream)) return -1;
+    } else if (a.fmt == 2 || a.fmt == 3) {
+      if (deinterleave_launch(a.p, (size_t)n, a.fmt - 2, dst, (cudaStream_t)stream)) return -1;
     } else {
       OFB_CUDA(cudaMemcpyAsync(dst, a.p, n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     }

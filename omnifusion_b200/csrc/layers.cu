@@ -104,34 +104,58 @@ stem_kernel(const float* __restrict__ in, int n, int h, int w, const float* __re
 }
 
 // -------------------------------------------------------------------- maxpool
+// F.max_pool3d((3,3,1), s(2,2,1), p(1,1,0)).  Thread = (image, band of output rows, output column, 8-channel
+// chunk); it walks its band top to bottom and carries the horizontal 3-max of input row 2*oh+1 over to the next
+// output row (where it is row 2*oh'-1), so every input row is fetched once instead of 1.5 times and an output costs
+// 6 instead of 9 taps; all loads are 16 bytes per plane, a warp touches whole 128-byte pixel vectors.
 template <bool SPLIT>
-__global__ void maxpool_kernel(const void* __restrict__ in, int n, int h, int w, int c4,
-                               void* __restrict__ out) {
-  int oh_n = h / 2, ow_n = w / 2;
-  // 32-bit index arithmetic (the host checks total < 2^31): 64-bit div/mod costs ~100 instructions each
-  const uint32_t total = (uint32_t)n * oh_n * ow_n * c4;
+__device__ __forceinline__ float8 pool_hmax(const void* __restrict__ in, size_t row_off, int ow, int w, int c8, int c,
+                                            size_t plane) {
+  float8 m;
+  m.a = m.b = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+  for (int dx = -1; dx <= 1; ++dx) {
+    const int iw = ow * 2 + dx;
+    if (iw < 0 || iw >= w) continue;
+    const float8 v = act_ld8<SPLIT>(in, (row_off + iw) * c8 * 8 + (size_t)c * 8, plane);
+    m.a.x = fmaxf(m.a.x, v.a.x); m.a.y = fmaxf(m.a.y, v.a.y); m.a.z = fmaxf(m.a.z, v.a.z); m.a.w = fmaxf(m.a.w, v.a.w);
+    m.b.x = fmaxf(m.b.x, v.b.x); m.b.y = fmaxf(m.b.y, v.b.y); m.b.z = fmaxf(m.b.z, v.b.z); m.b.w = fmaxf(m.b.w, v.b.w);
+  }
+  return m;
+}
+__device__ __forceinline__ float8 max8(const float8& x, const float8& y) {
+  float8 m;
+  m.a = make_float4(fmaxf(x.a.x, y.a.x), fmaxf(x.a.y, y.a.y), fmaxf(x.a.z, y.a.z), fmaxf(x.a.w, y.a.w));
+  m.b = make_float4(fmaxf(x.b.x, y.b.x), fmaxf(x.b.y, y.b.y), fmaxf(x.b.z, y.b.z), fmaxf(x.b.w, y.b.w));
+  return m;
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(256)
+maxpool_kernel(const void* __restrict__ in, int n, int h, int w, int c8, int bands, void* __restrict__ out) {
+  const int oh_n = h / 2, ow_n = w / 2;
+  // 32-bit index arithmetic (the host checks the range)
+  const uint32_t total = (uint32_t)n * bands * ow_n * c8;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int c = (int)(i % (uint32_t)c4);
-  uint32_t r = i / (uint32_t)c4;
+  const int c = (int)(i % (uint32_t)c8);
+  uint32_t r = i / (uint32_t)c8;
   const int ow = (int)(r % (uint32_t)ow_n); r /= (uint32_t)ow_n;
-  const int oh = (int)(r % (uint32_t)oh_n);
-  const int img = (int)(r / (uint32_t)oh_n);
-  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-  const size_t in_plane = (size_t)n * h * w * c4 * 4;
-#pragma unroll
-  for (int dy = -1; dy <= 1; ++dy) {
-    int ih = oh * 2 + dy;
-    if (ih < 0 || ih >= h) continue;
-#pragma unroll
-    for (int dx = -1; dx <= 1; ++dx) {
-      int iw = ow * 2 + dx;
-      if (iw < 0 || iw >= w) continue;
-      float4 v = act_ld4<SPLIT>(in, (((size_t)(img * h + ih) * w + iw) * c4 + c) * 4, in_plane);
-      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
-    }
+  const int band = (int)(r % (uint32_t)bands);
+  const int img = (int)(r / (uint32_t)bands);
+  const int rows = (oh_n + bands - 1) / bands;
+  const int oh0 = band * rows, oh1 = min(oh0 + rows, oh_n);
+  const size_t in_plane = (size_t)n * h * w * c8 * 8, out_plane = (size_t)n * oh_n * ow_n * c8 * 8;
+  float8 carry;                                   // horizontal max of input row 2*oh - 1
+  carry.a = carry.b = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  if (oh0 > 0) carry = pool_hmax<SPLIT>(in, ((size_t)img * h + 2 * oh0 - 1) * w, ow, w, c8, c, in_plane);
+  for (int oh = oh0; oh < oh1; ++oh) {
+    const float8 mid = pool_hmax<SPLIT>(in, ((size_t)img * h + 2 * oh) * w, ow, w, c8, c, in_plane);
+    const float8 low = pool_hmax<SPLIT>(in, ((size_t)img * h + 2 * oh + 1) * w, ow, w, c8, c, in_plane);   // 2*oh+1 < h: h is even
+    const float8 m = max8(max8(carry, mid), low);
+    act_st8<SPLIT>(out, ((((size_t)img * oh_n + oh) * ow_n + ow) * c8 + c) * 8, out_plane, m);
+    carry = low;
   }
-  act_st4<SPLIT>(out, (size_t)i * 4, (size_t)total * 4, m);
 }
 
 // ------------------------------------------------------------------- upsample
@@ -142,7 +166,8 @@ __global__ void maxpool_kernel(const void* __restrict__ in, int n, int h, int w,
 // (clamped at the borders) and produces the 2x2 output block, i.e. 2.25 loads per output instead of 4.
 // Per output the expression tree is ATen's: h0*(w0*a + w1*b) + h1*(w0*c + w1*d).
 template <bool SPLIT>
-__global__ void upsample2x_kernel(const void* __restrict__ in, const float* __restrict__ img_bias,
+__global__ void __launch_bounds__(256, 3)
+upsample2x_kernel(const void* __restrict__ in, const float* __restrict__ img_bias,
                                   int n, int h, int w, int c8, void* __restrict__ out) {
   const uint32_t total = (uint32_t)n * h * w * c8;       // 32-bit index arithmetic, see maxpool_kernel
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -155,33 +180,38 @@ __global__ void upsample2x_kernel(const void* __restrict__ in, const float* __re
   const size_t in_plane = (size_t)n * h * w * c8 * 8, out_plane = in_plane * 4;
   const int ys[3] = {max(y - 1, 0), y, min(y + 1, h - 1)};
   const int xs[3] = {max(x - 1, 0), x, min(x + 1, w - 1)};
-  float8 v[3][3];
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int b = 0; b < 3; ++b)
-      v[a][b] = act_ld8<SPLIT>(in, (((size_t)img * h + ys[a]) * w + xs[b]) * c8 * 8 + (size_t)c * 8, in_plane);
+  float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
   if (img_bias) {
     const float4* bp = reinterpret_cast<const float4*>(img_bias) + ((size_t)img * c8 + c) * 2;
-    float4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-      for (int b = 0; b < 3; ++b) {
-        v[a][b].a.x += b0.x; v[a][b].a.y += b0.y; v[a][b].a.z += b0.z; v[a][b].a.w += b0.w;
-        v[a][b].b.x += b1.x; v[a][b].b.y += b1.y; v[a][b].b.z += b1.z; v[a][b].b.w += b1.w;
-      }
+    b0 = __ldg(bp); b1 = __ldg(bp + 1);
   }
+  auto load_row = [&](int a, float8* row) {
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      row[b] = act_ld8<SPLIT>(in, (((size_t)img * h + ys[a]) * w + xs[b]) * c8 * 8 + (size_t)c * 8, in_plane);
+      if (img_bias) {
+        row[b].a.x += b0.x; row[b].a.y += b0.y; row[b].a.z += b0.z; row[b].a.w += b0.w;
+        row[b].b.x += b1.x; row[b].b.y += b1.y; row[b].b.z += b1.z; row[b].b.w += b1.w;
+      }
+    }
+  };
   // Output row 2y+dy blends source rows (dy, dy+1) of the clamped 3x3 block; same for columns.
   // dy = 0: rows (y-1, y) weighted (0.25, 0.75); at the top border both are row 0 and the weights
   // become (0, 1) so the value is exact, like ATen's lambda = 0.  dy = 1: rows (y, y+1) with (0.75, 0.25).
+  // Two source rows are live at a time (the third replaces the first): 48 instead of 72 data registers.
+  float8 ra[3], rb[3];
+  load_row(0, ra);
+  load_row(1, rb);
 #pragma unroll
   for (int dy = 0; dy < 2; ++dy) {
+    if (dy == 1) load_row(2, ra);                  // rows (1, 2): rb is the upper one now
+    const float8* up = dy == 0 ? ra : rb;
+    const float8* dn = dy == 0 ? rb : ra;
     const float h1 = dy == 0 ? (y == 0 ? 1.f : 0.75f) : 0.25f, h0 = 1.f - h1;
 #pragma unroll
     for (int dx = 0; dx < 2; ++dx) {
       const float w1 = dx == 0 ? (x == 0 ? 1.f : 0.75f) : 0.25f, w0 = 1.f - w1;
-      const float8 &A = v[dy][dx], &B = v[dy][dx + 1], &Cc = v[dy + 1][dx], &D = v[dy + 1][dx + 1];
+      const float8 &A = up[dx], &B = up[dx + 1], &Cc = dn[dx], &D = dn[dx + 1];
 #define OFB_UP(f) (h0 * (w0 * A.f + w1 * B.f) + h1 * (w0 * Cc.f + w1 * D.f))
       float8 o;
       o.a = make_float4(OFB_UP(a.x), OFB_UP(a.y), OFB_UP(a.z), OFB_UP(a.w));
@@ -194,9 +224,15 @@ __global__ void upsample2x_kernel(const void* __restrict__ in, const float* __re
 }
 
 // ---------------------------------------------------------------- point embed
-// 16 threads per pixel: lane g of the group evaluates hidden unit g once, the group exchanges
-// the 16 hidden values by shuffle, then each lane produces 4 of the 64 output channels with the
-// second-layer weights staged k-major in shared memory.  Bound by its 256 B/pixel store.
+// Thread = 4 pixels x 8 of the 64 output channels.  The work per pixel is a 16 x 64 matrix-vector product whose
+// operand (the second-layer weights, shared memory) must be re-read for every pixel: with one pixel per thread the
+// kernel is bound by the shared-memory pipe (measured: 85 % LSU wavefront utilisation at a quarter of the HBM rate).
+// Four pixels per thread reuse every 16-byte weight load for 4 x 4 FMAs; the 16 hidden units of a pixel (<= 5 inputs
+// each, uniform weights = broadcast loads) are recomputed by the 8 threads that share the pixel, which is cheaper
+// than exchanging them.  A warp covers 16 consecutive pixels: every base load / result store instruction moves four
+// whole 256-byte pixel vectors.  Accumulation order as in the reference's conv: c, then k ascending.
+constexpr int PE_PIX = 4;
+
 template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 point_embed_kernel(const float* __restrict__ pts, int N, int cin, int p,
@@ -206,48 +242,77 @@ point_embed_kernel(const float* __restrict__ pts, int N, int cin, int p,
                                    const float* __restrict__ s2, const float* __restrict__ t2,
                                    const void* __restrict__ base, void* __restrict__ out) {
   __shared__ __align__(16) float w2s[16][64];
+  __shared__ __align__(16) float w1s[16][8];       // [k][c0..c4, scale, shift, -]
   for (int i = threadIdx.x; i < 1024; i += 256) w2s[i & 15][i >> 4] = __ldg(&w2[i]);   // w2 is [co][k]
+  if (threadIdx.x < 128) {
+    const int k = threadIdx.x >> 3, c = threadIdx.x & 7;
+    w1s[k][c] = c < cin ? __ldg(&w1[k * cin + c]) : (c == 5 ? __ldg(&s1[k]) : (c == 6 ? __ldg(&t1[k]) : 0.f));
+  }
   __syncthreads();
-  const size_t total = (size_t)imgs * p * p * 16;
-  const size_t plane = (size_t)imgs * p * p * 64;
-  const float s1g = __ldg(&s1[threadIdx.x & 15]), t1g = __ldg(&t1[threadIdx.x & 15]);
-  const float4 sc = __ldg(reinterpret_cast<const float4*>(s2 + (threadIdx.x & 15) * 4));
-  const float4 sh = __ldg(reinterpret_cast<const float4*>(t2 + (threadIdx.x & 15) * 4));
-  // grid-stride over 16-pixel groups: the 4 KB weight stage above is paid once per CTA, not once per 16 pixels
-  for (size_t i0 = blockIdx.x * (size_t)blockDim.x; i0 < total; i0 += gridDim.x * (size_t)blockDim.x) {
-    size_t i = i0 + threadIdx.x;
-    const bool live = i < total;
-    if (!live) i = total - 1;
-    const int g = (int)(i & 15);
-    const size_t pix = i >> 4;
-    const uint32_t pp = (uint32_t)(p * p), pix32 = (uint32_t)pix;     // 32-bit div/mod (host checks the range)
-    const int xy = (int)(pix32 % pp);
-    const int img = (int)(pix32 / pp);
-    const int n = img % N;
-    const float dsc = depth ? __ldg(&depth[pix]) : 1.f;
-    float a = 0.f;
-    for (int c = 0; c < cin; ++c) {
-      float v = __ldg(&pts[((size_t)n * cin + c) * p * p + xy]);
-      if (depth && c < 3) v *= dsc;
-      a += v * __ldg(&w1[g * cin + c]);
-    }
-    const float hid = fmaxf(a * s1g + t1g, 0.f);
-    float o[4] = {0.f, 0.f, 0.f, 0.f};
+  const uint32_t npix = (uint32_t)imgs * p * p;             // 32-bit index arithmetic (the host checks the range)
+  const size_t plane = (size_t)npix * 64;
+  const int g = threadIdx.x & 7, sub = (threadIdx.x & 31) >> 3;
+  float sc[8], sh[8];
 #pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = __ldg(&s2[g * 8 + j]); sh[j] = __ldg(&t2[g * 8 + j]); }
+  const uint32_t pp = (uint32_t)(p * p);
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5, warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  for (uint32_t blk = warp0; blk * (4 * PE_PIX) < npix; blk += warps) {       // 16 pixels per warp and step
+    float v[PE_PIX][5];
+    uint32_t pix[PE_PIX];
+#pragma unroll
+    for (int q = 0; q < PE_PIX; ++q) {
+      pix[q] = blk * (4 * PE_PIX) + q * 4 + sub;
+      const uint32_t pc = min(pix[q], npix - 1);
+      const int xy = (int)(pc % pp);
+      const int n = (int)((pc / pp) % (uint32_t)N);
+      const float dsc = depth ? __ldg(&depth[pc]) : 1.f;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        v[q][c] = c < cin ? __ldg(&pts[((size_t)n * cin + c) * pp + xy]) : 0.f;
+        if (depth && c < 3) v[q][c] *= dsc;
+      }
+    }
+    float o[PE_PIX][8];
+#pragma unroll
+    for (int q = 0; q < PE_PIX; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[q][j] = 0.f;
+#pragma unroll 4
     for (int k = 0; k < 16; ++k) {
-      const float hk = __shfl_sync(0xffffffffu, hid, k, 16);
-      const float4 w = *reinterpret_cast<const float4*>(&w2s[k][g * 4]);
-      o[0] += hk * w.x; o[1] += hk * w.y; o[2] += hk * w.z; o[3] += hk * w.w;
+      const float4 wl = *reinterpret_cast<const float4*>(&w1s[k][0]);
+      const float4 wh = *reinterpret_cast<const float4*>(&w1s[k][4]);      // c4, scale, shift
+      const float4 wa = *reinterpret_cast<const float4*>(&w2s[k][g * 8]);
+      const float4 wb = *reinterpret_cast<const float4*>(&w2s[k][g * 8 + 4]);
+#pragma unroll
+      for (int q = 0; q < PE_PIX; ++q) {
+        float a = 0.f;
+        a += v[q][0] * wl.x;
+        if (cin > 1) a += v[q][1] * wl.y;
+        if (cin > 2) a += v[q][2] * wl.z;
+        if (cin > 3) a += v[q][3] * wl.w;
+        if (cin > 4) a += v[q][4] * wh.x;
+        const float hk = fmaxf(a * wh.y + wh.z, 0.f);
+        o[q][0] += hk * wa.x; o[q][1] += hk * wa.y; o[q][2] += hk * wa.z; o[q][3] += hk * wa.w;
+        o[q][4] += hk * wb.x; o[q][5] += hk * wb.y; o[q][6] += hk * wb.z; o[q][7] += hk * wb.w;
+      }
     }
-    if (!live) continue;
-    float4 v = make_float4(fmaxf(o[0] * sc.x + sh.x, 0.f), fmaxf(o[1] * sc.y + sh.y, 0.f),
-                           fmaxf(o[2] * sc.z + sh.z, 0.f), fmaxf(o[3] * sc.w + sh.w, 0.f));
-    const size_t off = pix * 64 + g * 4;
-    if (base) {
-      const float4 b = act_ld4<SPLIT>(base, off, plane);
-      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+#pragma unroll
+    for (int q = 0; q < PE_PIX; ++q) {
+      if (pix[q] >= npix) continue;
+      float8 r;
+      r.a = make_float4(fmaxf(o[q][0] * sc[0] + sh[0], 0.f), fmaxf(o[q][1] * sc[1] + sh[1], 0.f),
+                        fmaxf(o[q][2] * sc[2] + sh[2], 0.f), fmaxf(o[q][3] * sc[3] + sh[3], 0.f));
+      r.b = make_float4(fmaxf(o[q][4] * sc[4] + sh[4], 0.f), fmaxf(o[q][5] * sc[5] + sh[5], 0.f),
+                        fmaxf(o[q][6] * sc[6] + sh[6], 0.f), fmaxf(o[q][7] * sc[7] + sh[7], 0.f));
+      const size_t off = (size_t)pix[q] * 64 + g * 8;
+      if (base) {
+        const float8 bb = act_ld8<SPLIT>(base, off, plane);
+        r.a.x += bb.a.x; r.a.y += bb.a.y; r.a.z += bb.a.z; r.a.w += bb.a.w;
+        r.b.x += bb.b.x; r.b.y += bb.b.y; r.b.z += bb.b.z; r.b.w += bb.b.w;
+      }
+      act_st8<SPLIT>(out, off, plane, r);
     }
-    act_st4<SPLIT>(out, off, plane, v);
   }
 }
 
@@ -569,11 +634,15 @@ extern "C" int ofb_stem_f32(const float* in, int n, int h, int w, const float* w
 }
 
 extern "C" int ofb_maxpool3x3s2_f32(const void* in, int n, int h, int w, int c, void* out, int fmt, void* stream) {
-  OFB_CHECK(in && out && c % 4 == 0 && h % 2 == 0 && w % 2 == 0 && OFB_FMT_OK(fmt), "maxpool: bad arguments");
-  size_t total = (size_t)n * (h / 2) * (w / 2) * (c / 4);
-  OFB_CHECK(total < (1ull << 31), "maxpool: %zu output vectors exceed the 32-bit index range (process fewer images per call)", total);
-  if (fmt) maxpool_kernel<true><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, n, h, w, c / 4, out);
-  else maxpool_kernel<false><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, n, h, w, c / 4, out);
+  OFB_CHECK(in && out && c % 8 == 0 && h % 2 == 0 && w % 2 == 0 && OFB_FMT_OK(fmt), "maxpool: bad arguments (c %% 8, even h and w)");
+  // bands of output rows per image: enough threads to fill the GPU (>= ~8 warps per SM), at least 4 rows per band
+  const int oh_n = h / 2;
+  int bands = 1;
+  while (bands * 2 <= oh_n / 4 && (size_t)n * bands * (w / 2) * (c / 8) < (size_t)148 * 2048) bands *= 2;
+  size_t total = (size_t)n * bands * (w / 2) * (c / 8);
+  OFB_CHECK((size_t)n * h * w * (c / 8) < (1ull << 31), "maxpool: input exceeds the 32-bit index range (process fewer images per call)");
+  if (fmt) maxpool_kernel<true><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, n, h, w, c / 8, bands, out);
+  else maxpool_kernel<false><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, n, h, w, c / 8, bands, out);
   OFB_LAUNCH_CHECK();
   return 0;
 }
@@ -596,8 +665,9 @@ extern "C" int ofb_point_embed_f32(const float* pts, int N, int cin, int p, cons
   OFB_CHECK(pts && w1 && s1 && t1 && w2 && s2 && t2 && out && OFB_FMT_OK(fmt), "point_embed: bad arguments");
   OFB_CHECK(cin >= 1 && cin <= 5, "point_embed: cin must be <= 5 (got %d)", cin);
   OFB_CHECK((size_t)imgs * p * p < (1ull << 31), "point_embed: too many pixels for the 32-bit index range");
-  size_t total = (size_t)imgs * p * p * 16;
-  const int blocks = (int)(cdiv(total, 256) < 148 * 8 ? cdiv(total, 256) : 148 * 8);
+  size_t total = (size_t)imgs * p * p * 8 / PE_PIX;         // threads: 8 per group of PE_PIX pixels
+  // persistent CTAs (two per SM at this register count): the 4.5 KB weight stage is paid once per CTA
+  const int blocks = (int)(cdiv(total, 256) < 148 * 2 ? (cdiv(total, 256) > 0 ? cdiv(total, 256) : 1) : 148 * 2);
   if (fmt) point_embed_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(pts, N, cin, p, depth, imgs, w1, s1, t1, w2, s2, t2, base, out);
   else point_embed_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(pts, N, cin, p, depth, imgs, w1, s1, t1, w2, s2, t2, base, out);
   OFB_LAUNCH_CHECK();

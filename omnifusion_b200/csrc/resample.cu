@@ -58,9 +58,15 @@ __global__ void e2p_ref_kernel(const float* __restrict__ erp, const float2* __re
     out[(size_t)bc * total + s] = e2p_sample(erp + bc * plane, t, He, We);
 }
 
-// FOLDED layout: out[b*N+n][i][j][Cpad].  One thread per (n,i,j).
+// FOLDED layout: out[b*N+n][i][j][Cpad].  One thread per (n,i,j) and chunk of E2P_EB panoramas (blockIdx.y): the
+// sampling grid entry and the tap arithmetic live in registers and are reused for every panorama / channel of the
+// chunk, whose 4 * C * E2P_EB gathers are all independent and in flight together.  (A thread used to walk the whole
+// batch: one wave of long-running CTAs, half of the SMs idle behind the slow polar patches.)
+constexpr int E2P_EB = 2;
+
 template <int C>
-__global__ void e2p_folded_kernel(const float* __restrict__ erp, const float2* __restrict__ grid,
+__global__ void __launch_bounds__(256)
+e2p_folded_kernel(const float* __restrict__ erp, const float2* __restrict__ grid,
                                   float* __restrict__ out, int B, int He, int We, int N, int Ph,
                                   int Pw) {
   int total = N * Ph * Pw;
@@ -69,7 +75,11 @@ __global__ void e2p_folded_kernel(const float* __restrict__ erp, const float2* _
   float2 g = __ldg(&grid[s]);
   E2PTaps t = e2p_taps(g.x, g.y, He, We);
   size_t plane = (size_t)He * We;
-  for (int b = 0; b < B; ++b) {
+  const int b0 = blockIdx.y * E2P_EB;
+#pragma unroll
+  for (int k = 0; k < E2P_EB; ++k) {
+    const int b = b0 + k;
+    if (b >= B) break;
     const float* img = erp + (size_t)b * C * plane;
     if (C == 3) {
       float4 v;
@@ -86,7 +96,8 @@ __global__ void e2p_folded_kernel(const float* __restrict__ erp, const float2* _
 }
 
 // STEM16 layout: split-half planes of (B*N, Ph, Pw+8, 4); the 4-pixel row pads are never written.
-__global__ void e2p_stem16_kernel(const float* __restrict__ erp, const float2* __restrict__ grid,
+__global__ void __launch_bounds__(256)
+e2p_stem16_kernel(const float* __restrict__ erp, const float2* __restrict__ grid,
                                   __half* __restrict__ out, int B, int He, int We, int N, int Ph, int Pw) {
   int total = N * Ph * Pw;
   int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -97,15 +108,22 @@ __global__ void e2p_stem16_kernel(const float* __restrict__ erp, const float2* _
   int j = s % Pw, ni = s / Pw;                       // ni = n*Ph + i
   const int pitch = Pw + 8;
   const size_t out_plane = (size_t)B * N * Ph * pitch * 4;
-  for (int b = 0; b < B; ++b) {
-    const float* img = erp + (size_t)b * 3 * plane;
-    float4 v;
-    v.x = e2p_sample(img, t, He, We);
-    v.y = e2p_sample(img + plane, t, He, We);
-    v.z = e2p_sample(img + 2 * plane, t, He, We);
-    v.w = 0.f;
+  const int b0 = blockIdx.y * E2P_EB;
+  float4 v[E2P_EB];
+#pragma unroll
+  for (int k = 0; k < E2P_EB; ++k) {                 // all gathers of the chunk first ...
+    const float* img = erp + (size_t)min(b0 + k, B - 1) * 3 * plane;
+    v[k].x = e2p_sample(img, t, He, We);
+    v[k].y = e2p_sample(img + plane, t, He, We);
+    v[k].z = e2p_sample(img + 2 * plane, t, He, We);
+    v[k].w = 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < E2P_EB; ++k) {                 // ... then the stores
+    const int b = b0 + k;
+    if (b >= B) break;
     size_t o = (((size_t)b * N * Ph + ni) * pitch + 4 + j) * 4;
-    act_st4<true>(out, o, out_plane, v);
+    act_st4<true>(out, o, out_plane, v[k]);
   }
 }
 
@@ -132,81 +150,139 @@ __device__ __forceinline__ void p2e_decode(uint32_t id, int& n, int& y0, int& x0
   dx = id & 1;
 }
 
-// One thread per ERP pixel, PL (b,c) planes per thread in registers so a table row is
-// read once per PL planes.  Tap/weight order follows pers2equi_v3.py:174-177,194-196.
-template <int PL>
-__global__ void p2e_kernel(const float* __restrict__ pers, const int32_t* __restrict__ rowptr,
-                           const uint32_t* __restrict__ idx, const float4* __restrict__ w,
-                           float* __restrict__ out, int npix, int B, int C, P2EStrides st) {
-  int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= npix) return;
-  int plane0 = blockIdx.y * PL;
-  int planes = B * C;
-  const float* base[PL];
-#pragma unroll
-  for (int k = 0; k < PL; ++k) {
-    int q = min(plane0 + k, planes - 1);
-    base[k] = pers + (q / C) * st.sb + (q % C) * st.sc;
+// Both blend kernels share one structure.  A CTA owns BL_TILE consecutive ERP pixels (thread = pixel).  Their CSR
+// rows are one contiguous range of the table, so the CTA copies that range - packed tap indices and pre-normalised
+// weight vectors, 20 bytes per (pixel, covering patch) - into shared memory ONCE with fully coalesced loads, and
+// then walks the whole batch reading the table from shared memory: per panorama only the 2x2 tap gathers touch
+// global memory.  (Before: every thread walked its own row in global memory, once per group of four panoramas -
+// three dependent global round trips per entry and the table re-fetched B/4 times.)  PL panoramas are gathered
+// together so 4*PL (8*PL) independent loads are in flight per table entry.  Entries beyond the staged capacity
+// (only possible where one tile is covered by very many patches) are read from global memory.
+// Tap/weight order follows pers2equi_v3.py:174-177,194-196.
+constexpr int BL_TILE = 256;
+constexpr int BL_CAP = 2048;          // staged entries: 8 KB of indices + 32 KB of weights
+
+struct BlendStage {
+  uint32_t idx[BL_CAP];
+  float4 w[BL_CAP];
+  int row[BL_TILE + 1];
+};
+
+// returns false for threads beyond the last pixel; beg/end are relative to e0
+__device__ __forceinline__ bool blend_stage(BlendStage& st, const int32_t* __restrict__ rowptr,
+                                            const uint32_t* __restrict__ idx, const float4* __restrict__ w, int npix,
+                                            int& e0, int& beg, int& end) {
+  const int t = threadIdx.x, p0 = blockIdx.x * BL_TILE;
+  st.row[t] = __ldg(&rowptr[min(p0 + t, npix)]);
+  if (t == 0) st.row[BL_TILE] = __ldg(&rowptr[min(p0 + BL_TILE, npix)]);
+  __syncthreads();
+  e0 = st.row[0];
+  const int cnt = min(st.row[BL_TILE] - e0, BL_CAP);
+  for (int i = t; i < cnt; i += BL_TILE) {
+    st.idx[i] = __ldg(&idx[e0 + i]);
+    st.w[i] = __ldg(&w[e0 + i]);
   }
-  float acc[PL];
-#pragma unroll
-  for (int k = 0; k < PL; ++k) acc[k] = 0.f;
-  int beg = __ldg(&rowptr[pix]), end = __ldg(&rowptr[pix + 1]);
-  for (int e = beg; e < end; ++e) {
-    int n, y0, x0, dy, dx;
-    p2e_decode(__ldg(&idx[e]), n, y0, x0, dy, dx);
-    float4 ww = __ldg(&w[e]);
-    long long o00 = y0 * st.sy + x0 * st.sx + n * st.sn;
-    long long oy = dy * st.sy, ox = dx * st.sx;
-#pragma unroll
-    for (int k = 0; k < PL; ++k) {
-      const float* p = base[k] + o00;
-      float a = __ldg(p), b = __ldg(p + oy), c = __ldg(p + ox), d = __ldg(p + oy + ox);
-      acc[k] += a * ww.x + b * ww.y + c * ww.z + d * ww.w;
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < PL; ++k)
-    if (plane0 + k < planes) out[(size_t)(plane0 + k) * npix + pix] = acc[k];
+  __syncthreads();
+  beg = st.row[t] - e0;
+  end = st.row[t + 1] - e0;
+  return p0 + t < npix;
 }
 
-// Fused confidence merge (spherical_model_iterative.py:372-378): blends pred*w and w
-// with the same table walk and divides.
 template <int PL>
-__global__ void blend_conf_kernel(const float* __restrict__ pred, const float* __restrict__ conf,
-                                  const int32_t* __restrict__ rowptr,
-                                  const uint32_t* __restrict__ idx, const float4* __restrict__ w,
-                                  float* __restrict__ out, int npix, int B, int N, int Ph, int Pw) {
-  int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= npix) return;
-  int b0 = blockIdx.y * PL;
-  float accD[PL], accW[PL];
-#pragma unroll
-  for (int k = 0; k < PL; ++k) accD[k] = accW[k] = 0.f;
-  size_t img = (size_t)Ph * Pw;
-  int beg = __ldg(&rowptr[pix]), end = __ldg(&rowptr[pix + 1]);
-  for (int e = beg; e < end; ++e) {
-    int n, y0, x0, dy, dx;
-    p2e_decode(__ldg(&idx[e]), n, y0, x0, dy, dx);
-    float4 ww = __ldg(&w[e]);
-    size_t o00 = (size_t)n * img + y0 * Pw + x0;
-    int oy = dy * Pw, ox = dx;
+__global__ void __launch_bounds__(BL_TILE)
+p2e_kernel(const float* __restrict__ pers, const int32_t* __restrict__ rowptr, const uint32_t* __restrict__ idx,
+           const float4* __restrict__ w, float* __restrict__ out, int npix, int B, int C, P2EStrides st) {
+  __shared__ BlendStage sm;
+  int e0, beg, end;
+  if (!blend_stage(sm, rowptr, idx, w, npix, e0, beg, end)) return;
+  const int pix = blockIdx.x * BL_TILE + threadIdx.x;
+  const int planes = B * C;
+  for (int plane0 = 0; plane0 < planes; plane0 += PL) {
+    const float* base[PL];
 #pragma unroll
     for (int k = 0; k < PL; ++k) {
-      int b = min(b0 + k, B - 1);
-      const float* p = pred + (size_t)b * N * img + o00;
-      const float* q = conf + (size_t)b * N * img + o00;
-      accD[k] += __ldg(p) * ww.x + __ldg(p + oy) * ww.y + __ldg(p + ox) * ww.z + __ldg(p + oy + ox) * ww.w;
-      accW[k] += __ldg(q) * ww.x + __ldg(q + oy) * ww.y + __ldg(q + ox) * ww.z + __ldg(q + oy + ox) * ww.w;
+      const int q = min(plane0 + k, planes - 1);
+      base[k] = pers + (q / C) * st.sb + (q % C) * st.sc;
     }
-  }
+    float acc[PL];
 #pragma unroll
-  for (int k = 0; k < PL; ++k)
-    if (b0 + k < B) {
-      float W = accW[k];
-      float zero = (W <= 1e-8f) ? 1.f : 0.f;
-      out[(size_t)(b0 + k) * npix + pix] = accD[k] / (W + 1e-8f * zero);
+    for (int k = 0; k < PL; ++k) acc[k] = 0.f;
+    for (int e = beg; e < end; ++e) {
+      int n, y0, x0, dy, dx;
+      const bool staged = e < BL_CAP;
+      p2e_decode(staged ? sm.idx[e] : __ldg(&idx[e0 + e]), n, y0, x0, dy, dx);
+      const float4 ww = staged ? sm.w[e] : __ldg(&w[e0 + e]);
+      const long long o00 = y0 * st.sy + x0 * st.sx + n * st.sn;
+      const long long oy = dy * st.sy, ox = dx * st.sx;
+#pragma unroll
+      for (int k = 0; k < PL; ++k) {
+        const float* p = base[k] + o00;
+        const float a = __ldg(p), b = __ldg(p + oy), c = __ldg(p + ox), d = __ldg(p + oy + ox);
+        acc[k] += a * ww.x + b * ww.y + c * ww.z + d * ww.w;
+      }
     }
+#pragma unroll
+    for (int k = 0; k < PL; ++k)
+      if (plane0 + k < planes) out[(size_t)(plane0 + k) * npix + pix] = acc[k];
+  }
+}
+
+// Fused confidence merge (spherical_model_iterative.py:372-378): blends pred*w and w with the same table walk and
+// divides.  IL: the two patch maps arrive interleaved per pixel, (pred*w, w) as one float2 (the layout the
+// tensor-core heads kernel writes), so every tap is ONE 8-byte load instead of two 4-byte loads from two arrays.
+template <int PL, bool IL>
+__global__ void __launch_bounds__(BL_TILE)
+blend_conf_kernel(const float* __restrict__ pred, const float* __restrict__ conf, const int32_t* __restrict__ rowptr,
+                  const uint32_t* __restrict__ idx, const float4* __restrict__ w, float* __restrict__ out, int npix,
+                  int B, int N, int Ph, int Pw) {
+  __shared__ BlendStage sm;
+  int e0, beg, end;
+  if (!blend_stage(sm, rowptr, idx, w, npix, e0, beg, end)) return;
+  const int pix = blockIdx.x * BL_TILE + threadIdx.x;
+  const size_t img = (size_t)Ph * Pw;
+  const float2* pc = reinterpret_cast<const float2*>(pred);
+  for (int b0 = 0; b0 < B; b0 += PL) {
+    float accD[PL], accW[PL];
+#pragma unroll
+    for (int k = 0; k < PL; ++k) accD[k] = accW[k] = 0.f;
+    for (int e = beg; e < end; ++e) {
+      int n, y0, x0, dy, dx;
+      const bool staged = e < BL_CAP;
+      p2e_decode(staged ? sm.idx[e] : __ldg(&idx[e0 + e]), n, y0, x0, dy, dx);
+      const float4 ww = staged ? sm.w[e] : __ldg(&w[e0 + e]);
+      const size_t o00 = (size_t)n * img + y0 * Pw + x0;
+      const int oy = dy * Pw, ox = dx;
+#pragma unroll
+      for (int k = 0; k < PL; ++k) {
+        const size_t o = (size_t)min(b0 + k, B - 1) * N * img + o00;
+        if (IL) {
+          const float2 a = __ldg(pc + o), b = __ldg(pc + o + oy), c = __ldg(pc + o + ox), d = __ldg(pc + o + oy + ox);
+          accD[k] += a.x * ww.x + b.x * ww.y + c.x * ww.z + d.x * ww.w;
+          accW[k] += a.y * ww.x + b.y * ww.y + c.y * ww.z + d.y * ww.w;
+        } else {
+          const float* p = pred + o;
+          const float* q = conf + o;
+          accD[k] += __ldg(p) * ww.x + __ldg(p + oy) * ww.y + __ldg(p + ox) * ww.z + __ldg(p + oy + ox) * ww.w;
+          accW[k] += __ldg(q) * ww.x + __ldg(q + oy) * ww.y + __ldg(q + ox) * ww.z + __ldg(q + oy + ox) * ww.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < PL; ++k)
+      if (b0 + k < B) {
+        const float W = accW[k];
+        const float zero = (W <= 1e-8f) ? 1.f : 0.f;
+        out[(size_t)(b0 + k) * npix + pix] = accD[k] / (W + 1e-8f * zero);
+      }
+  }
+}
+
+// component `comp` of an interleaved pair map -> contiguous (debug / test read-back of the engine's head outputs)
+__global__ void deinterleave_kernel(const float2* __restrict__ src, size_t n, int comp, float* __restrict__ dst) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float2 v = src[i];
+  dst[i] = comp ? v.y : v.x;
 }
 
 // ------------------------------------------------------------------- abs-rel
@@ -327,12 +403,14 @@ extern "C" int ofb_equi2pers_f32(const float* erp, int B, int C, int He, int We,
   if (layout == OFB_LAYOUT_REF) {
     e2p_ref_kernel<<<blocks, thr, 0, s>>>(erp, g, out, B, C, He, We, N, Ph, Pw);
   } else if (layout == OFB_LAYOUT_FOLDED) {
-    if (C == 3) e2p_folded_kernel<3><<<blocks, thr, 0, s>>>(erp, g, out, B, He, We, N, Ph, Pw);
-    else if (C == 1) e2p_folded_kernel<1><<<blocks, thr, 0, s>>>(erp, g, out, B, He, We, N, Ph, Pw);
+    const dim3 grd(blocks, cdiv(B, E2P_EB));
+    if (C == 3) e2p_folded_kernel<3><<<grd, thr, 0, s>>>(erp, g, out, B, He, We, N, Ph, Pw);
+    else if (C == 1) e2p_folded_kernel<1><<<grd, thr, 0, s>>>(erp, g, out, B, He, We, N, Ph, Pw);
     else OFB_CHECK(false, "equi2pers: folded layout supports C in {1,3}, got %d", C);
   } else if (layout == OFB_LAYOUT_STEM16) {
     OFB_CHECK(C == 3, "equi2pers: the stem layout needs C == 3, got %d", C);
-    e2p_stem16_kernel<<<blocks, thr, 0, s>>>(erp, g, reinterpret_cast<__half*>(out), B, He, We, N, Ph, Pw);
+    const dim3 grd(blocks, cdiv(B, E2P_EB));
+    e2p_stem16_kernel<<<grd, thr, 0, s>>>(erp, g, reinterpret_cast<__half*>(out), B, He, We, N, Ph, Pw);
   } else {
     OFB_CHECK(false, "equi2pers: unknown layout %d", layout);
   }
@@ -363,41 +441,54 @@ extern "C" int ofb_pers2equi_f32(const float* pers, int B, int C, int N, int Ph,
   } else {
     OFB_CHECK(false, "pers2equi: unknown layout %d", layout);
   }
-  int npix = He * We, planes = B * C;
+  const int npix = He * We, planes = B * C;
   const float4* w4 = reinterpret_cast<const float4*>(w);
   cudaStream_t s = (cudaStream_t)stream;
-  int thr = 128;
-  if (planes >= 8) {
-    dim3 g(cdiv(npix, thr), cdiv(planes, 8));
-    p2e_kernel<8><<<g, thr, 0, s>>>(pers, rowptr, idx, w4, out, npix, B, C, st);
-  } else if (planes >= 3) {
-    dim3 g(cdiv(npix, thr), cdiv(planes, 4));
-    p2e_kernel<4><<<g, thr, 0, s>>>(pers, rowptr, idx, w4, out, npix, B, C, st);
+  const int grid = cdiv(npix, BL_TILE);
+  if (planes >= 4) p2e_kernel<4><<<grid, BL_TILE, 0, s>>>(pers, rowptr, idx, w4, out, npix, B, C, st);
+  else if (planes >= 2) p2e_kernel<2><<<grid, BL_TILE, 0, s>>>(pers, rowptr, idx, w4, out, npix, B, C, st);
+  else p2e_kernel<1><<<grid, BL_TILE, 0, s>>>(pers, rowptr, idx, w4, out, npix, B, C, st);
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+
+namespace ofb {
+int blend_conf_launch(const float* pred_w, const float* conf, bool interleaved, int B, int N, int Ph, int Pw,
+                      const int32_t* rowptr, const uint32_t* idx, const float* w, int He, int We, float* out,
+                      cudaStream_t s) {
+  const int npix = He * We;
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  const int grid = cdiv(npix, BL_TILE);
+  if (interleaved) {
+    if (B >= 4) blend_conf_kernel<4, true><<<grid, BL_TILE, 0, s>>>(pred_w, nullptr, rowptr, idx, w4, out, npix, B, N, Ph, Pw);
+    else blend_conf_kernel<1, true><<<grid, BL_TILE, 0, s>>>(pred_w, nullptr, rowptr, idx, w4, out, npix, B, N, Ph, Pw);
   } else {
-    dim3 g(cdiv(npix, thr), planes);
-    p2e_kernel<1><<<g, thr, 0, s>>>(pers, rowptr, idx, w4, out, npix, B, C, st);
+    if (B >= 4) blend_conf_kernel<4, false><<<grid, BL_TILE, 0, s>>>(pred_w, conf, rowptr, idx, w4, out, npix, B, N, Ph, Pw);
+    else blend_conf_kernel<1, false><<<grid, BL_TILE, 0, s>>>(pred_w, conf, rowptr, idx, w4, out, npix, B, N, Ph, Pw);
   }
   OFB_LAUNCH_CHECK();
   return 0;
 }
+int deinterleave_launch(const float* src_pairs, size_t n, int comp, float* dst, cudaStream_t s) {
+  deinterleave_kernel<<<cdiv((long long)n, 256), 256, 0, s>>>(reinterpret_cast<const float2*>(src_pairs), n, comp, dst);
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace ofb
 
 extern "C" int ofb_blend_conf_f32(const float* pred_w, const float* conf, int B, int N, int Ph, int Pw,
                                   const int32_t* rowptr, const uint32_t* idx, const float* w, int He,
                                   int We, float* out, void* stream) {
   OFB_CHECK(pred_w && conf && rowptr && idx && w && out, "blend_conf: null pointer");
-  int npix = He * We;
-  const float4* w4 = reinterpret_cast<const float4*>(w);
-  cudaStream_t s = (cudaStream_t)stream;
-  int thr = 128;
-  if (B >= 4) {
-    dim3 g(cdiv(npix, thr), cdiv(B, 4));
-    blend_conf_kernel<4><<<g, thr, 0, s>>>(pred_w, conf, rowptr, idx, w4, out, npix, B, N, Ph, Pw);
-  } else {
-    dim3 g(cdiv(npix, thr), B);
-    blend_conf_kernel<1><<<g, thr, 0, s>>>(pred_w, conf, rowptr, idx, w4, out, npix, B, N, Ph, Pw);
-  }
-  OFB_LAUNCH_CHECK();
-  return 0;
+  return blend_conf_launch(pred_w, conf, false, B, N, Ph, Pw, rowptr, idx, w, He, We, out, (cudaStream_t)stream);
+}
+
+extern "C" int ofb_blend_conf_pairs_f32(const float* pred_conf, int B, int N, int Ph, int Pw, const int32_t* rowptr,
+                                        const uint32_t* idx, const float* w, int He, int We, float* out,
+                                        void* stream) {
+  OFB_CHECK(pred_conf && rowptr && idx && w && out, "blend_conf_pairs: null pointer");
+  OFB_CHECK((reinterpret_cast<uintptr_t>(pred_conf) & 7) == 0, "blend_conf_pairs: the pair map must be 8-byte aligned");
+  return blend_conf_launch(pred_conf, nullptr, true, B, N, Ph, Pw, rowptr, idx, w, He, We, out, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------ loader-side input conversion

@@ -238,6 +238,12 @@ def test_heads_on_tensor_cores_match_torch_cpu(n, h, confidence):
     assert (err <= 2e-5 + 2e-5 * want.abs()).all()
     if confidence:
         assert ((gc.cpu() - conf[:, 0]).abs() <= 2e-5).all()
+        # the engine's layout: (pred*conf, conf) interleaved per pixel - must carry exactly the same numbers
+        pairs = torch.full((n, h, 128, 2), -1.0, device=DEV)
+        _lib.check(_lib.lib().ofb_heads_tc_pairs_f16(_lib.ptr(xs), n, h, 128, _lib.ptr(ws), 1.0 / mul, bp, bc,
+                                                      _lib.ptr(pairs), _lib.stream_of(torch.device(DEV))))
+        torch.cuda.synchronize()
+        assert torch.equal(pairs[..., 0], gp) and torch.equal(pairs[..., 1], gc)
     else:
         assert (gc == -1.0).all()          # conf_out untouched
 

@@ -383,3 +383,30 @@ def test_depth_meters_follow_the_reference_average_meters():
     with pytest.raises(ValueError):
         metrics.depth_metrics_partial(torch.zeros(2, 1, 4, 4, device=DEV), torch.zeros(2, 4, 4, device=DEV),
                                       torch.ones(2, 1, 4, 4, device=DEV))
+
+
+@pytest.mark.parametrize("nrows,erp,P,B", [(4, (128, 256), 32, 5), (6, (64, 128), 16, 3), (4, (512, 1024), 128, 2)])
+def test_blend_conf_pair_map_matches_separate_maps_and_oracle(nrows, erp, P, B):
+    """ofb_blend_conf_pairs_f32 (interleaved (pred*conf, conf) map, the engine's hot path) against the two-map kernel
+    (bit-identical: same table walk, same expression) and the oracle; nrows=6 at a tiny ERP makes CSR rows long
+    enough to overflow the shared-memory stage (global-memory fallback for the entries beyond the capacity)."""
+    o = ops()
+    n = tables.NUM_PATCHES[nrows]
+    pred = urand(B * n, P, P, seed=1) * 3
+    conf = urand(B * n, P, P, seed=2)
+    tab = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in tables.blend_table(FOV, nrows, (P, P), erp).items()}
+    sep = o.blend_conf((pred * conf).to(DEV), conf.to(DEV), B, n, tab, *erp)
+    pairs = torch.stack([pred * conf, conf], -1).contiguous().to(DEV)
+    got = torch.empty((B, 1, *erp), device=DEV)
+    _lib.check(_lib.lib().ofb_blend_conf_pairs_f32(_lib.ptr(pairs), B, n, P, P, _lib.ptr(tab["rowptr"]), _lib.ptr(tab["idx"]),
+                                                   _lib.ptr(tab["w"]), erp[0], erp[1], _lib.ptr(got),
+                                                   _lib.stream_of(torch.device(DEV))))
+    torch.cuda.synchronize()
+    assert torch.equal(got, sep)
+    unf = lambda t: t.reshape(B, n, 1, P, P).permute(0, 2, 3, 4, 1)
+    W = oe.pers2equi(unf(conf), FOV, nrows, (P, P), erp)
+    D = oe.pers2equi(unf(pred * conf), FOV, nrows, (P, P), erp)
+    report("blend_conf pairs", got.cpu(), D / (W + 1e-8 * (W <= 1e-8).float()), atol=0, rtol=1e-5)
+    rows = (tab["rowptr"][1:] - tab["rowptr"][:-1]).reshape(-1)
+    print(f"[parity] blend table nrows={nrows} erp={erp}: max entries per 256-pixel tile = "
+          f"{int(rows.cpu().reshape(-1, 256).sum(1).max()) if rows.numel() % 256 == 0 else -1}")
