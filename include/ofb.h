@@ -194,6 +194,12 @@ int ofb_attention_f32(const void* q, const void* kv, int B, int N, int heads, in
 int ofb_attention_qkv_f32(const void* qkv, int B, int N, int heads, int head_dim,
                           void* out, int fmt, void* stream);
 
+/* The same attention core on the tensor pipe (csrc/conv_tc.cu: attention_tc_kernel): qkv_planes = split-half planes
+ * of (B*N, 3*heads*128) = [q | k | v] per row, out_planes = split-half planes of (B*N, heads*128).  One CTA per head
+ * and tile of 128 / N whole panoramas: QK^T and PV as tcgen05 MMAs (three split-half products, fp32 accumulation in
+ * TMEM), softmax per query row out of TMEM.  N <= 64, head_dim == 128. */
+int ofb_attention_tc_f16(const void* qkv_planes, int B, int N, int heads, int head_dim, void* out_planes, void* stream);
+
 /* The same heads on the tensor pipe (split-half format only): x_planes = split-half planes of (imgs,h,128,32),
  * wgt_split = split-half planes of the (16,3,3,32) filter bank [pred; weight_pred; 14 zero rows] scaled by
  * 1 / wgt_unscale (ofb_split_f16).  Rolling-row tcgen05 kernel, see csrc/conv_tc.cu (conv_tc_heads). */
@@ -286,7 +292,7 @@ long long ofb_workspace_generation(ofb_handle* h);
 /* Engine knobs (key, value): "engine" conv engine (OFB_ENGINE_*), "chunk" panoramas per internal chunk
  * (0 = auto), "dedup" reuse of the iteration-invariant stem/layer1 across iterations (default 1), "format"
  * activation storage (OFB_FMT_*), "fuse_ups" fold the last decoder upsample into de_conv4_0 (default 1),
- * "heads_tc" heads on the tensor pipe (default 1), "lanes" 2 = two concurrent half-batches on two streams
+ * "heads_tc" heads on the tensor pipe (default 1), "attn_tc" attention core on the tensor pipe (default 1), "lanes" 2 = two concurrent half-batches on two streams
  * (default 1), "cta2" / "pdl" / "store128" / "fill_div" / "direct32" / "khr_bw" / "khr_row64" tcgen05 launch variants (per handle);
  * "tc_debug" / "dbg_blocks" switch parts of the pipeline OFF for timing experiments (results are wrong). */
 int ofb_set_option(ofb_handle* h, const char* key, int value);
@@ -316,6 +322,7 @@ int64_t ofb_launch_count(int reset);
 /* Timing experiments: copies the clock stamps an epilogue warp of CTA 0 recorded while "tc_debug" & 16
  * was set (512 tiles x 8 int64) to host_dst (tools/probe_tail.py). */
 int ofb_debug_stamps(long long* host_dst);
+int ofb_debug_set(int tc_debug);      /* "tc_debug" for convs launched directly through ofb_conv_f32 */
 /* Timing experiments: with "tc_debug" & 256 CTA 0 of every tcgen05 conv launch records eight %globaltimer stamps
  * (kernel entry, prologue done, producer past its dependency wait, first operands landed, last MMA issued, first
  * accumulator complete, last store issued, kernel end).  Copies up to max_slots x 8 int64 of the launches since the

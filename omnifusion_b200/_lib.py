@@ -65,6 +65,7 @@ _SIGNATURES = {
     "ofb_splitk_finish_ln_f32": (_I, [_P, _I, C.c_float, _P, _P, _I, _I, _P, _P, _P, C.c_float, _P, _I, _P]),
     "ofb_attention_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "ofb_attention_qkv_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _P]),
+    "ofb_attention_tc_f16": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "ofb_heads_tc_f16": (_I, [_P, _I, _I, _I, _P, C.c_float, C.c_float, C.c_float, _I, _P, _P, _P]),
     "ofb_heads_f32": (_I, [_P, _I, _I, _I, _P, C.c_float, _P, C.c_float, _I, _P, _P, _I, _P]),
     "ofb_u8hwc_to_f32chw": (_I, [_P, _I, _I, _I, _I, _P, _P]),
@@ -86,6 +87,7 @@ _SIGNATURES = {
     "ofb_workspace_generation": (C.c_longlong, [_P]),
     "ofb_last_conv_variant": (C.c_char_p, []),
     "ofb_debug_stamps": (_I, [_P]),
+    "ofb_debug_set": (_I, [_I]),
     "ofb_debug_timeline": (_I, [_P, _I]),
     "ofb_profile_enable": (_I, [_P, _I]),
     "ofb_profile_report": (_I, [_P, C.c_char_p, _I]),

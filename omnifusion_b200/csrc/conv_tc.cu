@@ -1023,7 +1023,8 @@ bool conv_tc_supported(const ofb_conv_desc* d) {
 // Launch variants are per engine handle (TcOptions, common.cuh): the engine installs its handle's options for the
 // duration of a forward (TcOptScope); operator calls made directly through the C ABI use the defaults.
 static thread_local const TcOptions* t_opts = nullptr;
-static const TcOptions k_default_opts{};
+static TcOptions k_default_opts{};      // options of operator calls made outside an engine forward
+void conv_tc_default_debug(int v) { k_default_opts.dbg = v; }
 const TcOptions& tc_opts() { return t_opts ? *t_opts : k_default_opts; }
 TcOptScope::TcOptScope(const TcOptions* o) : prev(t_opts) { t_opts = o; }
 TcOptScope::~TcOptScope() { t_opts = prev; }
@@ -1321,6 +1322,298 @@ int stem_tc(const void* patches, int n, int h, int w, const void* wgt_split, flo
     if (make_map(&maps.o[pl], true, 4, (char*)out + (size_t)pl * p.plane * 2, od, ob, 64)) return -1;
   }
   return launch_tc<64, MODE_F16X3, 64, true, false>(maps, p, s);
+}
+
+// ------------------------------------------------------------------ attention on tensor cores
+// Attention core of a Transformer_Block (model/blocks.py:50-62) on tcgen05: softmax(q k^T / sqrt(d)) v per panorama
+// and head, d = 128, N <= 64 tokens per panorama.  One CTA = one head x one ROW TILE of G whole panoramas, each in
+// a SLOT of `slot` = N rounded up to 16 rows (G = 128 / slot: 4 panoramas at N = 18 or 26, 2 at 46): the tile's
+// 128 rows are the M dimension of both GEMMs,
+//   S = Q K^T   (M = 128 query rows, N = 128 key rows, K = 128 dims)
+//   O = P V     (M = 128 query rows, N = 128 dims,     K = 128 keys)
+// i.e. all pairs of tokens of the tile are scored at once and the softmax keeps only the block of a row's own
+// panorama (block-diagonal mask) - that wastes most of S, but one M = 128 tcgen05 tile is the smallest unit the
+// tensor pipe has and the whole problem is 24 + 24 MMAs.  Slots start at multiples of 16 keys = the K extent of one
+// MMA, so a panorama's keys meet the same K16 blocks wherever it sits in a tile and the other blocks contribute
+// exact zeros: results do not depend on the batch composition, bit for bit.  Operands are the split-half planes of
+// the fused qkv activation: Q and K slots arrive by TMA (2-D boxes of 64 dims x slot rows, 128B swizzle = the
+// K-major layout tcgen05 reads), V is transposed into the same layout by the CTA's threads (V^T: rows = dims,
+// K = keys), and the three products hi*hi + hi*lo + lo*hi accumulate in one TMEM accumulator (fp32-level result
+// like the conv engine).  The softmax runs with one thread per query row straight out of TMEM (tcgen05.ld), writes
+// P as split-half planes over the Q tiles (Q is dead once S is complete), and the O rows go back to global memory
+// as split-half planes.
+struct AttMaps { CUtensorMap qk[2]; };      // hi / lo plane of the (rows, 3*dim) qkv activation
+
+constexpr int ATT_TILE = 128 * 128 * 2;     // one 128-row x 128-column fp16 operand = two 16 KB K-chunks
+constexpr int ATT_SMEM = 6 * ATT_TILE + 1024 + 64 + 2 * 2 * 128 * 4;
+
+__global__ void __launch_bounds__(256, 1)
+attention_tc_kernel(const __grid_constant__ AttMaps maps, const __half* __restrict__ qkv, long long plane, int rows,
+                    int N, int G, int slot, int heads, float scale, __half* __restrict__ out, long long out_plane) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  // [0] Q hi | [1] Q lo (later P hi | P lo) | [2] K hi | [3] K lo | [4] V^T hi | [5] V^T lo
+  const uint32_t bar_ld = base + 6 * ATT_TILE, bar_mma = bar_ld + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + 6 * ATT_TILE + 16);
+  float* red_max = reinterpret_cast<float*>(base_ptr + 6 * ATT_TILE + 64);       // [2 column halves][128 rows]
+  float* red_sum = red_max + 256;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int head = blockIdx.x % heads, tile = blockIdx.x / heads;
+  const int dim = heads * 128;
+  const int row0 = tile * G * N;                     // first token row of the tile's first panorama
+  const int pans = min(G, (rows - row0) / N);        // panoramas of this tile that exist
+
+  if (tid == 0) {
+    mbar_init(bar_ld, 1);
+    mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&maps.qk[0]);
+    tma_prefetch_desc(&maps.qk[1]);
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  if (tid == 0) {
+    // Q and K slots of this head: per plane and panorama two 64-dim chunks each.  A box is `slot` rows: the rows
+    // behind a panorama's N own ones belong to the next panorama (masked below); rows beyond the activation are
+    // zero-filled by TMA, so every row of the tile is initialised.
+    mbar_expect_tx(bar_ld, (uint32_t)(8 * G * slot * 128));
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+        for (int kc = 0; kc < 2; ++kc) {
+          const uint32_t dst = (uint32_t)(kc * 16384 + g * slot * 128);
+          tma_load_2d(base + pl * ATT_TILE + dst, &maps.qk[pl], bar_ld, head * 128 + kc * 64, row0 + g * N);
+          tma_load_2d(base + (2 + pl) * ATT_TILE + dst, &maps.qk[pl], bar_ld, dim + head * 128 + kc * 64, row0 + g * N);
+        }
+  }
+  if (G * slot < 128) {        // rows behind the last slot (N = 46: 96 of 128): never loaded, must not hold NaN patterns
+    for (int i = G * slot * 128 + tid * 16; i < 128 * 128; i += 256 * 16) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        *reinterpret_cast<uint4*>(base_ptr + t * ATT_TILE + i) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(base_ptr + t * ATT_TILE + 16384 + i) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  }
+  // V^T: element (dim d, key j) of plane pl -> chunk j / 64, row d, column j % 64 (128B swizzle: 16-byte chunk ^= row & 7).
+  // Thread = key column j; per step it carries 8 dims of its key.  The 32 lanes of a warp then write 32 consecutive
+  // 2-byte columns of the SAME row (conflict-free), and the global loads of four steps are in flight together.
+  {
+    const __half* vsrc = qkv + 2 * dim + head * 128;
+    const int j = tid & 127;
+    const int g = j / slot, t = j - g * slot;
+    const bool have = g < pans && t < N;
+    const size_t o = have ? (size_t)(row0 + g * N + t) * (3 * dim) : 0;
+    const uint32_t kc = (uint32_t)j >> 6, col = (uint32_t)(j & 63) * 2;          // byte column inside the 128-byte row
+#pragma unroll 1
+    for (int dg0 = (tid >> 7) * 8; dg0 < (tid >> 7) * 8 + 8; dg0 += 4) {
+      uint4 hi[4], lo[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        hi[q] = lo[q] = make_uint4(0u, 0u, 0u, 0u);
+        if (have) {
+          hi[q] = __ldg(reinterpret_cast<const uint4*>(vsrc + o + (dg0 + q) * 8));
+          lo[q] = __ldg(reinterpret_cast<const uint4*>(vsrc + plane + o + (dg0 + q) * 8));
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const __half* hh = reinterpret_cast<const __half*>(&hi[q]);
+        const __half* ll = reinterpret_cast<const __half*>(&lo[q]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t r = (uint32_t)(dg0 + q) * 8 + u;
+          const uint32_t off = kc * 16384 + r * 128 + ((((col >> 4) ^ (r & 7)) << 4) | (col & 15));
+          *reinterpret_cast<__half*>(base_ptr + 4 * ATT_TILE + off) = hh[u];
+          *reinterpret_cast<__half*>(base_ptr + 5 * ATT_TILE + off) = ll[u];
+        }
+      }
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+
+  // instruction descriptor: F32 accumulate, F16 operands, K-major A and B, N = 128, M = 128
+  const uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint64_t dconst = umma_desc<128>(0);
+  auto gemm3 = [&](uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t acc) {
+    // hi*hi + hi*lo + lo*hi over K = 128 (two 64-wide chunks x four K16 slices)
+#pragma unroll
+    for (int kc = 0; kc < 2; ++kc) {
+      const uint64_t ah = dconst | (((a_hi + kc * 16384) >> 4) & 0x3FFF), al = dconst | (((a_lo + kc * 16384) >> 4) & 0x3FFF);
+      const uint64_t bh = dconst | (((b_hi + kc * 16384) >> 4) & 0x3FFF), bl = dconst | (((b_lo + kc * 16384) >> 4) & 0x3FFF);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        tc_mma<MODE_F16X3>(acc, ah + 2 * kk, bh + 2 * kk, idesc, (kc | kk) != 0);
+        tc_mma<MODE_F16X3>(acc, ah + 2 * kk, bl + 2 * kk, idesc, 1);
+        tc_mma<MODE_F16X3>(acc, al + 2 * kk, bh + 2 * kk, idesc, 1);
+      }
+    }
+  };
+  if (tid == 0) {
+    mbar_wait(bar_ld, 0);
+    tc_fence_after();
+    gemm3(base, base + ATT_TILE, base + 2 * ATT_TILE, base + 3 * ATT_TILE, tmem);          // S = Q K^T
+    tc_commit(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(bar_mma, 0);
+  tc_fence_after();
+
+  // softmax: two threads per query row r (TMEM lane r; warps w and w + 4 share a lane quarter), each owning 64 of
+  // the 128 key columns; keys of the row's own panorama are columns [c0, c1).  Sweep 1: row maximum.  Sweep 2:
+  // e = exp(s - max) written UNNORMALISED as P (values in (0, 1], the largest exactly 1: ideal for the split-half
+  // planes) plus the row sum; 1 / sum is applied to the O row in the epilogue.
+  const int r = tid & 127, half = tid >> 7;
+  const int g = r / slot;
+  const int c0 = g * slot, c1 = c0 + N;
+  const bool live = g < pans && r - c0 < N;
+  const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  {
+    float m = -INFINITY;
+#pragma unroll 1
+    for (int cb = half * 64; cb < half * 64 + 64; cb += 32) {
+      uint32_t v[32];
+      tmem_ld32_issue(trow + cb, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int c = cb + j;
+        if (c >= c0 && c < c1) m = fmaxf(m, __uint_as_float(v[j]) * scale);
+      }
+    }
+    red_max[half * 128 + r] = m;
+    __syncthreads();
+    m = fmaxf(red_max[r], red_max[128 + r]);
+    float sum = 0.f;
+    uint8_t* p_hi = base_ptr, * p_lo = base_ptr + ATT_TILE;        // P over the Q tiles: K-major, two 64-key chunks
+#pragma unroll 1
+    for (int cb = half * 64; cb < half * 64 + 64; cb += 32) {
+      uint32_t v[32];
+      tmem_ld32_issue(trow + cb, v);
+      tmem_ld_wait();
+      float pv[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int c = cb + j;
+        pv[j] = (live && c >= c0 && c < c1) ? expf(__uint_as_float(v[j]) * scale - m) : 0.f;
+        sum += pv[j];
+      }
+#pragma unroll
+      for (int q8 = 0; q8 < 4; ++q8) {       // 16-byte chunks of 8 keys
+        uint4 hi4, lo4;
+        __half2* hh = reinterpret_cast<__half2*>(&hi4);
+        __half2* ll = reinterpret_cast<__half2*>(&lo4);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float f0 = pv[q8 * 8 + 2 * u], f1 = pv[q8 * 8 + 2 * u + 1];
+          const __half2 h = __floats2half2_rn(f0, f1);
+          const float2 hf = __half22float2(h);
+          hh[u] = h;
+          ll[u] = __floats2half2_rn(f0 - hf.x, f1 - hf.y);
+        }
+        const uint32_t ch = (uint32_t)(cb >> 3) + q8;               // 16-byte chunk index 0..15 along the 128 keys
+        const uint32_t kc = ch >> 3, c16 = ch & 7;
+        const uint32_t off = kc * 16384 + (uint32_t)r * 128 + ((c16 ^ ((uint32_t)r & 7)) << 4);
+        *reinterpret_cast<uint4*>(p_hi + off) = hi4;
+        *reinterpret_cast<uint4*>(p_lo + off) = lo4;
+      }
+    }
+    red_sum[half * 128 + r] = sum;
+  }
+  tc_fence_before();
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    gemm3(base, base + ATT_TILE, base + 4 * ATT_TILE, base + 5 * ATT_TILE, tmem + 128);  // O = P V
+    tc_commit(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(bar_mma, 1);
+  tc_fence_after();
+  // O row r (this thread's 64 dims), normalised -> out[(row0 + ..), head*128 ..] as split-half planes
+  const float inv = 1.f / (red_sum[r] + red_sum[128 + r]);
+#pragma unroll 1
+  for (int cb = half * 64; cb < half * 64 + 64; cb += 32) {
+    uint32_t v[32];
+    tmem_ld32_issue(trow + 128 + cb, v);
+    tmem_ld_wait();
+    if (live) {
+      __half* ohi = out + (size_t)(row0 + g * N + (r - c0)) * dim + head * 128 + cb;
+      __half* olo = ohi + out_plane;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 hi4, lo4;
+        __half2* hh = reinterpret_cast<__half2*>(&hi4);
+        __half2* ll = reinterpret_cast<__half2*>(&lo4);
+#pragma unroll
+        for (int tt = 0; tt < 4; ++tt) {
+          const float f0 = __uint_as_float(v[j + 2 * tt]) * inv, f1 = __uint_as_float(v[j + 2 * tt + 1]) * inv;
+          const __half2 h = __floats2half2_rn(f0, f1);
+          const float2 hf = __half22float2(h);
+          hh[tt] = h;
+          ll[tt] = __floats2half2_rn(f0 - hf.x, f1 - hf.y);
+        }
+        *reinterpret_cast<uint4*>(ohi + j) = hi4;
+        *reinterpret_cast<uint4*>(olo + j) = lo4;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+  }
+}
+
+// qkv: split-half planes of (rows, 3*heads*128) = [q | k | v] per row, rows = B*N; out: split-half (rows, heads*128)
+int attention_tc(const void* qkv, int B, int N, int heads, void* out, cudaStream_t s) {
+  OFB_CHECK(qkv && out && B > 0 && heads > 0, "attention_tc: bad arguments");
+  OFB_CHECK(N >= 1 && N <= 64, "attention_tc: 1..64 tokens per panorama (got %d)", N);
+  const int rows = B * N, dim = heads * 128, slot = (N + 15) & ~15, G = 128 / slot, tiles = (B + G - 1) / G;
+  AttMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int pl = 0; pl < 2; ++pl) {
+    cuuint64_t dims[2] = {(cuuint64_t)3 * dim, (cuuint64_t)rows};
+    cuuint32_t box[2] = {64u, (cuuint32_t)slot};
+    char* a = (char*)qkv + (size_t)pl * rows * 3 * dim * 2;
+    if (make_map(&maps.qk[pl], true, 2, a, dims, box, 128)) return -1;
+  }
+  static bool attr[kMaxDevices] = {false};
+  const int dev = cur_device();
+  if (!attr[dev]) {
+    OFB_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    attr[dev] = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(tiles * heads); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = ATT_SMEM; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  int na = 0;
+  if (tc_opts().pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = at; cfg.numAttrs = na;
+  const __half* q = reinterpret_cast<const __half*>(qkv);
+  OFB_CUDA(cudaLaunchKernelEx(&cfg, attention_tc_kernel, maps, q, (long long)rows * 3 * dim, rows, N, G, slot, heads,
+                              1.f / sqrtf(128.f), reinterpret_cast<__half*>(out), (long long)rows * dim));
+  OFB_LAUNCH_CHECK();
+  return 0;
 }
 
 // ------------------------------------------------------------ split-half conversion

@@ -34,12 +34,14 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s);
 bool conv_tc_supported(const ofb_conv_desc* d);
 int conv_tc_heads(const void* x, int n, int h, int w, const void* wgt_split, float wgt_unscale, float b_pred,
                   float b_conf, int confidence, float* pred_out, float* conf_out, int interleaved, cudaStream_t s);
+int attention_tc(const void* qkv, int B, int N, int heads, void* out, cudaStream_t s);
 int blend_conf_launch(const float* pred_w, const float* conf, bool interleaved, int B, int N, int Ph, int Pw,
                       const int32_t* rowptr, const uint32_t* idx, const float* w, int He, int We, float* out,
                       cudaStream_t s);
 int deinterleave_launch(const float* src_pairs, size_t n, int comp, float* dst, cudaStream_t s);
 long long* conv_tc_debug_buffer();
 int conv_tc_timeline_slots();
+void conv_tc_default_debug(int v);
 const char* conv_tc_last_variant();
 
 int conv_dispatch(const ofb_conv_desc* d, cudaStream_t s) {
@@ -86,6 +88,7 @@ struct ofb_handle {
   int dbg_blocks = 6;              // timing experiments only: number of transformer blocks executed
   int splitk = 4;                  // K slices of the two 512-wide token linears on the tcgen05 engine (1 = off)
   int heads_tc = 1;                // run the heads on the tensor pipe (split-half format, 128-pixel rows)
+  int attn_tc = 1;                 // attention core on the tensor pipe (split-half format; tcgen05 QK^T and PV)
   float pred_b = 0.f, conf_b = 0.f;
   Mlp mlp[2]{};
   std::vector<void*> owned;        // device allocations for weights
@@ -579,7 +582,8 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
         Block& B = h->blk[i];
         if (run_linear(c, B.qkv, b.ln, nullptr, OFB_ACT_NONE, b.kv)) return -1;     // (imgs,1536) = [q | k | v]
         { Prof pr(h, s, "attention", 0.0, 4.0*((double)imgs*2048));
-        if (ofb_attention_qkv_f32(b.kv, Bc, N, 4, 128, b.att, F, vs)) return -1; }
+        if (h->attn_tc) { if (attention_tc(b.kv, Bc, N, 4, b.att, s)) return -1; }
+        else if (ofb_attention_qkv_f32(b.kv, Bc, N, 4, 128, b.att, F, vs)) return -1; }
         if (run_linear(c, B.proj, b.att, nullptr, OFB_ACT_NONE, b.kv, SK, b.part)) return -1;
         { Prof pr(h, s, "splitk_finish_ln", 0.0, 4.0*((double)imgs*512*(SK + 3)));     // y = x + proj(att); ln = norm2(y)
         if (ofb_splitk_finish_ln_f32(b.part, SK, B.proj.unscale, B.proj.shift, x, imgs, 512, y, B.n2g, B.n2b, 1e-5f, b.ln, F, vs)) return -1; }
@@ -598,7 +602,8 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
       if (ofb_layernorm_f32(x, B.n1g, B.n1b, imgs, 512, 1e-5f, b.ln, F, F, vs)) return -1; }
       if (run_linear(c, B.qkv, b.ln, nullptr, OFB_ACT_NONE, b.kv)) return -1;     // (imgs,1536) = [q | k | v]
       { Prof pr(h, s, "attention", 0.0, 4.0*((double)imgs*2048));
-      if (ofb_attention_qkv_f32(b.kv, Bc, N, 4, 128, b.att, F, vs)) return -1; }
+      if (h->attn_tc && F == OFB_FMT_SPLIT16 && h->engine != OFB_ENGINE_SIMT) { if (attention_tc(b.kv, Bc, N, 4, b.att, s)) return -1; }
+      else if (ofb_attention_qkv_f32(b.kv, Bc, N, 4, 128, b.att, F, vs)) return -1; }
       if (run_linear(c, B.proj, b.att, x, OFB_ACT_NONE, y)) return -1;          // y = x + proj(att)
       { Prof pr(h, s, "layernorm", 0.0, 4.0*((double)imgs*1024));
       if (ofb_layernorm_f32(y, B.n2g, B.n2b, imgs, 512, 1e-5f, b.ln, F, F, vs)) return -1; }
@@ -692,6 +697,12 @@ extern "C" int ofb_heads_tc_pairs_f16(const void* x_planes, int imgs, int h, int
                        (cudaStream_t)stream);
 }
 
+extern "C" int ofb_attention_tc_f16(const void* qkv_planes, int B, int N, int heads, int head_dim, void* out_planes,
+                                    void* stream) {
+  OFB_CHECK(head_dim == 128, "attention_tc: head_dim must be 128 (got %d)", head_dim);
+  return attention_tc(qkv_planes, B, N, heads, out_planes, (cudaStream_t)stream);
+}
+
 extern "C" int ofb_stem_tc_f16(const void* patches, int n, int h, int w, const void* wgt_split, float wgt_unscale,
                                const float* scale, const float* shift, void* out, void* stream) {
   return stem_tc(patches, n, h, w, wgt_split, wgt_unscale, scale, shift, out, (cudaStream_t)stream);
@@ -763,6 +774,7 @@ extern "C" int ofb_set_option(ofb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "dedup")) h->dedup = value;
   else if (!strcmp(key, "fuse_ups")) h->fuse_ups = value;
   else if (!strcmp(key, "heads_tc")) h->heads_tc = value;
+  else if (!strcmp(key, "attn_tc")) h->attn_tc = value;
   else if (!strcmp(key, "splitk")) h->splitk = value == 2 || value == 4 ? value : 1;
   else if (!strcmp(key, "khr_row64")) h->tc.khr_row64 = value != 0;
   else if (!strcmp(key, "khr_bw")) h->tc.khr_bw = value == 32 ? 32 : 16;    // tile width of the kh-reuse kernels
@@ -834,6 +846,9 @@ extern "C" int ofb_forward_f32(ofb_handle* h, const float* rgb, int B, int iters
   OFB_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
   return rc;
 }
+
+// timing experiments: TcParams::dbg of tcgen05 convs launched directly through ofb_conv_f32 (tools/probe_mid.py)
+extern "C" int ofb_debug_set(int v) { conv_tc_default_debug(v); return 0; }
 
 // timing experiments: copies the clock stamps recorded with tc_debug & 16 (512 x 8 int64) to the host
 extern "C" int ofb_debug_stamps(long long* host_dst) {

@@ -279,3 +279,27 @@ def test_splitk_linear_and_finish_layernorm(rows, cin, ksplit):
         ex, el = (got_x - want_x).abs().max().item(), (got_ln - want_ln).abs().max().item()
         print(f"[parity] split-K linear rows={rows} K={cin} S={ksplit} ln_fmt={ln_fmt}: x max_abs_err={ex:.3e} ln max_abs_err={el:.3e}")
         assert ex <= 2e-5 and el <= 5e-5
+
+
+@pytest.mark.parametrize("B,n_tok", [(8, 18), (3, 18), (16, 46), (5, 26), (13, 10), (1, 64)])
+def test_attention_on_tensor_cores_matches_torch_cpu(B, n_tok):
+    """Attention core of model/blocks.py:50-62 on tcgen05 (ofb_attention_tc_f16): one CTA per head and tile of
+    128 // N whole panoramas, block-diagonal softmax.  Against torch-CPU fp32; B chosen so that the last tile is
+    ragged (8 = 7 + 1 panoramas at N = 18) and so that N = 64 fills half a tile exactly."""
+    o = ops()
+    heads, d = 4, 128
+    qkv = rand(B * n_tok, 3 * heads * d, seed=41 + n_tok)
+    q, k, v = qkv[:, :512], qkv[:, 512:1024], qkv[:, 1024:]
+    sh = lambda t: t.reshape(B, n_tok, heads, d).permute(0, 2, 1, 3)
+    att = ((sh(q) @ sh(k).transpose(-2, -1)) * d ** -0.5).softmax(-1)
+    ref = (att @ sh(v)).transpose(1, 2).reshape(B * n_tok, heads * d)
+    planes = o.split16(qkv.to(DEV))
+    out = torch.full((2 * B * n_tok * heads * d,), float("nan"), dtype=torch.float16, device=DEV)
+    _lib.check(_lib.lib().ofb_attention_tc_f16(_lib.ptr(planes), B, n_tok, heads, d, _lib.ptr(out),
+                                                _lib.stream_of(torch.device(DEV))))
+    torch.cuda.synchronize()
+    got = o.merge16(out, (B * n_tok, heads * d)).cpu()
+    err = (got - ref).abs()
+    print(f"[parity] attention_tc B={B} N={n_tok}: max_abs_err={err.max().item():.3e} ref_absmax={ref.abs().max().item():.3e}")
+    assert torch.isfinite(got).all()
+    assert (err <= 3e-6 + 1e-5 * ref.abs()).all()
