@@ -292,10 +292,18 @@ long long ofb_workspace_generation(ofb_handle* h);
 /* Engine knobs (key, value): "engine" conv engine (OFB_ENGINE_*), "chunk" panoramas per internal chunk
  * (0 = auto), "dedup" reuse of the iteration-invariant stem/layer1 across iterations (default 1), "format"
  * activation storage (OFB_FMT_*), "fuse_ups" fold the last decoder upsample into de_conv4_0 (default 1),
- * "heads_tc" heads on the tensor pipe (default 1), "attn_tc" attention core on the tensor pipe (default 1), "lanes" 2 = two concurrent half-batches on two streams
+ * "check_range" see ofb_range_report, "heads_tc" heads on the tensor pipe (default 1), "attn_tc" attention core on the tensor pipe (default 1), "lanes" 2 = two concurrent half-batches on two streams
  * (default 1), "cta2" / "pdl" / "store128" / "fill_div" / "direct32" / "khr_bw" / "khr_row64" tcgen05 launch variants (per handle);
  * "tc_debug" / "dbg_blocks" switch parts of the pipeline OFF for timing experiments (results are wrong). */
 int ofb_set_option(ofb_handle* h, const char* key, int value);
+
+/* Numeric range of the network's activations.  The split-half storage format (OFB_FMT_SPLIT16) holds value = fp16 hi +
+ * fp16 lo: |x| above 65504 overflows to inf and |x| below ~6e-5 loses low-order bits to fp16 subnormals (absolute floor
+ * ~6e-8); the reference is fp32 and has neither limit.  With option "check_range" = 1 every forward also reduces the main
+ * activations (stem, pool, layer1-4, tokens, encoder output, decoder stages) to max |x| and a non-finite count;
+ * ofb_range_report synchronises, writes "name max_abs nonfinite" lines and returns how many of them left the
+ * representable range (0 = fine).  Checkpoints whose activations do not fit should run with "format" = OFB_FMT_F32. */
+int ofb_range_report(ofb_handle* h, char* buf, int capacity);
 
 /* Copies a named intermediate of the last forward (last chunk, last iteration) into
  * dst (device, `capacity` floats); returns the element count, or negative.  Names:

@@ -89,6 +89,7 @@ _SIGNATURES = {
     "ofb_debug_stamps": (_I, [_P]),
     "ofb_debug_set": (_I, [_I]),
     "ofb_debug_timeline": (_I, [_P, _I]),
+    "ofb_range_report": (_I, [_P, C.c_char_p, _I]),
     "ofb_profile_enable": (_I, [_P, _I]),
     "ofb_profile_report": (_I, [_P, C.c_char_p, _I]),
 }
@@ -106,7 +107,12 @@ def lib():
                            "(there is no CPU fallback)")
         handle = C.CDLL(LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
-            fn = getattr(handle, name)
+            try:
+                fn = getattr(handle, name)
+            except AttributeError:
+                if os.environ.get("OFB_LIB"):      # A/B run against an older build: newer entry points are absent
+                    continue
+                raise
             fn.restype, fn.argtypes = res, args
         _lib = handle
     return _lib

@@ -135,3 +135,30 @@ def strip_module_prefix(sd):
     if len(sd) and all(k.startswith("module.") for k in sd):
         return OrderedDict((k[len("module."):], v) for k, v in sd.items())
     return sd
+
+
+def rescale_activations(sd, s, kind="iterative"):
+    """A checkpoint whose conv-tower activations are `s` times those of `sd` while the depth output is unchanged in
+    exact arithmetic (up to the BatchNorm eps): every BatchNorm of the patch network gets gamma, beta * s and - when its
+    input is already scaled - running_mean * s, running_var * s^2; the token path stays at its own scale (down1.weight / s,
+    encoder_norm * s because its output is added to layer4); pred / weight_pred weights / s.  Used to probe the
+    numeric range of the split-half activation format (tests/test_gpu_model.py)."""
+    out = OrderedDict((k, v.clone()) for k, v in sd.items())
+    bn = sorted({k[: -len(".running_var")] for k in sd if k.endswith(".running_var")})
+    mlp = [p for p in bn if p.startswith("mlp_points")]
+    for p in bn:
+        # first BN of a point MLP feeds only the second one: left alone; the second one's OUTPUT joins layer1 (scaled)
+        if p in mlp and not p.endswith(".4"):
+            continue
+        out[p + ".weight"] *= s
+        out[p + ".bias"] *= s
+        if p != "bn1" and p not in mlp:                      # input already scaled by s
+            out[p + ".running_mean"] *= s
+            out[p + ".running_var"] *= s * s
+    down = "down1" if kind == "iterative" else "down"
+    out[down + ".weight"] /= s
+    out["transformer.encoder_norm.weight"] *= s
+    out["transformer.encoder_norm.bias"] *= s
+    out["pred.weight"] /= s
+    out["weight_pred.weight"] /= s
+    return out

@@ -351,11 +351,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
   // prefetch) may overlap the tail of the previous kernel in the stream; no global memory is
   // touched before this point.  Let the next kernel start its own prologue as early as possible.
-  // Let the next kernel start its own prologue as early as possible.  griddepcontrol.wait (= the previous kernel in
-  // the stream has completed and its writes are visible) is executed per role, immediately before the first access
-  // to memory another kernel writes: the WEIGHTS are written once at load time, so the producer warp issues the
-  // weight loads of the first ring stages (and the resident filter) BEFORE it waits - their HBM latency overlaps the
-  // previous kernel's tail and the launch gap instead of opening every layer's pipeline.
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
+  // prefetch) may overlap the tail of the previous kernel in the stream; no global memory is
+  // touched before this point.  Let the next kernel start its own prologue as early as possible.
+  // (Issuing the weight loads of the first ring stages BEFORE the wait and fetching the residual tile before the
+  // accumulator wait were both measured - same-box A/B, tools/_old builds - and bought nothing: the launch is not
+  // waiting for those latencies)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
@@ -368,7 +370,6 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       }
       __syncwarp();
     }
-    if (UPS == 2) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (UPS == 2) {
       // rolling rows: one box {32 channels, 130 pixels from x = -1, 1 row} per plane and produced row; rows -1
       // and H and the two border columns are out of bounds = zero-filled by TMA = the conv padding
@@ -417,23 +418,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         }
       }
     };
-    // prologue: weight loads of the first ring stages, before the dependency wait (all stages are empty)
-    int pre = 0;
-    if (ld_b && !UPS) {
-      for (int t = tile0; t < p.total_tiles && pre < Cfg::NST; t += tile_step) {
-        const int sp = t % p.ksplit, tq = t / p.ksplit;
-        const int n0 = (tq % p.tiles_n) * BN;
-        const int cq_begin = p.ksplit > 1 ? sp * ksteps : 0, cq_end = p.ksplit > 1 ? cq_begin + ksteps : cchunks;
-        for (int tap = 0; tap < ntap && pre < Cfg::NST; ++tap)
-          for (int cq = cq_begin; cq < cq_end && pre < Cfg::NST; ++cq, ++pre) {
-            if (elect_one()) load_b((uint32_t)pre, n0, tap, cq);
-            __syncwarp();
-          }
-      }
-    }
-    if (!UPS) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tl && lane == 0) tl_buf[2] = globaltimer_ns();
-    int gs = 0;                       // K-steps issued so far (the first `pre` already have their weights in flight)
     for (int t = tile0; !UPS && t < p.total_tiles; t += tile_step) {
       const int sp = t % p.ksplit, tq = t / p.ksplit;            // split-K slice (ksplit == 1: tq == t)
       const int nt = tq % p.tiles_n, mt = CTA2 ? 2 * (tq / p.tiles_n) + (int)rank : tq / p.tiles_n;
@@ -456,7 +441,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           mbar_wait(bars + 8 * (Cfg::NST + st), ph ^ 1);
           if (elect_one()) {
             // (CTA2: both CTAs' bytes land on the leader's barrier)
-            if (ld_b) { if (gs >= pre) load_b(st, n0, tap, cq); }
+            if (ld_b) load_b(st, n0, tap, cq);
             else mbar_expect_tx(full, tx);
 #pragma unroll
             for (int pl = 0; pl < Cfg::PLANES; ++pl) {
@@ -465,7 +450,6 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             }
           }
           __syncwarp();
-          ++gs;
           if (++st == Cfg::NST) { st = 0; ph ^= 1; }
         }
         if (++kw == p.kdiv) { kw = 0; ++kh; }
@@ -595,7 +579,6 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     }
   } else if (warp < 2 + Cfg::EPI_WARPS) {
     // ===================== epilogue (warps 2..5 <-> TMEM lane quarters) =====================
-    asm volatile("griddepcontrol.wait;" ::: "memory");   // residual reads / output writes: after the previous kernel
     const int q = warp & 3;                    // a warp may only touch TMEM lanes [32*(warp%4), +32)
     const int r = q * 32 + lane;               // accumulator row = pixel within the tile
     const int xx = r % p.BW, yy = (r / p.BW) % p.BH, ni = r / (p.BW * p.BH);
@@ -626,28 +609,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       const bool ok = img < p.n_img;
       const size_t pix = ((size_t)(ok ? img : 0) * p.H + (y0 + yy)) * p.W + (x0 + xx);
       const size_t off = pix * p.cout + n0;
-      // The residual operand of this tile is fetched BEFORE waiting for the accumulator: the epilogue warps idle
-      // during the K loop, so its L2 / HBM latency disappears behind the MMAs instead of heading the epilogue
-      // (with one tile per CTA - 8 panoramas per step - nothing else overlaps that tail).
       constexpr int NCH = (BN + 32 * Cfg::EPI_SETS - 1) / (32 * Cfg::EPI_SETS);     // 32-column chunks per epilogue warp
-      constexpr bool RES_PRE = MODE == MODE_F16X3;
-      uint4 rpre[RES_PRE ? NCH : 1][8];
-      const bool res_pre = RES_PRE && p.residual && ok && p.ksplit == 1;
-      if (res_pre) {
-#pragma unroll
-        for (int ci = 0; ci < NCH; ++ci) {
-          const int cb = 32 * eset + ci * 32 * Cfg::EPI_SETS;
-          if (cb < BN) {
-            const __half* rhi = reinterpret_cast<const __half*>(p.residual) + off + cb;
-            const __half* rlo = rhi + p.plane;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              rpre[ci][j] = __ldg(reinterpret_cast<const uint4*>(rhi + 8 * j));
-              rpre[ci][4 + j] = __ldg(reinterpret_cast<const uint4*>(rlo + 8 * j));
-            }
-          }
-        }
-      }
       if (stamp) p.dbg_buf[i * 8 + 0] = clock64();
       mbar_wait(bar_tfull + 8 * buf, (i >> 1) & 1);
       tc_fence_after();
@@ -724,10 +686,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
               f[j] += tt.x; f[j + 1] += tt.y; f[j + 2] += tt.z; f[j + 3] += tt.w;
             }
           } else {
+            const __half* rhi = reinterpret_cast<const __half*>(p.residual) + off + cb;
+            const __half* rlo = rhi + p.plane;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-              const uint4 a = rpre[RES_PRE ? ci : 0][j >> 3];
-              const uint4 b = rpre[RES_PRE ? ci : 0][4 + (j >> 3)];
+              uint4 a = __ldg(reinterpret_cast<const uint4*>(rhi + j));
+              uint4 b = __ldg(reinterpret_cast<const uint4*>(rlo + j));
               const __half2* ah = reinterpret_cast<const __half2*>(&a);
               const __half2* bh = reinterpret_cast<const __half2*>(&b);
 #pragma unroll
@@ -837,7 +801,6 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     // (clamped) with weights h0, h1; same for columns.  T(r) = the horizontally blended low-res row r (2 pixels
     // x 8 channels per thread) is cached in registers for the two rows in use: consecutive upsampled rows
     // share them, so a new low-res row is fetched only every second row.
-    asm volatile("griddepcontrol.wait;" ::: "memory");   // reads the previous layer's output
     constexpr int NT = 32 * Cfg::UPS_WARPS, C8 = Cfg::KC / 8;
     static_assert(UPS != 1 || (NT == 64 * C8), "one producer thread per (low-res column, 8-channel chunk)");
     const int pt = threadIdx.x - (64 + 32 * Cfg::EPI_WARPS);

@@ -39,6 +39,8 @@ int blend_conf_launch(const float* pred_w, const float* conf, bool interleaved, 
                       const int32_t* rowptr, const uint32_t* idx, const float* w, int He, int We, float* out,
                       cudaStream_t s);
 int deinterleave_launch(const float* src_pairs, size_t n, int comp, float* dst, cudaStream_t s);
+int zero_stem_pads(void* patches, int imgs, int P, cudaStream_t s);
+int range_launch(const void* p, size_t n, int fmt, unsigned int* out2, cudaStream_t s);
 long long* conv_tc_debug_buffer();
 int conv_tc_timeline_slots();
 void conv_tc_default_debug(int v);
@@ -69,6 +71,7 @@ struct Block {
   ConvW qkv, proj, fc1, fc2;     // qkv = rows of attn.q.weight followed by attn.kv.weight
 };
 struct Act { float* p = nullptr; int n = 0, h = 0, w = 0, c = 0, fmt = 0; };
+constexpr int kRangeSlots = 32;
 
 }  // namespace ofb
 
@@ -89,6 +92,9 @@ struct ofb_handle {
   int splitk = 4;                  // K slices of the two 512-wide token linears on the tcgen05 engine (1 = off)
   int heads_tc = 1;                // run the heads on the tensor pipe (split-half format, 128-pixel rows)
   int attn_tc = 1;                 // attention core on the tensor pipe (split-half format; tcgen05 QK^T and PV)
+  int check_range = 0;             // after every forward: max |x| / non-finite count of each registered activation
+  unsigned int* range_dev = nullptr;            // [kRangeSlots][2]
+  std::vector<std::string> range_names;         // names of the slots filled by the last forward
   float pred_b = 0.f, conf_b = 0.f;
   Mlp mlp[2]{};
   std::vector<void*> owned;        // device allocations for weights
@@ -520,18 +526,8 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
       // equi2pers(rgb, P) -> patches; stem; pool; layer1 (spherical_model_iterative.py:315,322-324)
       const ConvW& st = h->conv["stem"];
       const bool stem_tc_path = F == OFB_FMT_SPLIT16 && h->engine != OFB_ENGINE_SIMT;
-      if (stem_tc_path) {
-        // The stem layout's 4-pixel row pads must read as zero and e2p never writes them.  They are re-zeroed by
-        // EVERY forward, inside the stream-ordered (and therefore graph-captured) region: the arena is re-planned
-        // per batch size, so another forward may have put live data where this one's pads are.  The right pad of
-        // row r and the left pad of row r+1 are one contiguous 64-byte span (rows of both planes are back to
-        // back), so the pads are one strided 2-D memset plus the first and the last 32 bytes.
-        const size_t pitch = (size_t)(P + 8) * 4 * sizeof(__half), rows = (size_t)2 * imgs * P;
-        char* pp = reinterpret_cast<char*>(b.patches);
-        OFB_CUDA(cudaMemsetAsync(pp, 0, 32, s));
-        OFB_CUDA(cudaMemset2DAsync(pp + pitch - 32, pitch, 0, 64, rows - 1, s));
-        OFB_CUDA(cudaMemsetAsync(pp + rows * pitch - 32, 0, 32, s));
-      }
+      // the stem layout's zero row pads: re-zeroed by every forward, inside the captured region (layers.cu)
+      if (stem_tc_path && zero_stem_pads(b.patches, imgs, P, s)) return -1;
       { Prof pr(h, s, "e2p_rgb", 0.0, 4.0*((double)Bc*3*He*We + (double)imgs*P*P*4));
       if (ofb_equi2pers_f32(rgb, Bc, 3, He, We, g.grid_hi, N, P, P, b.patches,
                             stem_tc_path ? OFB_LAYOUT_STEM16 : OFB_LAYOUT_FOLDED, vs)) return -1; }
@@ -665,6 +661,20 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
   reg(h, "de_conv2_1", b.d21, imgs, p4, p4, 64); reg(h, "de_conv3_1", b.d31, imgs, P / 2, P / 2, 32);
   reg(h, "de_conv4_0", b.d40, imgs, P, P, 32); reg(h, "pred_patch", b.pred, imgs, P, P, 1, pairs ? 2 : 0);
   reg(h, "conf_patch", pairs ? b.pred : b.conf, imgs, P, P, 1, pairs ? 3 : 0);    // fmt 2 / 3: component 0 / 1 of a pair map
+  if (h->check_range) {
+    if (!h->range_dev) OFB_CUDA(cudaMalloc(&h->range_dev, kRangeSlots * 2 * sizeof(unsigned int)));
+    OFB_CUDA(cudaMemsetAsync(h->range_dev, 0, kRangeSlots * 2 * sizeof(unsigned int), s));
+    h->range_names.clear();
+    static const char* const kChecked[] = {"conv1", "pool", "layer1_pre", "layer1", "layer2", "layer3", "layer4", "tokens",
+                                           "encoded", "de_conv0_1", "de_conv1_1", "de_conv2_1", "de_conv3_1", "de_conv4_0"};
+    for (const char* nm : kChecked) {
+      const Act& a = h->acts[nm];
+      if (!a.p || (a.fmt != OFB_FMT_F32 && a.fmt != OFB_FMT_SPLIT16)) continue;
+      const size_t slot = h->range_names.size();
+      if (range_launch(a.p, (size_t)a.n * a.h * a.w * a.c, a.fmt, h->range_dev + 2 * slot, s)) return -1;
+      h->range_names.push_back(nm);
+    }
+  }
   return 0;
 }
 
@@ -732,6 +742,7 @@ extern "C" int ofb_destroy(ofb_handle* h) {
   drop_profile_records(h);
   for (int l = 0; l < 2; ++l)
     if (h->lane[l].ws) cudaFree(h->lane[l].ws);
+  if (h->range_dev) cudaFree(h->range_dev);
   if (h->aux) cudaStreamDestroy(h->aux);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -775,6 +786,7 @@ extern "C" int ofb_set_option(ofb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "fuse_ups")) h->fuse_ups = value;
   else if (!strcmp(key, "heads_tc")) h->heads_tc = value;
   else if (!strcmp(key, "attn_tc")) h->attn_tc = value;
+  else if (!strcmp(key, "check_range")) h->check_range = value;
   else if (!strcmp(key, "splitk")) h->splitk = value == 2 || value == 4 ? value : 1;
   else if (!strcmp(key, "khr_row64")) h->tc.khr_row64 = value != 0;
   else if (!strcmp(key, "khr_bw")) h->tc.khr_bw = value == 32 ? 32 : 16;    // tile width of the kh-reuse kernels
@@ -877,6 +889,29 @@ extern "C" int ofb_profile_enable(ofb_handle* h, int on) {
   h->profile = on != 0;
   if (!on) drop_profile_records(h);     // records nobody asked a report for
   return 0;
+}
+
+// Option "check_range": report of the last forward (last chunk).  Synchronises the device.  Writes one line per checked
+// activation, "name max_abs nonfinite\n", into buf; returns the number of activations whose values left the range the
+// storage format represents (non-finite, or |x| >= 65504 in the split-half format), or negative on error.
+extern "C" int ofb_range_report(ofb_handle* h, char* buf, int capacity) {
+  OFB_CHECK(h && buf && capacity > 0, "range_report: bad arguments");
+  buf[0] = 0;
+  if (!h->range_dev || h->range_names.empty()) return 0;
+  OFB_CUDA(cudaDeviceSynchronize());
+  unsigned int host[kRangeSlots * 2];
+  OFB_CUDA(cudaMemcpy(host, h->range_dev, sizeof(host), cudaMemcpyDeviceToHost));
+  int off = 0, bad = 0;
+  for (size_t i = 0; i < h->range_names.size(); ++i) {
+    float m;
+    memcpy(&m, &host[2 * i], sizeof(float));
+    const Act& a = h->acts[h->range_names[i]];
+    if (host[2 * i + 1] || (a.fmt == OFB_FMT_SPLIT16 && m >= 65504.f)) ++bad;
+    int w = snprintf(buf + off, capacity - off, "%s %.6e %u\n", h->range_names[i].c_str(), m, host[2 * i + 1]);
+    if (w < 0 || w >= capacity - off) break;
+    off += w;
+  }
+  return bad;
 }
 
 extern "C" long long ofb_workspace_generation(ofb_handle* h) { return h ? h->ws_generation : -1; }

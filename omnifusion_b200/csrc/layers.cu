@@ -610,6 +610,65 @@ heads_kernel(const void* __restrict__ x, int imgs, int h, int w, const float* __
   }
 }
 
+// ------------------------------------------------------------------ stem row pads
+// The tensor-core stem reads patches in the STEM16 layout (split-half planes of (imgs, P, P + 8, 4)): every row carries
+// 4 zero pixels on each side, which equi2pers never writes.  They are re-zeroed by EVERY forward inside the
+// stream-ordered (hence graph-captured) region, because the arena is re-planned per batch size and another forward
+// may have put live data there.  The right pad of row r and the left pad of row r + 1 are one contiguous 64-byte
+// span (rows of both planes are back to back): one thread per row boundary.
+__global__ void zero_stem_pads_kernel(uint4* __restrict__ base, uint32_t rows, uint32_t pitch16) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;        // boundary after row r - 1 (r == 0: head, r == rows: tail)
+  if (r > rows) return;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  uint4* p = base + (size_t)r * pitch16;
+  if (r > 0) { p[-2] = z; p[-1] = z; }
+  if (r < rows) { p[0] = z; p[1] = z; }
+}
+
+int zero_stem_pads(void* patches, int imgs, int P, cudaStream_t s) {
+  const uint32_t rows = (uint32_t)2 * imgs * P, pitch16 = (uint32_t)(P + 8) * 4 * 2 / 16;
+  zero_stem_pads_kernel<<<cdiv((long long)rows + 1, 256), 256, 0, s>>>(reinterpret_cast<uint4*>(patches), rows, pitch16);
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------- range check
+// max |x| and the number of non-finite elements of an activation (option "check_range"): the split-half format stores
+// value = fp16 hi + fp16 lo, so |x| > 65504 overflows to inf and |x| < ~6e-5 loses the lo plane to fp16 subnormals;
+// the reference is fp32 and has neither limit.  out[0] = bit pattern of max |x| (atomicMax on the non-negative float),
+// out[1] = non-finite count.
+__global__ void range_kernel(const void* __restrict__ p, size_t n, int fmt, unsigned int* __restrict__ out) {
+  float m = 0.f;
+  unsigned int bad = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float v;
+    if (fmt == OFB_FMT_SPLIT16) {
+      const __half* h = reinterpret_cast<const __half*>(p);
+      v = __half2float(h[i]) + __half2float(h[n + i]);
+    } else {
+      v = reinterpret_cast<const float*>(p)[i];
+    }
+    if (!isfinite(v)) ++bad; else m = fmaxf(m, fabsf(v));
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&out[0], __float_as_uint(m));
+    if (bad) atomicAdd(&out[1], bad);
+  }
+}
+
+int range_launch(const void* p, size_t n, int fmt, unsigned int* out2, cudaStream_t s) {
+  int blocks = (int)((n + 256 * 16 - 1) / (256 * 16));
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  range_kernel<<<blocks, 256, 0, s>>>(p, n, fmt, out2);
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace ofb
 
 using namespace ofb;

@@ -105,8 +105,11 @@ class SphericalFusionBase(nn.Module):
         """Re-packs the checkpoint on the device when any tensor changed.  The change check is one
         (data_ptr, version) pair per tensor over a cached tensor list - no state_dict() rebuild per forward."""
         if self._tensor_list is None:
+            # storage can only move through load_state_dict / _apply (.to, .cuda, .float ...), which reset this list;
+            # in between, an in-place edit shows up in the tensors' version counters - one attribute read each
             self._tensor_list = list(self.state_dict().items())
-        key = tuple((v.data_ptr(), v._version) for _, v in self._tensor_list)
+            self._weights_key = None
+        key = tuple(v._version for _, v in self._tensor_list)
         if key == self._weights_key:
             return
         tensors = OrderedDict(self._tensor_list)
@@ -198,6 +201,29 @@ class SphericalFusionBase(nn.Module):
         static_in.copy_(rgb, non_blocking=True)
         graph.replay()
         return static_out
+
+    def range_report(self):
+        """With set_option("check_range", 1): (number of activations outside the range the storage format represents,
+        {name: (max_abs, nonfinite_count)}) of the last forward.  Synchronises.  The split-half format overflows above
+        65504 and loses low-order bits below ~6e-5 (include/ofb.h); the reference is fp32."""
+        buf = C.create_string_buffer(4096)
+        bad = _lib.check(_lib.lib().ofb_range_report(self._handle, buf, len(buf)))
+        rows = {}
+        for ln in buf.value.decode().strip().split("\n"):
+            f = ln.split()
+            if len(f) == 3:
+                rows[f[0]] = (float(f[1]), int(f[2]))
+        return bad, rows
+
+    def check_numerics(self):
+        """Raises OfbError when the last forward's activations left the representable range (needs check_range = 1)."""
+        bad, rows = self.range_report()
+        if bad:
+            worst = max(rows.items(), key=lambda kv: (kv[1][1], kv[1][0]))
+            raise _lib.OfbError(f"{bad} activation tensor(s) left the range of the split-half storage format "
+                                f"(e.g. {worst[0]}: max |x| = {worst[1][0]:.3e}, {worst[1][1]} non-finite); "
+                                "run this checkpoint with set_option('format', 0)")
+        return rows
 
     def activation(self, name):
         """Debug/test hook: a named intermediate of the last forward as a (n,h,w,c) tensor."""

@@ -277,3 +277,42 @@ def test_module_prefix_checkpoint_and_errors():
         net(rgb, iter=1)
     with pytest.raises(ValueError):
         spherical_fusion(4, 18, (256, 256), FOV)
+
+
+@pytest.mark.parametrize("s", [1e-3, 30.0, 1e3, 1e4])
+def test_activation_range_of_the_split_half_format(s):
+    """The split-half storage format (fp16 hi + fp16 lo) overflows above 65504 and loses low-order bits below ~6e-5;
+    the reference is fp32.  Checkpoints whose conv-tower activations are scaled by s (checkpoint.rescale_activations;
+    same depth in exact arithmetic): at 1e-3 and 30x the depth must still meet the 1e-3 bar; at 1000x activations
+    exceed the fp16 range and option check_range must turn that into a clean error instead of silent inf / NaN, and
+    the same checkpoint must pass in the float32 storage format."""
+    from omnifusion_b200 import _lib
+    from omnifusion_b200.checkpoint import rescale_activations
+    from omnifusion_b200.model.spherical_model_iterative import spherical_fusion
+    sd = rescale_activations(synthetic_state_dict("iterative", 18, 0), s)
+    rgb = urand(2, 3, 64, 128, seed=123)
+    ref = om.forward_iterative(sd, rgb, 2, True)
+    net = spherical_fusion(4, 18, (128, 128), FOV)
+    net.load_state_dict(sd)
+    net = net.to(DEV).eval()
+    net.set_option("check_range", 1)
+    with torch.no_grad():
+        got = net(rgb.to(DEV), iter=2, confidence=True)
+    bad, rows = net.range_report()
+    top = max(v[0] for v in rows.values())
+    e = max_rel(got[1].cpu(), ref[1]) if torch.isfinite(got[1]).all() else float("inf")
+    print(f"[parity] activation scale {s:g}: max |activation| = {top:.3e}, out-of-range tensors = {bad}, depth max_rel = {e:.3e}")
+    if s >= 1e3:
+        assert (bad > 0 and top >= 65504) or e <= REL_TOL
+        if bad:
+            with pytest.raises(_lib.OfbError):
+                net.check_numerics()
+            net.set_option("format", 0)                    # float32 storage, CUDA-core conv engine: no range limit
+            with torch.no_grad():
+                got32 = net(rgb.to(DEV), iter=2, confidence=True)
+            assert net.range_report()[0] == 0
+            assert max_rel(got32[1].cpu(), ref[1]) <= REL_TOL
+    else:
+        assert bad == 0
+        net.check_numerics()
+        assert e <= REL_TOL
