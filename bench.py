@@ -380,6 +380,51 @@ def main():
         wall = (time.perf_counter() - t0) * 1000.0
         parallel.barrier()
         e2e_ms = parallel.max_over_ranks(wall, dev)
+
+        # ---- the same end-to-end loop fed the way a loader feeds it: decoded uint8 HWC panoramas (what cv2.imread
+        # returns, dataset_loader_stanford.py:92-94), converted to float32 CHW / 255 on the device
+        # (preprocess.rgb_u8_to_input, bit-identical to the loader's expression): 4x fewer bytes over PCIe
+        from omnifusion_b200.preprocess import rgb_u8_to_input
+        host_u8 = [(h.permute(0, 2, 3, 1) * 255).round().to(torch.uint8).contiguous().pin_memory() for h in host_in]
+        stage_u8 = [torch.empty(B, he, we, 3, dtype=torch.uint8, device=dev) for _ in range(2)]
+
+        def e2e_u8_run(n_steps):
+            for j in range(2):
+                ev_free[j].record(cur)
+                ev_out[j].record(s_out)
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_free[0])
+                stage_u8[0].copy_(host_u8[0], non_blocking=True)
+                ev_in[0].record(s_in)
+            for i in range(n_steps):
+                j = i & 1
+                if i + 1 < n_steps:
+                    with torch.cuda.stream(s_in):
+                        s_in.wait_event(ev_free[j ^ 1])
+                        stage_u8[j ^ 1].copy_(host_u8[(i + 1) % R], non_blocking=True)
+                        ev_in[j ^ 1].record(s_in)
+                cur.wait_event(ev_in[j])
+                out = fwd(rgb_u8_to_input(stage_u8[j]))
+                ev_free[j].record(cur)
+                cur.wait_event(ev_out[j])
+                result[j].copy_(out[-1], non_blocking=True)
+                ev_fwd[j].record(cur)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_fwd[j])
+                    host_out[j].copy_(result[j], non_blocking=True)
+                    ev_out[j].record(s_out)
+            cur.wait_stream(s_out)
+            cur.wait_stream(s_in)
+
+        e2e_u8_run(2)
+        torch.cuda.synchronize()
+        parallel.barrier()
+        t0 = time.perf_counter()
+        e2e_u8_run(K)
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1000.0
+        parallel.barrier()
+        e2e_u8_ms = parallel.max_over_ranks(wall, dev)
         clocks = sampler.summary()       # sampled over both timed regions (device-resident and end-to-end)
         clocks["sampled_over"] = "device-resident + end-to-end timed regions"
         e2e_check = float(host_out[(K - 1) & 1].mean())        # the result really reached the host
@@ -395,6 +440,7 @@ def main():
         meters.update(depth0, gt, gmask, use_median_scale=True)
         meters.all_reduce()
         eval_all = meters.result()
+        nonfinite = int((~torch.isfinite(depth0)).sum())
         one = metrics.compute_eval_metrics(depth0[:1].contiguous(), gt[:1].contiguous(), gmask[:1].contiguous(), True)
         one_raw = metrics.compute_eval_metrics(depth0[:1].contiguous(), gt[:1].contiguous(), gmask[:1].contiguous(), False)
 
@@ -423,7 +469,7 @@ def main():
         w_ms, w_fl, w_n = sum(r["ms"] for r in wide), sum(r["flops"] for r in wide), sum(r["launches"] for r in wide)
         achieved = w_fl / (w_ms * 1e-3) / 1e12
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r02_v27_ncu_traffic.json")
         if os.path.exists(tpath):
             t = json.load(open(tpath))
             k = t["kernels"].get("conv_tc_kernel<128, 1, 128, 1, 0, 0, 0, 1>")
@@ -455,6 +501,10 @@ def main():
                     "h2d_bytes_per_step": B * 3 * he * we * 4, "d2h_bytes_per_step": B * he * we * 4,
                     "timing": "host wall clock around K pipelined steps (sync at both ends), max over ranks",
                     "result_mean_on_host": e2e_check},
+            "e2e_uint8_input": {"value": world * B * K / (e2e_u8_ms * 1e-3), "unit": "panoramas/s", "ms_per_step": e2e_u8_ms / K,
+                                "h2d_bytes_per_step": B * 3 * he * we, "d2h_bytes_per_step": B * he * we * 4,
+                                "what": "same loop with the panoramas shipped as decoded uint8 HWC (the loader's cv2 output) and "
+                                        "converted on the device by ofb_u8hwc_to_f32chw (+1 kernel per step)"},
             "gpu_launches": launches_per_step * K,
             "launches_per_step": launches_per_step,
             "executed_gflop_per_step": sum(r["flops"] for r in prof_rows) / 2 / 1e9,
@@ -462,7 +512,11 @@ def main():
             "roofline": roofline,
             "kernel_breakdown": [{"name": r["name"], "launches": r["launches"] // 2, "ms_per_step": r["ms"] / 2,
                                   "tflops": (r["flops"] / (r["ms"] * 1e-3) / 1e12) if r["ms"] > 0 else 0,
-                                  "gbs": (r["bytes"] / (r["ms"] * 1e-3) / 1e9) if r["ms"] > 0 else 0} for r in top],
+                                  "gbs": (r["bytes"] / (r["ms"] * 1e-3) / 1e9) if r["ms"] > 0 else 0,
+                                  "frac_of_hbm_peak": (r["bytes"] / (r["ms"] * 1e-3) / 1e9 / pk["hbm"]) if r["ms"] > 0 else 0}
+                                 for r in top],
+            "kernel_breakdown_note": "CUDA events around every launch of two eager forwards (ofb_profile_enable); algorithmic "
+                                     "bytes / FLOPs per launch from the layer shapes; event bracketing adds ~3-5 us to tiny kernels",
             "graph": not args.no_graph}
     line["abs_rel"] = one["abs_rel"]
     line["abs_rel_ref"] = None
@@ -471,6 +525,10 @@ def main():
                 "rank 0 on the synthetic gt = 0.1 + 7.9*rand(seed 456), mask = (gt <= 8) & (gt > 0.1); abs_rel_ref = the "
                 "same for the reference's CPU forward (oracle port) on the same panorama",
         "without_median_scaling": one_raw["abs_rel"], "n_pixels": one["n"],
+        "nonfinite_depth_pixels_rank0": nonfinite,
+        "nonfinite_note": "the reference's own blend table holds NaN weights at two ERP pixels of the 1024x2048 / nrows=5 "
+                          "geometry (cos_c == 0 exactly -> inf * 0, pers2equi_v3.py:114,137-140), so the reference depth - "
+                          "and Abs-Rel - is NaN there too; reproduced bit for bit (tests/test_tables.py)" if nonfinite else None,
         "all_ranks": {"abs_rel": eval_all["abs_rel"], "panoramas": B * world, "n_pixels": eval_all["n"],
                       "how": "per-rank device meters (radix-select median + 7-metric kernel), one NCCL all-reduce(SUM) "
                              "of 8 float64" if world > 1 else "device meters (world size 1: no collective)",

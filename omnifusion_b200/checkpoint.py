@@ -33,7 +33,8 @@ def _bn(spec, p, c):
 
 def key_spec(kind="iterative", npatches=18):
     """OrderedDict name -> shape, in the reference's registration order."""
-    assert kind in ("iterative", "single")
+    # "test": the 256x256-patch variant of network_test.py:271 (down1 512 -> 8 over 8x8 positions), otherwise = iterative
+    assert kind in ("iterative", "single", "test")
     s = OrderedDict()
     s["conv1.weight"] = (64, 3, 7, 7, 1)
     _bn(s, "bn1", 64)
@@ -49,9 +50,10 @@ def key_spec(kind="iterative", npatches=18):
                 s[p + ".downsample.0.weight"] = (c, cin, 1, 1, 1)
                 _bn(s, p + ".downsample.1", c)
         cin = c
-    down = "down1" if kind == "iterative" else "down"
-    s[down + ".weight"] = (EMB // 16, 512, 1, 1, 1)
-    s[down + ".bias"] = (EMB // 16,)
+    down = "down" if kind == "single" else "down1"
+    dch = EMB // 64 if kind == "test" else EMB // 16
+    s[down + ".weight"] = (dch, 512, 1, 1, 1)
+    s[down + ".bias"] = (dch,)
     s["transformer.pos_emb"] = (1, npatches, EMB)
     for i in range(DEPTH):
         p = f"transformer.layer.{i}"
@@ -75,9 +77,9 @@ def key_spec(kind="iterative", npatches=18):
     for head in ("pred", "weight_pred"):
         s[head + ".weight"] = (1, 32, 3, 3, 1)
         s[head + ".bias"] = (1,)
-    mlps = ("mlp_points1", "mlp_points2") if kind == "iterative" else ("mlp_points",)
+    mlps = ("mlp_points",) if kind == "single" else ("mlp_points1", "mlp_points2")
     for m in mlps:
-        s[m + ".0.weight"] = (16, 3 if kind == "iterative" else 5, 1, 1)
+        s[m + ".0.weight"] = (16, 5 if kind == "single" else 3, 1, 1)
         _bn(s, m + ".1", 16)
         s[m + ".3.weight"] = (64, 16, 1, 1)
         _bn(s, m + ".4", 64)
@@ -155,7 +157,7 @@ def rescale_activations(sd, s, kind="iterative"):
         if p != "bn1" and p not in mlp:                      # input already scaled by s
             out[p + ".running_mean"] *= s
             out[p + ".running_var"] *= s * s
-    down = "down1" if kind == "iterative" else "down"
+    down = "down" if kind == "single" else "down1"
     out[down + ".weight"] /= s
     out["transformer.encoder_norm.weight"] *= s
     out["transformer.encoder_norm.bias"] *= s

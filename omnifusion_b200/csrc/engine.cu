@@ -40,6 +40,7 @@ int blend_conf_launch(const float* pred_w, const float* conf, bool interleaved, 
                       cudaStream_t s);
 int deinterleave_launch(const float* src_pairs, size_t n, int comp, float* dst, cudaStream_t s);
 int zero_stem_pads(void* patches, int imgs, int P, cudaStream_t s);
+int token_pack(const void* down, const float* pos_emb, int imgs, int N, int spatial, int cstride, void* tokens, int fmt, cudaStream_t s);
 int range_launch(const void* p, size_t n, int fmt, unsigned int* out2, cudaStream_t s);
 long long* conv_tc_debug_buffer();
 int conv_tc_timeline_slots();
@@ -86,12 +87,15 @@ struct ofb_handle {
   float *pos_emb = nullptr, *enc_g = nullptr, *enc_b = nullptr;
   int pos_patches = 0;
   ConvW down;
+  int down_cout = 32;              // logical output channels of the token reduction conv (down.cout is padded to 32s)
   float *pred_w = nullptr, *conf_w = nullptr;
   ConvW heads16;                   // both heads as one 16-channel 3x3 conv (0 = pred, 1 = weight_pred) for the tcgen05 engine
   int dbg_blocks = 6;              // timing experiments only: number of transformer blocks executed
   int splitk = 4;                  // K slices of the two 512-wide token linears on the tcgen05 engine (1 = off)
   int heads_tc = 1;                // run the heads on the tensor pipe (split-half format, 128-pixel rows)
   int attn_tc = 1;                 // attention core on the tensor pipe (split-half format; tcgen05 QK^T and PV)
+  int no_point_feat = 0;           // ablation of network_360d.py:325 - layer1 is used without the point-feature add
+  int no_transformer = 0;          // ablation of network_360d.py:330-335 - no token path, layer4 goes straight to the decoder
   int check_range = 0;             // after every forward: max |x| / non-finite count of each registered activation
   unsigned int* range_dev = nullptr;            // [kRangeSlots][2]
   std::vector<std::string> range_names;         // names of the slots filled by the last forward
@@ -152,7 +156,7 @@ static long long numel(const ofb_tensor_desc* t) {
 }
 
 // (O,I,kh,kw[,1]) or (O,I) -> OHWI, optional zero padding of I to cin_pad
-static int pack_conv(ofb_handle* h, const TMap& m, const std::string& wname, ConvW* cw, int cin_pad = 0) {
+static int pack_conv(ofb_handle* h, const TMap& m, const std::string& wname, ConvW* cw, int cin_pad = 0, int cout_pad = 0) {
   const ofb_tensor_desc* t = find(m, wname);
   if (!t) return -1;
   OFB_CHECK(t->ndim >= 2, "load_weights: '%s' must have >= 2 dims", wname.c_str());
@@ -161,13 +165,14 @@ static int pack_conv(ofb_handle* h, const TMap& m, const std::string& wname, Con
   OFB_CHECK(kh == kw, "load_weights: '%s' non-square kernel", wname.c_str());
   OFB_CHECK(t->ndim < 5 || t->shape[4] == 1, "load_weights: '%s' trailing dim must be 1", wname.c_str());
   int Ip = cin_pad ? cin_pad : I;
-  std::vector<float> p((size_t)O * kh * kw * Ip, 0.f);
+  const int Op = cout_pad > O ? cout_pad : O;          // extra output channels = zero filters
+  std::vector<float> p((size_t)Op * kh * kw * Ip, 0.f);
   for (int o = 0; o < O; ++o)
     for (int i = 0; i < I; ++i)
       for (int y = 0; y < kh; ++y)
         for (int x = 0; x < kw; ++x)
           p[(((size_t)o * kh + y) * kw + x) * Ip + i] = t->data[(((size_t)o * I + i) * kh + y) * kw + x];
-  cw->cout = O; cw->cin = Ip; cw->k = kh;
+  cw->cout = Op; cw->cin = Ip; cw->k = kh;
   if (dev_upload(h, p, &cw->w)) return -1;
   // split-half planes for the tcgen05 engine: scale by a power of two so max|w| lands in
   // [2^13, 2^14) and both the hi and the lo plane stay in fp16's normal range
@@ -214,9 +219,16 @@ static int conv_bn(ofb_handle* h, const TMap& m, const std::string& key, const s
   return 0;
 }
 
-static int linear(ofb_handle* h, const TMap& m, const std::string& prefix, bool bias, ConvW* cw) {
-  if (pack_conv(h, m, prefix + ".weight", cw)) return -1;
-  if (bias && pack_vec(h, m, prefix + ".bias", &cw->shift, cw->cout)) return -1;
+static int linear(ofb_handle* h, const TMap& m, const std::string& prefix, bool bias, ConvW* cw, int cout_pad = 0) {
+  if (pack_conv(h, m, prefix + ".weight", cw, 0, cout_pad)) return -1;
+  if (bias) {
+    const ofb_tensor_desc* t = find(m, prefix + ".bias");
+    if (!t) return -1;
+    OFB_CHECK(numel(t) <= cw->cout, "load_weights: '%s.bias' has %lld elements for %d outputs", prefix.c_str(), numel(t), cw->cout);
+    std::vector<float> v(cw->cout, 0.f);
+    for (long long i = 0; i < numel(t); ++i) v[i] = t->data[i];
+    if (dev_upload(h, v, &cw->shift)) return -1;
+  }
   return 0;
 }
 
@@ -282,7 +294,13 @@ static int load_all(ofb_handle* h, const TMap& m, bool single) {
       if (m.count(p + ".downsample.0.weight"))
         if (conv_bn(h, m, p + ".ds", p + ".downsample.0.weight", p + ".downsample.1")) return -1;
     }
-  if (linear(h, m, single ? "down" : "down1", true, &h->down)) return -1;
+  {  // token reduction conv: 512 -> 32 (128x128 patches) or 512 -> 8 (256x256, network_test.py:271); the conv engines
+     // work on multiples of 32 output channels, so a narrower one is padded with zero filters (token_pack skips them)
+    const ofb_tensor_desc* dw = find(m, single ? "down.weight" : "down1.weight");
+    if (!dw) return -1;
+    h->down_cout = (int)dw->shape[0];
+    if (linear(h, m, single ? "down" : "down1", true, &h->down, (h->down_cout + 31) / 32 * 32)) return -1;
+  }
   const ofb_tensor_desc* pe = find(m, "transformer.pos_emb");
   if (!pe) return -1;
   h->pos_patches = (int)pe->shape[1];
@@ -375,7 +393,7 @@ static size_t plan_buffers(ofb_handle* h, int imgs, int P, Buffers* b) {
   b->l2t = pl.take(s2); b->l2a = pl.take(s2); b->l2b = pl.take(s2); b->l2d = pl.take(s2); b->layer2 = pl.take(s2);
   b->l3t = pl.take(s3); b->l3a = pl.take(s3); b->l3b = pl.take(s3); b->l3d = pl.take(s3); b->layer3 = pl.take(s3);
   b->l4t = pl.take(s4); b->l4a = pl.take(s4); b->l4b = pl.take(s4); b->l4d = pl.take(s4); b->layer4 = pl.take(s4);
-  b->down = pl.take(I * 512); b->tok = pl.take(I * 512); b->ln = pl.take(I * 512); b->q = pl.take(I * 512);
+  b->down = pl.take(I * (size_t)p32 * p32 * 32 > I * 512 ? I * (size_t)p32 * p32 * 32 : I * 512); b->tok = pl.take(I * 512); b->ln = pl.take(I * 512); b->q = pl.take(I * 512);
   b->kv = pl.take(I * 1536); b->att = pl.take(I * 512); b->tok2 = pl.take(I * 512); b->fc1 = pl.take(I * 2048);
   b->enc = pl.take(I * 512);
   b->part = pl.take(I * 512 * 4);                  // split-K partial sums of attn.proj / mlp.fc2 (4 slices)
@@ -549,23 +567,30 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
                             OFB_LAYOUT_FOLDED, vs)) return -1; }
       depth = b.depth_p;
     }
-    const Mlp& mp = h->mlp[it > 0 ? 1 : 0];
-    OFB_CHECK(mp.cin == g.pts_c, "forward: point table has %d channels, mlp expects %d", g.pts_c, mp.cin);
-    { Prof pr(h, s, "point_embed", 0.0, 4.0*((double)imgs*p4*p4*128));
-    if (ofb_point_embed_f32(g.pts, N, mp.cin, p4, depth, imgs, mp.w1, mp.s1, mp.t1, mp.w2, mp.s2, mp.t2,
-                            b.layer1_pre, b.layer1, F, vs)) return -1; }
-    if (run_res_layer(c, 1, b.layer1, 64, p4, b.l2t, b.l2a, b.l2b, b.l2d, b.layer2)) return -1;
+    float* const layer1 = h->no_point_feat ? b.layer1_pre : b.layer1;
+    if (!h->no_point_feat) {
+      const Mlp& mp = h->mlp[it > 0 ? 1 : 0];
+      OFB_CHECK(mp.cin == g.pts_c, "forward: point table has %d channels, mlp expects %d", g.pts_c, mp.cin);
+      { Prof pr(h, s, "point_embed", 0.0, 4.0*((double)imgs*p4*p4*128));
+      if (ofb_point_embed_f32(g.pts, N, mp.cin, p4, depth, imgs, mp.w1, mp.s1, mp.t1, mp.w2, mp.s2, mp.t2,
+                              b.layer1_pre, b.layer1, F, vs)) return -1; }
+    }
+    if (run_res_layer(c, 1, layer1, 64, p4, b.l2t, b.l2a, b.l2b, b.l2d, b.layer2)) return -1;
     if (run_res_layer(c, 2, b.layer2, 128, P / 8, b.l3t, b.l3a, b.l3b, b.l3d, b.layer3)) return -1;
     if (run_res_layer(c, 3, b.layer3, 256, P / 16, b.l4t, b.l4a, b.l4b, b.l4d, b.layer4)) return -1;
 
-    // tokens: down1 1x1 conv (+bias) over the 4x4x512 map -> (imgs,512) (:330-331)
+    // tokens: down1 1x1 conv (+bias) over the SxSx512 map (S = P/32) -> (imgs,512) (:330-331)
+    const int S32 = P / 32;
+    if (!h->no_transformer) {
+    OFB_CHECK(h->down_cout * S32 * S32 == 512, "forward: down conv has %d channels, %dx%d patches need %d (token width 512)",
+              h->down_cout, P, P, 512 / (S32 * S32));
     {
-      Ctx c16{h, s, imgs * 16};
+      Ctx c16{h, s, imgs * S32 * S32};
       if (run_linear(c16, h->down, b.layer4, nullptr, OFB_ACT_NONE, b.down)) return -1;
     }
     OFB_CHECK(h->pos_patches == N, "forward: pos_emb has %d patches, geometry has %d", h->pos_patches, N);
     { Prof pr(h, s, "token_pack", 0.0, 4.0*((double)imgs*1024));
-    if (ofb_token_pack_f32(b.down, h->pos_emb, imgs, N, b.tok, F, vs)) return -1; }
+    if (token_pack(b.down, h->pos_emb, imgs, N, S32, h->down.cout, b.tok, F, s)) return -1; }
     float* x = b.tok;
     float* y = b.tok2;
     const int SK = (F == OFB_FMT_SPLIT16 && h->engine != OFB_ENGINE_SIMT) ? h->splitk : 1;
@@ -609,10 +634,11 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
     { Prof pr(h, s, "layernorm", 0.0, 4.0*((double)imgs*1024));
     if (ofb_layernorm_f32(x, h->enc_g, h->enc_b, imgs, 512, 1e-6f, b.enc, F, OFB_FMT_F32, vs)) return -1; }
     }
+    }   // !no_transformer
 
     // decoder (:337-369); the token broadcast-add (:334-335) is fused into the first upsample
     { Prof pr(h, s, "upsample2x_c512", 0.0, 4.0*5.0*(double)imgs*(P / 32)*(P / 32)*512);
-    if (ofb_upsample2x_f32(b.layer4, b.enc, imgs, P / 32, P / 32, 512, b.up0, F, vs)) return -1; }
+    if (ofb_upsample2x_f32(b.layer4, h->no_transformer ? nullptr : b.enc, imgs, P / 32, P / 32, 512, b.up0, F, vs)) return -1; }
     if (run_conv(c, h->conv["de_conv0_0"], b.up0, 512, nullptr, 0, P / 16, P / 16, 1, 1, nullptr, OFB_ACT_RELU, b.d00)) return -1;
     if (run_conv(c, h->conv["de_conv0_1"], b.d00, 256, b.layer3, 256, P / 16, P / 16, 1, 1, nullptr, OFB_ACT_RELU, b.d01)) return -1;
     { Prof pr(h, s, "upsample2x_c128", 0.0, 4.0*5.0*(double)imgs*(P / 16)*(P / 16)*128);
@@ -622,7 +648,7 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
     { Prof pr(h, s, "upsample2x_c64", 0.0, 4.0*5.0*(double)imgs*(P / 8)*(P / 8)*64);
     if (ofb_upsample2x_f32(b.d11, nullptr, imgs, P / 8, P / 8, 64, b.up2, F, vs)) return -1; }
     if (run_conv(c, h->conv["de_conv2_0"], b.up2, 64, nullptr, 0, p4, p4, 1, 1, nullptr, OFB_ACT_RELU, b.d20)) return -1;
-    if (run_conv(c, h->conv["de_conv2_1"], b.d20, 64, b.layer1, 64, p4, p4, 1, 1, nullptr, OFB_ACT_RELU, b.d21)) return -1;
+    if (run_conv(c, h->conv["de_conv2_1"], b.d20, 64, layer1, 64, p4, p4, 1, 1, nullptr, OFB_ACT_RELU, b.d21)) return -1;
     { Prof pr(h, s, "upsample2x_c64", 0.0, 4.0*5.0*(double)imgs*(p4)*(p4)*64);
     if (ofb_upsample2x_f32(b.d21, nullptr, imgs, p4, p4, 64, b.up3, F, vs)) return -1; }
     if (run_conv(c, h->conv["de_conv3_0"], b.up3, 64, nullptr, 0, P / 2, P / 2, 1, 1, nullptr, OFB_ACT_RELU, b.d30)) return -1;
@@ -656,7 +682,7 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
   reg(h, "pool", b.pool, imgs, p4, p4, 64); reg(h, "layer1_pre", b.layer1_pre, imgs, p4, p4, 64);
   reg(h, "layer1", b.layer1, imgs, p4, p4, 64); reg(h, "layer2", b.layer2, imgs, P / 8, P / 8, 128);
   reg(h, "layer3", b.layer3, imgs, P / 16, P / 16, 256); reg(h, "layer4", b.layer4, imgs, P / 32, P / 32, 512);
-  reg(h, "tokens", b.down, imgs, 4, 4, 32); reg(h, "encoded", b.enc, imgs, 1, 1, 512, 0);
+  reg(h, "tokens", b.down, imgs, P / 32, P / 32, h->down.cout); reg(h, "encoded", b.enc, imgs, 1, 1, 512, 0);
   reg(h, "de_conv0_1", b.d01, imgs, P / 16, P / 16, 128); reg(h, "de_conv1_1", b.d11, imgs, P / 8, P / 8, 64);
   reg(h, "de_conv2_1", b.d21, imgs, p4, p4, 64); reg(h, "de_conv3_1", b.d31, imgs, P / 2, P / 2, 32);
   reg(h, "de_conv4_0", b.d40, imgs, P, P, 32); reg(h, "pred_patch", b.pred, imgs, P, P, 1, pairs ? 2 : 0);
@@ -753,7 +779,10 @@ extern "C" int ofb_destroy(ofb_handle* h) {
 extern "C" int ofb_set_geometry(ofb_handle* h, const ofb_geometry* g) {
   OFB_CHECK(h && g, "set_geometry: null pointer");
   OFB_CHECK(g->grid_hi && g->grid_lo && g->pts && g->blend_rowptr && g->blend_idx && g->blend_w, "set_geometry: null table");
-  OFB_CHECK(g->patch == 128, "set_geometry: the token path is hard-wired to patch 128 (32*(P/32)^2 == 512), got %d", g->patch);
+  // 128 is the reference's default; 256 is the network_test.py variant (down1 512 -> 8 over 8x8 positions); 64 works
+  // the same way (down 512 -> 128 over 2x2).  The token width 32*(P/32)^2-independent 512 is checked against the
+  // loaded down conv at forward time.
+  OFB_CHECK(g->patch == 64 || g->patch == 128 || g->patch == 256, "set_geometry: patch must be 64, 128 or 256, got %d", g->patch);
   OFB_CHECK(g->n_patch > 0 && g->n_patch <= 64, "set_geometry: n_patch must be in [1,64], got %d", g->n_patch);
   OFB_CHECK(g->pts_c == 3 || g->pts_c == 5, "set_geometry: pts_c must be 3 or 5");
   h->geo = *g;
@@ -787,6 +816,8 @@ extern "C" int ofb_set_option(ofb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "heads_tc")) h->heads_tc = value;
   else if (!strcmp(key, "attn_tc")) h->attn_tc = value;
   else if (!strcmp(key, "check_range")) h->check_range = value;
+  else if (!strcmp(key, "no_point_feat")) h->no_point_feat = value != 0;
+  else if (!strcmp(key, "no_transformer")) h->no_transformer = value != 0;
   else if (!strcmp(key, "splitk")) h->splitk = value == 2 || value == 4 ? value : 1;
   else if (!strcmp(key, "khr_row64")) h->tc.khr_row64 = value != 0;
   else if (!strcmp(key, "khr_bw")) h->tc.khr_bw = value == 32 ? 32 : 16;    // tile width of the kh-reuse kernels

@@ -317,15 +317,19 @@ point_embed_kernel(const float* __restrict__ pts, int N, int cin, int p,
 }
 
 // ----------------------------------------------------------------- token pack
+// down (imgs, S, S, Cd) with S*S*Cd == 512 -> tokens (imgs, 512), token index = c*S*S + i*S + j (the reference's
+// reshape of the (B, Cd, S, S, N) map, spherical_model_iterative.py:330-331), + pos_emb.  S = 4, Cd = 32 for 128x128
+// patches; S = 8, Cd = 8 for the 256x256 variant (network_test.py:271).
 template <bool SPLIT>
 __global__ void token_pack_kernel(const void* __restrict__ down, const float* __restrict__ pos,
-                                  int imgs, int N, void* __restrict__ tokens) {
+                                  int imgs, int N, int ss, int cstride, void* __restrict__ tokens) {
+  // cstride: channels per position of `down` in memory (>= 512 / ss: narrower reductions are padded to 32 channels)
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= imgs * 512) return;
   int img = i >> 9, t = i & 511;
-  int c = t >> 4, ij = t & 15;
-  const size_t plane = (size_t)imgs * 512;
-  float v = act_ld1<SPLIT>(down, (size_t)img * 512 + ij * 32 + c, plane) + __ldg(&pos[(img % N) * 512 + t]);
+  int c = t / ss, ij = t - c * ss;
+  const size_t in_plane = (size_t)imgs * ss * cstride, plane = (size_t)imgs * 512;
+  float v = act_ld1<SPLIT>(down, ((size_t)img * ss + ij) * cstride + c, in_plane) + __ldg(&pos[(img % N) * 512 + t]);
   act_st1<SPLIT>(tokens, i, plane, v);
 }
 
@@ -733,14 +737,22 @@ extern "C" int ofb_point_embed_f32(const float* pts, int N, int cin, int p, cons
   return 0;
 }
 
-extern "C" int ofb_token_pack_f32(const void* down, const float* pos_emb, int imgs, int N, void* tokens, int fmt,
-                                  void* stream) {
+namespace ofb {
+int token_pack(const void* down, const float* pos_emb, int imgs, int N, int spatial, int cstride, void* tokens, int fmt, cudaStream_t s) {
   OFB_CHECK(down && pos_emb && tokens && OFB_FMT_OK(fmt), "token_pack: bad arguments");
+  const int ss = spatial * spatial;
+  OFB_CHECK(ss > 0 && 512 % ss == 0 && cstride >= 512 / ss, "token_pack: %dx%d positions x %d channels do not hold the 512-wide token", spatial, spatial, cstride);
   int blocks = cdiv((long long)imgs * 512, 256);
-  if (fmt) token_pack_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(down, pos_emb, imgs, N, tokens);
-  else token_pack_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(down, pos_emb, imgs, N, tokens);
+  if (fmt) token_pack_kernel<true><<<blocks, 256, 0, s>>>(down, pos_emb, imgs, N, ss, cstride, tokens);
+  else token_pack_kernel<false><<<blocks, 256, 0, s>>>(down, pos_emb, imgs, N, ss, cstride, tokens);
   OFB_LAUNCH_CHECK();
   return 0;
+}
+}  // namespace ofb
+
+extern "C" int ofb_token_pack_f32(const void* down, const float* pos_emb, int imgs, int N, void* tokens, int fmt,
+                                  void* stream) {
+  return token_pack(down, pos_emb, imgs, N, 4, 32, tokens, fmt, (cudaStream_t)stream);
 }
 
 extern "C" int ofb_layernorm_f32(const void* x, const float* gamma, const float* beta, int rows, int dim,

@@ -26,6 +26,7 @@ class _Holder(nn.Module):
 
 class SphericalFusionBase(nn.Module):
     KIND = "iterative"
+    PATCH_SIZES = ((128, 128),)      # what the token width allows: 32 * (P / 32)^2 == 512
 
     def __init__(self, nrows=4, npatches=18, patch_size=(128, 128), fov=(80, 80)):
         super().__init__()
@@ -33,10 +34,10 @@ class SphericalFusionBase(nn.Module):
         self.npatches = npatches
         self.patch_size = tables.pair(patch_size)
         self.fov = tables.pair(fov)
-        if self.patch_size != (128, 128):
+        if self.patch_size not in self.PATCH_SIZES:
             # the reference hard-wires the token width to 32*(P/32)^2 == 512
             # (spherical_model_iterative.py:274,276,331): any other patch size shape-errors there too
-            raise ValueError(f"patch_size must be (128, 128), got {self.patch_size}")
+            raise ValueError(f"patch_size must be one of {self.PATCH_SIZES}, got {self.patch_size}")
         if tables.NUM_PATCHES.get(nrows) != npatches:
             raise ValueError(f"nrows={nrows} has {tables.NUM_PATCHES.get(nrows)} patches, npatches={npatches}")
         init = synthetic_state_dict(self.KIND, npatches, seed=0)
@@ -130,7 +131,7 @@ class SphericalFusionBase(nn.Module):
         return low_geo["xyz"]
 
     def _ensure_geometry(self, erp_hw, device):
-        key = (erp_hw, str(device))
+        key = (erp_hw, str(device), self.fov, self.nrows, self.patch_size)
         if key == self._geometry_key:
             return
         p = self.patch_size[0]

@@ -116,7 +116,7 @@ def _unfold(x, B):
     return x.reshape(B, BN // B, C, H, W).permute(0, 2, 3, 4, 1)
 
 
-def patch_network(sd, patches, point_feat, bs, down_name="down1", trace=None):
+def patch_network(sd, patches, point_feat, bs, down_name="down1", trace=None, use_points=True, use_transformer=True):
     """Encoder + token fusion + decoder + both heads on folded patches.
 
     patches (B*N,3,P,P); point_feat (B*N,64,P/4,P/4).
@@ -129,19 +129,21 @@ def patch_network(sd, patches, point_feat, bs, down_name="down1", trace=None):
     pool = F.max_pool2d(conv1, kernel_size=3, stride=2, padding=1)
     layer1 = _res_layer(sd, "layer1", pool, 3, 1)
     tr["layer1_pre"] = layer1
-    layer1 = layer1 + point_feat
+    if use_points:                                             # network_360d.py:325 comments this add out
+        layer1 = layer1 + point_feat
     layer2 = _res_layer(sd, "layer2", layer1, 4, 2)
     layer3 = _res_layer(sd, "layer3", layer2, 6, 2)
     layer4 = _res_layer(sd, "layer4", layer3, 3, 2)
     tr.update(conv1=conv1, pool=pool, layer1=layer1, layer2=layer2, layer3=layer3, layer4=layer4)
 
     # token = flattened (c, i, j) of the 32x4x4 map (spherical_model_iterative.py:330-331)
-    down = _conv(sd, down_name, layer4)                       # (B*N,32,4,4)
-    tokens = down.reshape(bs, n_patch, -1)                     # (B,N,512)
-    tr["tokens"] = tokens
-    enc = transformer(sd, tokens, trace=tr)                    # (B,N,512)
-    tr["encoded"] = enc
-    layer4 = layer4 + enc.reshape(bs * n_patch, -1, 1, 1)      # broadcast over 4x4 (:334-335)
+    if use_transformer:                                        # network_360d.py:330-335 comments the token path out
+        down = _conv(sd, down_name, layer4)                       # (B*N,32,4,4); (B*N,8,8,8) for 256x256 patches
+        tokens = down.reshape(bs, n_patch, -1)                     # (B,N,512)
+        tr["tokens"] = tokens
+        enc = transformer(sd, tokens, trace=tr)                    # (B,N,512)
+        tr["encoded"] = enc
+        layer4 = layer4 + enc.reshape(bs * n_patch, -1, 1, 1)      # broadcast over the SxS map (:334-335)
 
     def up(x, ref):
         return F.interpolate(x, size=ref.shape[-2:], mode="bilinear", align_corners=False)
@@ -228,6 +230,32 @@ def forward_single(sd, rgb, confidence=True, nrows=4, fov=(80, 80), patch_size=(
     tr = trace if trace is not None else {}
     pred, weight, _ = patch_network(sd, _fold(patches), pf, bs, down_name="down", trace=tr)
     return _merge(pred, weight, bs, confidence, fov, nrows, (ph, pw), erp_size)
+
+
+@torch.no_grad()
+def forward_360d(sd, high_res, fov, patch_size, nrows):
+    """network_360d.py:308-380: encoder/decoder without point features and without the transformer, one pass, plain
+    pers2equi blend of relu(pred)."""
+    sd = strip_module_prefix(sd)
+    bs = high_res.shape[0]
+    erp_size = tuple(high_res.shape[-2:])
+    ph, pw = _pair(patch_size)
+    patches, _, _, _ = equi2pers(high_res, fov, nrows, (ph, pw))
+    pred, weight, _ = patch_network(sd, _fold(patches), None, bs, use_points=False, use_transformer=False)
+    return _merge(pred, weight, bs, False, fov, nrows, (ph, pw), erp_size)
+
+
+@torch.no_grad()
+def forward_test(sd, high_res, fov, patch_size, nrows, iters):
+    """network_test.py:308-460: the iterative network with down1 512 -> 8 (256x256 patches) and the plain blend.
+    Like the reference, iterations >= 1 return the PATCH prediction relu(pred) (B,1,P,P,N) - the pers2equi of the
+    refinement pass is commented out there (:441-445) - so only iters <= 2 is meaningful."""
+    assert iters in (1, 2)
+    tr = {}
+    outs = forward_iterative(sd, high_res, iters, False, nrows=nrows, fov=fov, patch_size=_pair(patch_size), trace=tr)
+    if iters == 2:
+        outs = [outs[0], _unfold(torch.relu(tr["iter1"]["pred_raw"]), high_res.shape[0])]
+    return outs
 
 
 def abs_rel_error(pred, gt, mask):

@@ -185,7 +185,43 @@ def model_case(tag, kind, nrows, erp, bs, iters, conf, stride, seed=123):
     in_fresh_cwd(run)
 
 
+def variant_case(tag, which, erp, bs, seed=123):
+    """network_360d.py / network_test.py through the real reference classes."""
+    def run(d):
+        import network_360d
+        import network_test
+        rgb = rand((bs, 3, *erp), seed)
+        if which == "360d":
+            sd = synthetic_state_dict("iterative", 18, 0)
+            net = network_360d.spherical_fusion().eval()
+            net.load_state_dict(sd)
+            with torch.no_grad():
+                outs = [net(rgb, FOV, (128, 128), 4)]
+            o_outs = [om.forward_360d(sd, rgb, FOV, (128, 128), 4)]
+        else:
+            sd = synthetic_state_dict("test", 18, 0)
+            net = network_test.spherical_fusion().eval()
+            net.load_state_dict(sd)
+            with torch.no_grad():
+                outs = net(rgb, FOV, (256, 256), 4, 2)
+            o_tr = {}
+            o_erp = om.forward_iterative(sd, rgb, 2, False, nrows=4, fov=FOV, patch_size=(256, 256), trace=o_tr)
+            # the reference appends the PATCH prediction relu(pred) (B,1,P,P,N) for iterations >= 1 (network_test.py:441-445)
+            o_outs = [o_erp[0], om._unfold(torch.relu(o_tr["iter1"]["pred_raw"]), bs)]
+        rel = max((((a - b).abs() / a.abs().clamp_min(1e-6)).max().item()) for a, b in zip(outs, o_outs))
+        meta["checks"][tag] = {"oracle_vs_reference_max_rel": rel, "depth_min": min(o.min().item() for o in outs),
+                               "depth_max": max(o.max().item() for o in outs), "depth_std": outs[-1].std().item()}
+        arrs = {"which": which, "erp": np.array(erp), "bs": bs, "seed": seed}
+        for i, o in enumerate(outs):
+            arrs[f"out{i}"] = o if o.dim() == 4 else o[:, :, ::8, ::8, :]      # patch-space output: strided
+            arrs[f"out{i}_mean"] = o.double().mean()
+        save(f"variant_{tag}", **arrs)
+    in_fresh_cwd(run)
+
+
 CASES = {
+    "net360d_small": lambda: variant_case("net360d_small", "360d", (64, 128), 2),
+    "nettest_p256_small": lambda: variant_case("nettest_p256_small", "test", (64, 128), 1),
     **{f"small_n{n}": (lambda n=n: resampler_case(f"small_n{n}", n, (16, 32), 16, 1, 10 + n)) for n in (3, 4, 5, 6)},
     "mid_n4_p32": lambda: resampler_case("mid_n4_p32", 4, (128, 256), 32, 4, 21),
     "full_n4": lambda: resampler_case("full_n4", 4, (512, 1024), 128, 16, 22),

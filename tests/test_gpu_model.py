@@ -316,3 +316,50 @@ def test_activation_range_of_the_split_half_format(s):
         assert bad == 0
         net.check_numerics()
         assert e <= REL_TOL
+
+
+def test_network_360d_ablation_matches_reference_golden(golden_dir):
+    """network_360d.py:308-380 (test_360d_tmp.py:198): no point-feature add, no transformer, plain blend - behind
+    omnifusion_b200.network_360d.spherical_fusion with the reference's call signature."""
+    from omnifusion_b200.network_360d import spherical_fusion
+    z = np.load(os.path.join(golden_dir, "variant_net360d_small.npz"))
+    erp = tuple(int(v) for v in z["erp"])
+    net = spherical_fusion()
+    net.load_state_dict(synthetic_state_dict("iterative", 18, 0))
+    net = net.to(DEV).eval()
+    rgb = urand(int(z["bs"]), 3, *erp, seed=int(z["seed"])).to(DEV)
+    with torch.no_grad():
+        got = net(rgb, FOV, (128, 128), 4)
+    assert torch.is_tensor(got) and got.shape == (int(z["bs"]), 1, *erp)
+    e = max_rel(got.cpu(), torch.from_numpy(z["out0"]))
+    print(f"[parity] network_360d variant: max_rel={e:.3e}")
+    assert e <= REL_TOL
+    # other geometry at call time, like the reference's signature allows
+    ref5 = om.forward_360d(synthetic_state_dict("iterative", 18, 0), rgb.cpu(), FOV, (128, 128), 5)
+    with torch.no_grad():
+        got5 = net(rgb, FOV, (128, 128), 5)
+    assert max_rel(got5.cpu(), ref5) <= REL_TOL
+
+
+def test_network_test_256_patch_variant_matches_reference_golden(golden_dir):
+    """network_test.py:271,308-460: 256x256 patches, down1 512 -> 8 over the 8x8 layer4 map, plain blend; iter = 2
+    returns [ERP depth, patch prediction] exactly like the reference."""
+    from omnifusion_b200.network_test import spherical_fusion
+    z = np.load(os.path.join(golden_dir, "variant_nettest_p256_small.npz"))
+    erp = tuple(int(v) for v in z["erp"])
+    net = spherical_fusion()
+    net.load_state_dict(synthetic_state_dict("test", 18, 0))
+    net = net.to(DEV).eval()
+    rgb = urand(int(z["bs"]), 3, *erp, seed=int(z["seed"])).to(DEV)
+    with torch.no_grad():
+        got = net(rgb, FOV, (256, 256), 4, 2)
+    assert len(got) == 2 and got[0].shape == (1, 1, *erp) and got[1].shape == (1, 1, 256, 256, 18)
+    e0 = max_rel(got[0].cpu(), torch.from_numpy(z["out0"]))
+    ref1 = torch.from_numpy(z["out1"])
+    g1 = got[1].cpu()[:, :, ::8, ::8, :]
+    e1 = ((g1 - ref1).abs().max() / ref1.abs().max()).item()
+    print(f"[parity] network_test (P=256) variant: ERP max_rel={e0:.3e}, patch prediction max_err/absmax={e1:.3e}")
+    assert e0 <= REL_TOL and e1 <= REL_TOL
+    assert abs(got[1].double().mean().item() - float(z["out1_mean"])) <= REL_TOL * abs(float(z["out1_mean"]))
+    with pytest.raises(ValueError):
+        net(rgb, FOV, (128, 128), 4, 1)
