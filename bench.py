@@ -57,29 +57,34 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi SM clocks and throttle reasons during the timed region."""
+    """Samples nvidia-smi SM clocks and throttle reasons during the timed regions: ONE streaming nvidia-smi process
+    (-lms 20: a line every 20 ms) read by this thread, instead of one process start per sample."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.proc = index, [], None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for ln in self.proc.stdout:
+                f = [x.strip() for x in ln.strip().split(",")]
                 if len(f) >= 8:
                     self.rows.append(f)
-            except Exception:
-                pass
-            time.sleep(0.03)
+        except Exception:
+            pass
 
     def summary(self):
-        self.stop_flag = True
+        try:
+            if self.proc is not None:
+                self.proc.terminate()
+        except Exception:
+            pass
         self.join(timeout=6)
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
