@@ -292,7 +292,8 @@ long long ofb_workspace_generation(ofb_handle* h);
 /* Engine knobs (key, value): "engine" conv engine (OFB_ENGINE_*), "chunk" panoramas per internal chunk
  * (0 = auto), "dedup" reuse of the iteration-invariant stem/layer1 across iterations (default 1), "format"
  * activation storage (OFB_FMT_*), "fuse_ups" fold the last decoder upsample into de_conv4_0 (default 1),
- * "check_range" see ofb_range_report, "heads_tc" heads on the tensor pipe (default 1), "attn_tc" attention core on the tensor pipe (default 1), "lanes" 2 = two concurrent half-batches on two streams
+ * "check_range" see ofb_range_report, "chain" image-stationary layer chains: 0 off, 1 (default) for the encoder stages whose
+ * dependencies stay inside a CTA pair (layer2), 2 also stages that hand images over between clusters (layer3), "heads_tc" heads on the tensor pipe (default 1), "attn_tc" attention core on the tensor pipe (default 1), "lanes" 2 = two concurrent half-batches on two streams
  * (default 1), "cta2" / "pdl" / "store128" / "fill_div" / "direct32" / "khr_bw" / "khr_row64" tcgen05 launch variants (per handle);
  * "tc_debug" / "dbg_blocks" switch parts of the pipeline OFF for timing experiments (results are wrong). */
 int ofb_set_option(ofb_handle* h, const char* key, int value);
@@ -336,6 +337,7 @@ int ofb_debug_set(int tc_debug);      /* "tc_debug" for convs launched directly 
  * accumulator complete, last store issued, kernel end).  Copies up to max_slots x 8 int64 of the launches since the
  * last call to host_dst and returns their number (tools/timeline.py). */
 int ofb_debug_timeline(long long* host_dst, int max_slots);
+int ofb_debug_timeline_raw(long long* host_dst);   /* the whole 1024 x 8 stamp buffer, no reset (tools/chain_timeline.py) */
 
 #ifdef __cplusplus
 }

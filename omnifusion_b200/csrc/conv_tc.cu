@@ -1091,7 +1091,10 @@ static int launch_bn(int bn, bool khr, bool cta2, const TcMaps& maps, const TcPa
   return launch_tc<32, MODE, ROW_BYTES, true, false>(maps, p, s);
 }
 
-int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
+// everything a launch needs: tensor maps, parameters and the tile configuration chosen for the layer
+struct TcPlan { TcMaps maps; TcParams p; int bn, row_bytes; bool khr, cta2, split; };
+
+static int tc_prepare(const ofb_conv_desc* d, TcPlan& plan) {
   OFB_CHECK(conv_tc_supported(d), "conv_tc: unsupported shape");
   const bool split = d->in_fmt == OFB_FMT_SPLIT16;
   const int c1 = d->in1 ? d->c1 : 0, cin = d->c0 + c1;
@@ -1193,12 +1196,403 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
     }
   }
   snprintf(t_variant, sizeof(t_variant), "%s", cta2 ? "cta2" : (d->ups2x ? "ups" : (khr ? "khr" : (S > 1 ? "splitk" : "plain"))));
-  if (split) {
-    if (row_bytes == 128) return launch_bn<MODE_F16X3, 128>(bn, khr, cta2, maps, p, s);
-    return launch_bn<MODE_F16X3, 64>(bn, khr, false, maps, p, s);
+  plan.maps = maps; plan.p = p; plan.bn = bn; plan.row_bytes = row_bytes; plan.khr = khr; plan.cta2 = cta2; plan.split = split;
+  return 0;
+}
+
+int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
+  TcPlan pl;
+  if (tc_prepare(d, pl)) return -1;
+  if (pl.split) {
+    if (pl.row_bytes == 128) return launch_bn<MODE_F16X3, 128>(pl.bn, pl.khr, pl.cta2, pl.maps, pl.p, s);
+    return launch_bn<MODE_F16X3, 64>(pl.bn, pl.khr, false, pl.maps, pl.p, s);
   }
-  if (row_bytes == 128) return launch_bn<MODE_TF32, 128>(bn, false, false, maps, p, s);
-  return launch_bn<MODE_TF32, 64>(bn, false, false, maps, p, s);
+  if (pl.row_bytes == 128) return launch_bn<MODE_TF32, 128>(pl.bn, false, false, pl.maps, pl.p, s);
+  return launch_bn<MODE_TF32, 64>(pl.bn, false, false, pl.maps, pl.p, s);
+}
+
+// ------------------------------------------------------------------ image-stationary layer chains
+// A run of consecutive 3x3 stride-1 convs of one encoder stage (layer2: seven 128 -> 128 convs at 16x16) executed
+// by ONE launch of the CTA-pair kernel's pipeline.  A pair-tile of such a layer is exactly one image (two 128-pixel
+// halves) and the layer has a single N tile, so a conv depends only on what the SAME cluster wrote one layer
+// earlier: every cluster walks  for layer: for its images  with the ring, the TMEM double buffer and the role warps
+// running straight through.  Measured per launch of the unchained kernel at 8 panoramas (tools/timeline.py): 16.5 us
+// of K loop in a 25 us period - dependency release, first-operand latency, the un-overlapped epilogue of the last
+// tile, teardown and the launch gap make up the rest.  In the chain the epilogue of image A's layer l drains while
+// the MMAs of image B's layer l run, and A's layer l+1 operands are already in flight when B finishes.
+// Synchronisation: per local image slot one mbarrier (in both CTAs of the pair) that the epilogue warps of BOTH CTAs
+// arrive on once their bulk stores of that image have completed; the producer waits for it before loading the next
+// layer's activations of that image (the 3x3 halo crosses the two halves).  With several N tiles per M pair
+// (layer3: 256 channels = two N tiles, handled by two clusters) the images of a pair are complete only when all
+// those clusters are done: the same hand-off then goes through one global arrival counter per M pair (release /
+// acquire at gpu scope, zeroed before the launch); all clusters of the launch are co-resident (<= one per SM pair)
+// and a layer's tiles depend only on the previous layer, so the waits cannot form a cycle.  Residual reads use
+// ld.global.cg: the buffer is rewritten during the launch, the non-coherent path could return a stale L1 line.
+constexpr int CH_MAX = 12;        // layers per chain
+constexpr int CH_SLOTS = 4;       // images per cluster
+struct TcLayer {
+  CUtensorMap a[2], b[2], o[2];
+  const float* scale; const float* shift; const void* residual;
+  float wscale; int act;
+};
+struct TcChain {
+  int L;
+  int use_flags;             // dependencies cross clusters (several N tiles per M pair): global arrival counters
+  unsigned int* flags;       // [M pair]: CTAs (2 per cluster x N tiles) that have finished their tile of the layers so far
+  TcLayer layer[CH_MAX];
+};
+
+__global__ void __launch_bounds__((TcCfg<128, MODE_F16X3, 128, true, false, false, 0, true>::THREADS), 1)
+conv_chain_kernel(const __grid_constant__ TcChain ch, const TcParams p) {
+  using Cfg = TcCfg<128, MODE_F16X3, 128, true, false, false, 0, true>;
+  constexpr int BN = 128, ROW_BYTES = 128;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  constexpr int RING = Cfg::NST * Cfg::STAGE;
+  const uint32_t stage_out = base + RING;
+  uint8_t* stage_out_ptr = base_ptr + RING;
+  constexpr int AFTER = RING + 2 * Cfg::OUT_BUF;
+  const uint32_t bars = base + AFTER;                            // full[NST], empty[NST], tfull[2], tempty[2], -, dep[CH_SLOTS]
+  const uint32_t bar_tfull = bars + 8 * (2 * Cfg::NST), bar_tempty = bar_tfull + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + AFTER + 8 * (2 * Cfg::NST + 5));
+  const uint32_t bar_dep = bars + 8 * (2 * Cfg::NST + 6);
+  static_assert(8 * (2 * Cfg::NST + 6 + CH_SLOTS) <= 256, "barrier block");
+  float* s_scale = reinterpret_cast<float*>(base_ptr + AFTER + 256);
+  float* s_shift = s_scale + BN;
+
+  const int warp = (int)uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const uint32_t rank = uniform(cluster_ctarank());
+  const int tile0 = (int)(blockIdx.x >> 1), tile_step = (int)(gridDim.x >> 1);
+  const int cchunks = p.c0 / Cfg::KC;
+  const int ksteps = p.taps * cchunks;
+  const int tiles_per_group = p.tiles_x * p.tiles_y;
+  const int L = ch.L;
+  // timing experiments ("tc_debug" & 256): CTA 0 stamps %globaltimer per (layer, slot): 0 dependency released,
+  // 1 first operands landed, 2 last MMA issued, 3 accumulator complete, 4 stores issued, 5 stores complete + arrive
+  const bool tl = (p.dbg & 256) && blockIdx.x == 0;
+  long long* const tlb = p.dbg_buf + 512 * 8;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < Cfg::NST; ++i) {
+      mbar_init(bars + 8 * i, 1);
+      mbar_init(bars + 8 * (Cfg::NST + i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, 2 * Cfg::EPI_WARPS);
+    }
+    for (int i = 0; i < CH_SLOTS; ++i) mbar_init(bar_dep + 8 * i, 2);      // one arrival per CTA of the pair
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&ch.layer[0].a[0]);
+    tma_prefetch_desc(&ch.layer[0].b[0]);
+    tma_prefetch_desc(&ch.layer[0].o[0]);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = uniform(*tmem_slot);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    uint32_t st = 0, ph = 0;
+    const uint32_t tx = (uint32_t)Cfg::PLANES * ((uint32_t)Cfg::A_BYTES + (uint32_t)Cfg::B_BYTES);
+    for (int l = 0; l < L; ++l) {
+      const TcLayer& ly = ch.layer[l];
+      int j = 0;
+      for (int t = tile0; t < p.total_tiles; t += tile_step, ++j) {
+        const int nt = t % p.tiles_n, mp = t / p.tiles_n, n0 = nt * BN;
+        if (l > 0) {
+          // the previous layer's output of these images (both halves, all channels) is complete in global memory
+          if (ch.use_flags) {
+            const unsigned int need = (unsigned int)(l * 2 * p.tiles_n);
+            int spins = 0;
+            while (true) {
+              unsigned int v;
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ch.flags + mp) : "memory");
+              if (v >= need) break;
+              if (++spins > (1 << 22)) __trap();          // a broken chain must fault, not hang the GPU
+            }
+          } else {
+            mbar_wait(bar_dep + 8 * j, (uint32_t)((l - 1) & 1));
+          }
+          asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        if (tl && lane == 0) tlb[(l * CH_SLOTS + j) * 8 + 0] = globaltimer_ns();
+        const int mt = 2 * mp + (int)rank;
+        const int grp = mt / tiles_per_group, trem = mt - grp * tiles_per_group;
+        const int ty = trem / p.tiles_x, tx_ = trem - ty * p.tiles_x;
+        const int img0 = grp * p.BNI, y0 = ty * p.BH, x0 = tx_ * p.BW;
+        int kh = 0, kw = 0;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int cx = x0 + kw - p.padx, cy = y0 + kh - p.pady;
+          const int wk = tap * p.c0;
+          for (int cq = 0; cq < cchunks; ++cq) {
+            const uint32_t full = bars + 8 * st;
+            const uint32_t sa = base + st * Cfg::STAGE;
+            const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
+            mbar_wait(bars + 8 * (Cfg::NST + st), ph ^ 1);
+            if (elect_one()) {
+              if (rank == 0) mbar_expect_tx(full, 2 * tx);
+#pragma unroll
+              for (int pl = 0; pl < Cfg::PLANES; ++pl) {
+                tma_load_4d_2sm(sa + pl * Cfg::A_BYTES, &ly.a[pl], full, cq * Cfg::KC, cx, cy, img0);
+                tma_load_2d_2sm(sb + pl * Cfg::B_BYTES, &ly.b[pl], full, wk + cq * Cfg::KC,
+                                n0 + (BN / 2) * (pl == 0 ? (int)rank : 1 - (int)rank));
+              }
+            }
+            __syncwarp();
+            if (++st == Cfg::NST) { st = 0; ph ^= 1; }
+          }
+          if (++kw == p.kdiv) { kw = 0; ++kh; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA) =====================
+    if (rank == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((256u >> 4) << 24);
+      const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * BN) >> 3) << 17);
+      const uint64_t dconst = umma_desc<ROW_BYTES>(0);
+      uint32_t st = 0, ph = 0, i = 0;
+      for (int l = 0; l < L; ++l) {
+        int j = 0;
+        for (int t = tile0; t < p.total_tiles; t += tile_step, ++i, ++j) {
+          const uint32_t buf = i & 1;
+          mbar_wait(bar_tempty + 8 * buf, ((i >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t acc = tmem + buf * Cfg::ACC_COLS;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            mbar_wait(bars + 8 * st, ph);
+            tc_fence_after();
+            if (tl && lane == 0 && ks == 0) tlb[(l * CH_SLOTS + j) * 8 + 1] = globaltimer_ns();
+            const uint32_t sa = base + st * Cfg::STAGE;
+            const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
+            if (elect_one()) {
+              const uint64_t a_hi = dconst | ((sa >> 4) & 0x3FFF), b_hi = dconst | ((sb >> 4) & 0x3FFF);
+              const uint64_t a_lo = dconst | (((sa + Cfg::A_BYTES) >> 4) & 0x3FFF);
+#pragma unroll
+              for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk) {
+                tc_mma<MODE_F16X3, true>(acc, a_hi + 2 * kk, b_hi + 2 * kk, idesc2, (ks | kk) != 0);   // hi*Whi | hi*Wlo
+                tc_mma<MODE_F16X3, true>(acc, a_lo + 2 * kk, b_hi + 2 * kk, idesc, 1);                 // + lo*Whi
+              }
+              tc_commit_2sm(bars + 8 * (Cfg::NST + st));
+              if (ks == ksteps - 1) tc_commit_2sm(bar_tfull + 8 * buf);
+            }
+            __syncwarp();
+            if (++st == Cfg::NST) { st = 0; ph ^= 1; }
+          }
+          if (tl && lane == 0) tlb[(l * CH_SLOTS + j) * 8 + 2] = globaltimer_ns();
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (8 warps: two per TMEM lane quarter) =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int xx = r % p.BW, yy = (r / p.BW) % p.BH, ni = r / (p.BW * p.BH);
+    const int et = threadIdx.x - 64;
+    const int eset = (warp - 2) >> 2;
+    const int sub_x = (q * 32) % p.BW, sub_y = ((q * 32) / p.BW) % p.BH, sub_n = (q * 32) / (p.BW * p.BH);
+    uint32_t i = 0;
+    for (int l = 0; l < L; ++l) {
+      const TcLayer& ly = ch.layer[l];
+      int last_n0 = -1;
+      int j = 0;
+      for (int t = tile0; t < p.total_tiles; t += tile_step, ++i, ++j) {
+        const int nt = t % p.tiles_n, mp = t / p.tiles_n, n0 = nt * BN;
+        if (n0 != last_n0) {
+          epi_bar<32 * Cfg::EPI_WARPS>();          // nobody still reads the previous scale / shift
+          for (int jj = et; jj < BN; jj += 32 * Cfg::EPI_WARPS) {
+            s_scale[jj] = (ly.scale ? __ldg(&ly.scale[n0 + jj]) : 1.f) * ly.wscale;
+            s_shift[jj] = ly.shift ? __ldg(&ly.shift[n0 + jj]) : 0.f;
+          }
+          epi_bar<32 * Cfg::EPI_WARPS>();
+          last_n0 = n0;
+        }
+        const int mt = 2 * mp + (int)rank;
+        const int grp = mt / tiles_per_group, trem = mt - grp * tiles_per_group;
+        const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
+        const int img0 = grp * p.BNI, y0 = ty * p.BH, x0 = tx * p.BW;
+        const uint32_t buf = i & 1;
+        mbar_wait(bar_tfull + 8 * buf, (i >> 1) & 1);
+        tc_fence_after();
+        if (tl && et == 0) tlb[(l * CH_SLOTS + j) * 8 + 3] = globaltimer_ns();
+        const int img = img0 + ni;
+        const bool ok = img < p.n_img;
+        const size_t pix = ((size_t)(ok ? img : 0) * p.H + (y0 + yy)) * p.W + (x0 + xx);
+        const size_t off = pix * p.cout + n0;
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int cb = 32 * eset + ci * 64;
+          uint32_t v[32], v2[32];
+          tmem_ld32_issue(tmem + ((uint32_t)(q * 32) << 16) + buf * Cfg::ACC_COLS + cb, v);
+          tmem_ld32_issue(tmem + ((uint32_t)(q * 32) << 16) + buf * Cfg::ACC_COLS + (cb < 64 ? 192 : 64) + cb, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) + __uint_as_float(v2[k]));
+          if (ci == 1) {                         // this warp's share of the accumulator is read
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (rank != 0) mbar_arrive_remote(bar_tempty + 8 * buf, 0);
+              else mbar_arrive(bar_tempty + 8 * buf);
+            }
+          }
+          float f[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]) * s_scale[cb + k] + s_shift[cb + k];
+          if (ly.residual && ok) {
+            const __half* rhi = reinterpret_cast<const __half*>(ly.residual) + off + cb;
+            const __half* rlo = rhi + p.plane;
+#pragma unroll
+            for (int k = 0; k < 32; k += 8) {
+              const uint4 a = __ldcg(reinterpret_cast<const uint4*>(rhi + k));
+              const uint4 b = __ldcg(reinterpret_cast<const uint4*>(rlo + k));
+              const __half2* ah = reinterpret_cast<const __half2*>(&a);
+              const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+              for (int tt = 0; tt < 4; ++tt) {
+                const float2 x = __half22float2(ah[tt]), y = __half22float2(bh[tt]);
+                f[k + 2 * tt] += x.x + y.x;
+                f[k + 2 * tt + 1] += x.y + y.y;
+              }
+            }
+          }
+          if (ly.act == OFB_ACT_RELU) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) f[k] = fmaxf(f[k], 0.f);
+          }
+          // stage this warp's 32 pixels x 32 columns (64-byte rows, SWIZZLE_64B) and store them with one bulk tensor
+          // store per plane; one staging buffer per warp set
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+          uint8_t* dst = stage_out_ptr + eset * Cfg::OUT_BUF;
+#pragma unroll
+          for (int k = 0; k < 32; k += 8) {
+            uint4 hi4, lo4;
+            __half2* hh = reinterpret_cast<__half2*>(&hi4);
+            __half2* ll = reinterpret_cast<__half2*>(&lo4);
+#pragma unroll
+            for (int tt = 0; tt < 4; ++tt) {
+              const __half2 h = __floats2half2_rn(f[k + 2 * tt], f[k + 2 * tt + 1]);
+              const float2 hf = __half22float2(h);
+              hh[tt] = h;
+              ll[tt] = __floats2half2_rn(f[k + 2 * tt] - hf.x, f[k + 2 * tt + 1] - hf.y);
+            }
+            const int sw = ((k >> 3) ^ ((r >> 1) & 3)) << 4;
+            *reinterpret_cast<uint4*>(dst + r * 64 + sw) = hi4;
+            *reinterpret_cast<uint4*>(dst + 128 * 64 + r * 64 + sw) = lo4;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t src = stage_out + eset * Cfg::OUT_BUF + (uint32_t)(q * 32 * Cfg::OUT_ROW);
+#pragma unroll
+            for (int pl = 0; pl < Cfg::PLANES; ++pl)
+              tma_store_4d(&ly.o[pl], src + pl * 128 * Cfg::OUT_ROW, n0 + cb, x0 + sub_x, y0 + sub_y, img0 + sub_n);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        // this image's rows of layer l are in global memory once every epilogue warp's bulk stores have completed:
+        // release the next layer's loads of the image in both CTAs of the pair
+        if (tl && et == 0) tlb[(l * CH_SLOTS + j) * 8 + 4] = globaltimer_ns();
+        if (l + 1 < L) {
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          __syncwarp();
+          epi_bar<32 * Cfg::EPI_WARPS>();
+          if (et == 0) {
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __threadfence();
+            if (ch.use_flags) {
+              asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ch.flags + mp) : "memory");
+            } else {
+              mbar_arrive_remote(bar_dep + 8 * j, 0);
+              mbar_arrive_remote(bar_dep + 8 * j, 1);
+            }
+            if (tl) tlb[(l * CH_SLOTS + j) * 8 + 5] = globaltimer_ns();
+          }
+        }
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+// descs: L consecutive single-source 3x3 stride-1 convs over the same (n, h, w) with 128 -> 128 channels, each reading
+// the previous one's output.  Returns 1 (nothing launched) when the chain conditions do not hold for these shapes.
+int conv_tc_chain(const ofb_conv_desc* descs, int L, unsigned int* flags, int flags_capacity, cudaStream_t s) {
+  if (L < 2 || L > CH_MAX || !tc_opts().cta2) return 1;
+  using Cfg = TcCfg<128, MODE_F16X3, 128, true, false, false, 0, true>;
+  TcChain ch;
+  memset(&ch, 0, sizeof(ch));
+  ch.L = L;
+  TcParams p0{};
+  for (int l = 0; l < L; ++l) {
+    const ofb_conv_desc& d = descs[l];
+    if (d.in1 || d.k != 3 || d.stride != 1 || d.ups2x || d.ksplit > 1 || !conv_tc_supported(&d)) return 1;
+    if (l > 0 && (d.in0 != descs[l - 1].out || d.n != descs[0].n || d.h != descs[0].h || d.w != descs[0].w ||
+                  d.c0 != descs[0].c0 || d.cout != descs[0].cout)) return 1;
+    TcPlan pl;
+    if (tc_prepare(&d, pl)) return -1;
+    // CTA pairs whose pair-tile is a whole number of images; several N tiles need the global counters
+    if (!pl.cta2 || !pl.split || pl.bn != 128 || pl.row_bytes != 128 || !tc_opts().store128) return 1;
+    if (pl.p.tiles_n > 1 && (!flags || (pl.p.total_tiles / pl.p.tiles_n) > flags_capacity)) return 1;
+    if ((2 * 128) % (d.h * d.w) != 0 && (d.h * d.w) % (2 * 128) != 0) return 1;
+    if (d.h * d.w > 2 * 128) return 1;                   // an image larger than a pair-tile would need neighbours' rows
+    if (l == 0) p0 = pl.p;
+    TcLayer& ly = ch.layer[l];
+    ly.a[0] = pl.maps.a[0][0]; ly.a[1] = pl.maps.a[0][1];
+    ly.b[0] = pl.maps.b[0]; ly.b[1] = pl.maps.b[1];
+    ly.o[0] = pl.maps.o[0]; ly.o[1] = pl.maps.o[1];
+    ly.scale = d.scale; ly.shift = d.shift; ly.residual = d.residual; ly.wscale = pl.p.wscale; ly.act = d.act;
+    if (d.act != OFB_ACT_RELU && d.act != OFB_ACT_NONE) return 1;
+  }
+  static bool attr[kMaxDevices] = {false};
+  const int dev = cur_device();
+  if (!attr[dev]) {
+    OFB_CUDA(cudaFuncSetAttribute(conv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr[dev] = true;
+  }
+  const int units = (num_sms() / 2) / tc_opts().sm_share;
+  const int clusters = p0.total_tiles < units ? p0.total_tiles : units;
+  if ((p0.total_tiles + clusters - 1) / clusters > CH_SLOTS) return 1;
+  ch.use_flags = p0.tiles_n > 1 ? 1 : 0;
+  ch.flags = flags;
+  if (ch.use_flags) OFB_CUDA(cudaMemsetAsync(flags, 0, (size_t)(p0.total_tiles / p0.tiles_n) * sizeof(unsigned int), s));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * 2); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
+  if (tc_opts().pdl) {
+    attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  attrs[na].id = cudaLaunchAttributeClusterDimension;
+  attrs[na].val.clusterDim.x = 2; attrs[na].val.clusterDim.y = 1; attrs[na].val.clusterDim.z = 1;
+  ++na;
+  cfg.attrs = attrs; cfg.numAttrs = na;
+  OFB_CUDA(cudaLaunchKernelEx(&cfg, conv_chain_kernel, ch, p0));
+  OFB_LAUNCH_CHECK();
+  snprintf(t_variant, sizeof(t_variant), "chain%d", L);
+  return 0;
 }
 
 // ------------------------------------------------------------------ heads on tensor cores

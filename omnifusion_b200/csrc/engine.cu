@@ -35,6 +35,7 @@ bool conv_tc_supported(const ofb_conv_desc* d);
 int conv_tc_heads(const void* x, int n, int h, int w, const void* wgt_split, float wgt_unscale, float b_pred,
                   float b_conf, int confidence, float* pred_out, float* conf_out, int interleaved, cudaStream_t s);
 int attention_tc(const void* qkv, int B, int N, int heads, void* out, cudaStream_t s);
+int conv_tc_chain(const ofb_conv_desc* descs, int L, unsigned int* flags, int flags_capacity, cudaStream_t s);
 int blend_conf_launch(const float* pred_w, const float* conf, bool interleaved, int B, int N, int Ph, int Pw,
                       const int32_t* rowptr, const uint32_t* idx, const float* w, int He, int We, float* out,
                       cudaStream_t s);
@@ -73,6 +74,7 @@ struct Block {
 };
 struct Act { float* p = nullptr; int n = 0, h = 0, w = 0, c = 0, fmt = 0; };
 constexpr int kRangeSlots = 32;
+constexpr int kChainFlags = 1024;
 
 }  // namespace ofb
 
@@ -94,10 +96,13 @@ struct ofb_handle {
   int splitk = 4;                  // K slices of the two 512-wide token linears on the tcgen05 engine (1 = off)
   int heads_tc = 1;                // run the heads on the tensor pipe (split-half format, 128-pixel rows)
   int attn_tc = 1;                 // attention core on the tensor pipe (split-half format; tcgen05 QK^T and PV)
+  int chain = 1;                   // run the same-shape convs of an encoder stage as one image-stationary chain launch
+                                   // (1: stages whose dependencies stay inside a CTA pair; 2: also cross-cluster chains)
   int no_point_feat = 0;           // ablation of network_360d.py:325 - layer1 is used without the point-feature add
   int no_transformer = 0;          // ablation of network_360d.py:330-335 - no token path, layer4 goes straight to the decoder
   int check_range = 0;             // after every forward: max |x| / non-finite count of each registered activation
   unsigned int* range_dev = nullptr;            // [kRangeSlots][2]
+  unsigned int* chain_flags = nullptr;          // arrival counters of the layer chains (conv_tc.cu), kChainFlags entries
   std::vector<std::string> range_names;         // names of the slots filled by the last forward
   float pred_b = 0.f, conf_b = 0.f;
   Mlp mlp[2]{};
@@ -420,6 +425,7 @@ static int ensure_workspace(ofb_handle* h, int imgs, int P, Buffers* b) {
     h->lane[h->cur].ws_floats = need;
     ++h->ws_generation;
   }
+  if (!h->chain_flags) OFB_CUDA(cudaMalloc(&h->chain_flags, 2 * kChainFlags * sizeof(unsigned int)));   // one set per lane
   plan_buffers(h, imgs, P, b);
   return 0;
 }
@@ -453,8 +459,8 @@ static void conv_work(const ofb_conv_desc& d, double* flops, double* bytes) {
   *bytes = 4.0 * ((double)d.n * d.h * d.w * (d.c0 + d.c1) + M * d.cout * (d.residual ? 2 : 1) + (double)d.cout * K);
 }
 
-static int run_conv(Ctx& c, const ConvW& w, const float* in0, int c0, const float* in1, int c1, int hh, int ww,
-                    int stride, int pad, const float* residual, int act, float* out, int ups2x = 0) {
+static ofb_conv_desc conv_desc(Ctx& c, const ConvW& w, const float* in0, int c0, const float* in1, int c1, int hh, int ww,
+                               int stride, int pad, const float* residual, int act, float* out, int ups2x = 0) {
   ofb_conv_desc d{};
   d.ups2x = ups2x;
   d.in0 = in0; d.in1 = in1; d.c0 = c0; d.c1 = c1; d.n = c.imgs; d.h = hh; d.w = ww;
@@ -462,6 +468,12 @@ static int run_conv(Ctx& c, const ConvW& w, const float* in0, int c0, const floa
   d.scale = w.scale; d.shift = w.shift; d.residual = residual; d.act = act; d.out = out;
   d.engine = c.h->engine;
   d.in_fmt = d.out_fmt = c.h->fmt; d.wgt_split = w.ws; d.wgt_unscale = w.unscale;
+  return d;
+}
+
+static int run_conv(Ctx& c, const ConvW& w, const float* in0, int c0, const float* in1, int c1, int hh, int ww,
+                    int stride, int pad, const float* residual, int act, float* out, int ups2x = 0) {
+  ofb_conv_desc d = conv_desc(c, w, in0, c0, in1, c1, hh, ww, stride, pad, residual, act, out, ups2x);
   OFB_CHECK(w.w && w.cin == c0 + c1, "forward: conv weight/channel mismatch (%d vs %d+%d)", w.cin, c0, c1);
   double fl, by;
   conv_work(d, &fl, &by);
@@ -504,6 +516,56 @@ static int run_res_layer(Ctx& c, int l, const float* in, int cin, int hin, float
   int hout = hin / stride;
   const float* x = in;
   int xc = cin, xh = hin;
+  // Image-stationary chain: everything after the first block's strided conv / downsample is a run of same-shape 3x3
+  // convs - [b0.conv2, b1.conv1, b1.conv2, ...] - that one launch walks layer by layer (conv_tc.cu: conv_chain_kernel)
+  // when the stage's geometry keeps every dependency inside a CTA pair (layer2 at 128x128 patches); same buffers,
+  // same arithmetic, bit-identical results.
+  const bool try_chain = c.h->chain && c.h->fmt == OFB_FMT_SPLIT16 && c.h->engine != OFB_ENGINE_SIMT &&
+                         stride == 2 && nb >= 2;
+  if (try_chain) {
+    std::vector<ofb_conv_desc> ds_;
+    const float* cx = in;
+    const float* idn = nullptr;
+    bool ok = true;
+    for (int b = 0; b < nb && ok; ++b) {
+      std::string p = "layer" + std::to_string(l + 1) + "." + std::to_string(b);
+      float* y = (b == nb - 1) ? out_final : ((b & 1) ? pb : pa);
+      if (b == 0) {
+        ok = c.h->conv.count(p + ".ds") != 0;
+        idn = ds;
+      } else {
+        ds_.push_back(conv_desc(c, c.h->conv[p + ".conv1"], cx, ch, nullptr, 0, hout, hout, 1, 1, nullptr, OFB_ACT_RELU, tmp));
+        idn = cx;
+      }
+      ds_.push_back(conv_desc(c, c.h->conv[p + ".conv2"], tmp, ch, nullptr, 0, hout, hout, 1, 1, idn, OFB_ACT_RELU, y));
+      cx = y;
+    }
+    if (ok) {
+      // first block's strided conv1 and downsample as ordinary launches, then the chain
+      std::string p0 = "layer" + std::to_string(l + 1) + ".0";
+      if (run_conv(c, c.h->conv[p0 + ".conv1"], in, cin, nullptr, 0, hin, hin, stride, 1, nullptr, OFB_ACT_RELU, tmp)) return -1;
+      if (run_conv(c, c.h->conv[p0 + ".ds"], in, cin, nullptr, 0, hin, hin, stride, 0, nullptr, OFB_ACT_NONE, ds)) return -1;
+      double fl = 0, by = 0;
+      for (auto& d : ds_) { double f, b_; conv_work(d, &f, &b_); fl += f; by += b_; }
+      int rc;
+      { Prof pr(c.h, c.s, conv_class(ds_[0]) + "_chain" + std::to_string(ds_.size()), fl, by);
+        // chain = 1: only the chains whose dependencies stay inside a cluster; 2: also those that hand images over
+        // between clusters through global arrival counters (layer3; measured: no gain in a graph replay)
+        rc = conv_tc_chain(ds_.data(), (int)ds_.size(), c.h->chain >= 2 ? c.h->chain_flags + (size_t)c.h->cur * kChainFlags : nullptr,
+                           kChainFlags, c.s); }
+      if (rc < 0) return -1;
+      if (rc == 0) return 0;
+      // not chainable for this shape: the launches above are exactly the loop's first two; continue it from conv2
+      if (c.h->profile) { cudaEventDestroy(c.h->recs.back().e0); cudaEventDestroy(c.h->recs.back().e1); c.h->recs.pop_back(); }
+      for (auto& d : ds_) {
+        double f, b_;
+        conv_work(d, &f, &b_);
+        Prof pr(c.h, c.s, conv_class(d), f, b_);
+        if (conv_dispatch(&d, c.s)) return -1;
+      }
+      return 0;
+    }
+  }
   for (int b = 0; b < nb; ++b) {
     std::string p = "layer" + std::to_string(l + 1) + "." + std::to_string(b);
     int st = b == 0 ? stride : 1;
@@ -769,6 +831,7 @@ extern "C" int ofb_destroy(ofb_handle* h) {
   for (int l = 0; l < 2; ++l)
     if (h->lane[l].ws) cudaFree(h->lane[l].ws);
   if (h->range_dev) cudaFree(h->range_dev);
+  if (h->chain_flags) cudaFree(h->chain_flags);
   if (h->aux) cudaStreamDestroy(h->aux);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -816,6 +879,7 @@ extern "C" int ofb_set_option(ofb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "heads_tc")) h->heads_tc = value;
   else if (!strcmp(key, "attn_tc")) h->attn_tc = value;
   else if (!strcmp(key, "check_range")) h->check_range = value;
+  else if (!strcmp(key, "chain")) h->chain = value;
   else if (!strcmp(key, "no_point_feat")) h->no_point_feat = value != 0;
   else if (!strcmp(key, "no_transformer")) h->no_transformer = value != 0;
   else if (!strcmp(key, "splitk")) h->splitk = value == 2 || value == 4 ? value : 1;
@@ -913,6 +977,13 @@ extern "C" int ofb_debug_timeline(long long* host_dst, int max_slots) {
   if (host_dst && n > 0) OFB_CUDA(cudaMemcpy(host_dst, buf, (size_t)n * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
   OFB_CUDA(cudaMemset(buf, 0, ((size_t)slots * 8 + 8) * sizeof(long long)));
   return n;
+}
+
+// timing experiments: the whole stamp buffer (1024 x 8 int64), no reset (tools/chain_timeline.py)
+extern "C" int ofb_debug_timeline_raw(long long* host_dst) {
+  OFB_CUDA(cudaDeviceSynchronize());
+  OFB_CUDA(cudaMemcpy(host_dst, conv_tc_debug_buffer(), (size_t)conv_tc_timeline_slots() * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 extern "C" int ofb_profile_enable(ofb_handle* h, int on) {

@@ -252,6 +252,16 @@ def test_batch_invariance_chunking_dedup_and_graph(fmt):
             d = ((unfused[1] - base[1]).abs() / base[1].abs().clamp_min(1e-6)).max().item()
             print(f"[parity] fused vs materialised upsample: depth max rel diff {d:.3e}")
             assert d <= 2e-6
+        if FORMATS[fmt] == 1:
+            # layer2's seven same-shape convs run as one image-stationary chain launch; separate launches must agree
+            # bit for bit (same tiles, same accumulation order)
+            net.set_option("chain", 0)
+            unchained = net(rgb, iter=2, confidence=True)
+            assert torch.equal(unchained[0], base[0]) and torch.equal(unchained[1], base[1]), "chained vs separate launches"
+            net.set_option("chain", 2)                 # also layer3, whose images are handed over between clusters
+            chained2 = net(rgb, iter=2, confidence=True)
+            net.set_option("chain", 1)
+            assert torch.equal(chained2[0], base[0]) and torch.equal(chained2[1], base[1]), "cross-cluster chains"
         g = net.forward_graphed(rgb, 2, True)
         assert torch.equal(g[1], base[1])
         g2 = net.forward_graphed(rgb.flip(0).contiguous(), 2, True)
