@@ -1229,7 +1229,7 @@ int conv_tc(const ofb_conv_desc* d, cudaStream_t s) {
 // and a layer's tiles depend only on the previous layer, so the waits cannot form a cycle.  Residual reads use
 // ld.global.cg: the buffer is rewritten during the launch, the non-coherent path could return a stale L1 line.
 constexpr int CH_MAX = 12;        // layers per chain
-constexpr int CH_SLOTS = 4;       // images per cluster
+constexpr int CH_SLOTS = 8;       // pair-tiles per cluster
 struct TcLayer {
   CUtensorMap a[2], b[2], o[2];
   const float* scale; const float* shift; const void* residual;
@@ -1272,7 +1272,7 @@ conv_chain_kernel(const __grid_constant__ TcChain ch, const TcParams p) {
   // timing experiments ("tc_debug" & 256): CTA 0 stamps %globaltimer per (layer, slot): 0 dependency released,
   // 1 first operands landed, 2 last MMA issued, 3 accumulator complete, 4 stores issued, 5 stores complete + arrive
   const bool tl = (p.dbg & 256) && blockIdx.x == 0;
-  long long* const tlb = p.dbg_buf + 512 * 8;
+  long long* const tlb = p.dbg_buf + 512 * 8;      // rows [512, 512 + CH_MAX * CH_SLOTS) of the stamp buffer
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < Cfg::NST; ++i) {
@@ -1572,7 +1572,9 @@ int conv_tc_chain(const ofb_conv_desc* descs, int L, unsigned int* flags, int fl
   }
   const int units = (num_sms() / 2) / tc_opts().sm_share;
   const int clusters = p0.total_tiles < units ? p0.total_tiles : units;
-  if ((p0.total_tiles + clusters - 1) / clusters > CH_SLOTS) return 1;
+  // more than 4 pair-tiles per cluster: the launch already amortises its overhead (measured at 32 panoramas per step,
+  // 8 per cluster: 2104-2125 chained vs 2127-2131 panoramas/s unchained), separate launches are used
+  if ((p0.total_tiles + clusters - 1) / clusters > 4) return 1;
   ch.use_flags = p0.tiles_n > 1 ? 1 : 0;
   ch.flags = flags;
   if (ch.use_flags) OFB_CUDA(cudaMemsetAsync(flags, 0, (size_t)(p0.total_tiles / p0.tiles_n) * sizeof(unsigned int), s));

@@ -268,6 +268,22 @@ def test_batch_invariance_chunking_dedup_and_graph(fmt):
         assert torch.equal(g2[1], base[1].flip(0))
 
 
+def test_layer_chains_are_bit_identical_at_every_slot_count():
+    """The image-stationary chain gives a cluster 1 .. 8 pair-tiles depending on the batch (8 panoramas = 2, 32 = 8);
+    beyond that the engine falls back to separate launches.  Every case must equal the unchained forward bit for bit."""
+    net = model("iterative", 4)
+    for bs in (1, 8, 20, 32, 40):
+        rgb = urand(bs, 3, 32, 64, seed=100 + bs).to(DEV)
+        with torch.no_grad():
+            net.set_option("chain", 0)
+            want = [t.clone() for t in net(rgb, iter=2, confidence=True)]
+            for level in (1, 2):
+                net.set_option("chain", level)
+                got = net(rgb, iter=2, confidence=True)
+                assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1]), (bs, level)
+    net.set_option("chain", 1)
+
+
 def test_module_prefix_checkpoint_and_errors():
     from omnifusion_b200 import _lib
     from omnifusion_b200.model.spherical_model_iterative import spherical_fusion

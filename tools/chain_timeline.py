@@ -27,9 +27,9 @@ with torch.no_grad():
     torch.cuda.synchronize()
     buf = (C.c_longlong * (1024 * 8))()
     L.ofb_debug_timeline_raw(buf)
-rows = [[buf[(512 + i) * 8 + k] for k in range(6)] for i in range(48)]
+rows = [[buf[(512 + i) * 8 + k] for k in range(6)] for i in range(96)]
 rows = [(i, r) for i, r in enumerate(rows) if any(r)]
 t0 = min(v for _, r in rows for v in r if v)
 print("layer slot | dep_released first_ops last_mma_issued acc_complete stores_issued stores_complete (us from the first stamp)")
 for i, r in rows:
-    print(f"{i // 4:5d} {i % 4:4d} | " + " ".join(f"{(v - t0) / 1e3:9.2f}" if v else "        -" for v in r))
+    print(f"{i // 8:5d} {i % 8:4d} | " + " ".join(f"{(v - t0) / 1e3:9.2f}" if v else "        -" for v in r))
