@@ -482,8 +482,9 @@ def main():
                 traffic = (k["dram_read_mb_per_launch"] + k["dram_write_mb_per_launch"]) * 1e6
                 traffic_src = t["source"]
         roofline = {"bound": "tensor",
-                    "kernel": "conv_tc_kernel<BN=128, F16X3, 128B rows, TMA store, cta_group::2> (tcgen05 implicit-GEMM conv: all launches "
-                              "with cout >= 128; at small batch the 4x4-pixel layers among them run the 64-wide instantiation)",
+                    "kernel": "conv_tc_kernel<BN=128, F16X3, 128B rows, TMA store, cta_group::2> and conv_chain_kernel (the same CTA-pair "
+                              "pipeline walking layer2's seven convs in one launch) - tcgen05 implicit-GEMM conv: all launches with "
+                              "cout >= 128; at small batch the 4x4-pixel layers among them run the 64-wide instantiation",
                     "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"],
                     "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu)", "traffic_source": traffic_src,
                     "peak_source": pk["source"] + ", dense bf16 sustained",
