@@ -74,6 +74,16 @@ int ofb_pers2equi_f32(const float* pers, int B, int C, int N, int Ph, int Pw, in
                       const int32_t* rowptr, const uint32_t* idx, const float* w,
                       int He, int We, float* out, void* stream);
 
+/* Backward of the two resamplers (the training direction of SURVEY section 8f-4: losses back-propagate through
+ * equi2pers and pers2equi, e.g. train_erp_depth_iterative.py).  Both are linear in their image argument with
+ * input-independent taps, so the backward is the transposed gather: a scatter-add (atomicAdd) of the incoming gradient
+ * with the forward's weights.  The destination must be zeroed by the caller; reference layouts:
+ * grad_pers (B,C,Ph,Pw,N), grad_erp (B,C,He,We). */
+int ofb_equi2pers_backward_f32(const float* grad_pers, int B, int C, int He, int We, const float* grid, int N, int Ph,
+                               int Pw, float* grad_erp, void* stream);
+int ofb_pers2equi_backward_f32(const float* grad_erp, int B, int C, int N, int Ph, int Pw, const int32_t* rowptr,
+                               const uint32_t* idx, const float* w, int He, int We, float* grad_pers, void* stream);
+
 /* Confidence merge: model/spherical_model_iterative.py:372-378.
  * pred_w (B*N,Ph,Pw) = relu(pred)*sigmoid(weight), conf (B*N,Ph,Pw) = sigmoid(weight);
  * out (B,1,He,We) = blend(pred_w) / (blend(conf) + 1e-8*[blend(conf) <= 1e-8]). */

@@ -49,6 +49,8 @@ _SIGNATURES = {
     "ofb_equi2pers_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _I, _P]),
     "ofb_equi2pers_taps": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "ofb_pers2equi_f32": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P]),
+    "ofb_equi2pers_backward_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P]),
+    "ofb_pers2equi_backward_f32": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P]),
     "ofb_blend_conf_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P]),
     "ofb_blend_conf_pairs_f32": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P]),
     "ofb_heads_tc_pairs_f16": (_I, [_P, _I, _I, _I, _P, C.c_float, C.c_float, C.c_float, _P, _P]),
@@ -133,12 +135,12 @@ def stream_of(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def require_cuda(t, name, dtype=torch.float32):
+def require_cuda(t, name, dtype=torch.float32, allow_grad=False):
     if not t.is_cuda:
         raise OfbError(f"{name} must be a CUDA tensor: omnifusion_b200 has no CPU path (got {t.device})")
     if t.dtype != dtype:
         raise OfbError(f"{name} must be {dtype} (got {t.dtype})")
-    if torch.is_grad_enabled() and t.requires_grad:
+    if torch.is_grad_enabled() and t.requires_grad and not allow_grad:
         raise OfbError(f"{name} requires grad: omnifusion_b200 implements inference only; use torch.no_grad()")
     return t.contiguous()
 

@@ -285,6 +285,61 @@ __global__ void deinterleave_kernel(const float2* __restrict__ src, size_t n, in
   dst[i] = comp ? v.y : v.x;
 }
 
+// ------------------------------------------------------------------ backward of the two resamplers
+// Training direction (supervision back-propagates through both resamplers).  Both forwards are
+// linear in their image argument with input-independent taps and weights, so the backward is the transposed
+// gather: a scatter-add of the incoming gradient with the same weights (atomicAdd; the summation order, and with
+// it the last bits, is not deterministic - as in ATen's grid_sampler backward).
+// equi2pers: grad_erp[b,c,y_t,x_t] += w_t * grad_pers[b,c,i,j,n] over the 4 bilinear taps (REF layout).
+__global__ void e2p_backward_kernel(const float* __restrict__ gpers, const float2* __restrict__ grid,
+                                    float* __restrict__ gerp, int B, int C, int He, int We, int N, int Ph, int Pw) {
+  const int total = N * Ph * Pw;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= total) return;
+  const int n = s % N, ij = s / N;
+  const float2 g = __ldg(&grid[(size_t)n * Ph * Pw + ij]);
+  const E2PTaps t = e2p_taps(g.x, g.y, He, We);
+  const bool xin = t.x0 + 1 < We, yin = t.y0 + 1 < He;
+  const float ex = 1.f - t.wx, ey = 1.f - t.wy;
+  const float w00 = ex * ey, w01 = t.wx * ey, w10 = ex * t.wy, w11 = t.wx * t.wy;
+  const size_t plane = (size_t)He * We;
+  for (int bc = 0; bc < B * C; ++bc) {
+    const float gv = __ldg(&gpers[(size_t)bc * total + s]);
+    float* r0 = gerp + (size_t)bc * plane + (size_t)t.y0 * We + t.x0;
+    atomicAdd(r0, gv * w00);
+    if (xin) atomicAdd(r0 + 1, gv * w01);
+    if (yin) atomicAdd(r0 + We, gv * w10);
+    if (xin && yin) atomicAdd(r0 + We + 1, gv * w11);
+  }
+}
+
+// pers2equi: grad_pers[b,c,tap,n] += w_e[tap] * grad_erp[b,c,pix] over the CSR entries of the pixel.
+__global__ void __launch_bounds__(BL_TILE)
+p2e_backward_kernel(const float* __restrict__ gerp, const int32_t* __restrict__ rowptr, const uint32_t* __restrict__ idx,
+                    const float4* __restrict__ w, float* __restrict__ gpers, int npix, int B, int C, P2EStrides st) {
+  __shared__ BlendStage sm;
+  int e0, beg, end;
+  if (!blend_stage(sm, rowptr, idx, w, npix, e0, beg, end)) return;
+  const int pix = blockIdx.x * BL_TILE + threadIdx.x;
+  const int planes = B * C;
+  for (int q = 0; q < planes; ++q) {
+    const float gv = __ldg(&gerp[(size_t)q * npix + pix]);
+    float* base = gpers + (q / C) * st.sb + (q % C) * st.sc;
+    for (int e = beg; e < end; ++e) {
+      int n, y0, x0, dy, dx;
+      const bool staged = e < BL_CAP;
+      p2e_decode(staged ? sm.idx[e] : __ldg(&idx[e0 + e]), n, y0, x0, dy, dx);
+      const float4 ww = staged ? sm.w[e] : __ldg(&w[e0 + e]);
+      float* p = base + y0 * st.sy + x0 * st.sx + n * st.sn;
+      const long long oy = dy * st.sy, ox = dx * st.sx;
+      atomicAdd(p, gv * ww.x);
+      atomicAdd(p + oy, gv * ww.y);
+      atomicAdd(p + ox, gv * ww.z);
+      atomicAdd(p + oy + ox, gv * ww.w);
+    }
+  }
+}
+
 // ------------------------------------------------------------------- abs-rel
 __global__ void absrel_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
                               const uint8_t* __restrict__ mask, size_t n, float scale,
@@ -519,6 +574,31 @@ extern "C" int ofb_absrel_partial(const float* pred, const float* gt, const uint
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   absrel_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pred, gt, mask, n, scale, out);
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ofb_equi2pers_backward_f32(const float* grad_pers, int B, int C, int He, int We, const float* grid, int N,
+                                          int Ph, int Pw, float* grad_erp, void* stream) {
+  OFB_CHECK(grad_pers && grid && grad_erp, "equi2pers_backward: null pointer");
+  OFB_CHECK(B > 0 && C > 0 && He > 1 && We > 1 && N > 0 && Ph > 0 && Pw > 0, "equi2pers_backward: bad shape");
+  const int total = N * Ph * Pw;
+  e2p_backward_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(grad_pers, reinterpret_cast<const float2*>(grid),
+                                                                       grad_erp, B, C, He, We, N, Ph, Pw);
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ofb_pers2equi_backward_f32(const float* grad_erp, int B, int C, int N, int Ph, int Pw, const int32_t* rowptr,
+                                          const uint32_t* idx, const float* w, int He, int We, float* grad_pers,
+                                          void* stream) {
+  OFB_CHECK(grad_erp && rowptr && idx && w && grad_pers, "pers2equi_backward: null pointer");
+  OFB_CHECK(B > 0 && C > 0 && N > 0 && N <= 256 && Ph <= 256 && Pw <= 256, "pers2equi_backward: bad shape");
+  P2EStrides st;           // reference layout (B,C,Ph,Pw,N)
+  st.sn = 1; st.sx = N; st.sy = (long long)Pw * N; st.sc = (long long)Ph * Pw * N; st.sb = st.sc * C;
+  const int npix = He * We;
+  p2e_backward_kernel<<<cdiv(npix, BL_TILE), BL_TILE, 0, (cudaStream_t)stream>>>(
+      grad_erp, rowptr, idx, reinterpret_cast<const float4*>(w), grad_pers, npix, B, C, st);
   OFB_LAUNCH_CHECK();
   return 0;
 }

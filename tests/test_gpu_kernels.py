@@ -410,3 +410,31 @@ def test_blend_conf_pair_map_matches_separate_maps_and_oracle(nrows, erp, P, B):
     rows = (tab["rowptr"][1:] - tab["rowptr"][:-1]).reshape(-1)
     print(f"[parity] blend table nrows={nrows} erp={erp}: max entries per 256-pixel tile = "
           f"{int(rows.cpu().reshape(-1, 256).sum(1).max()) if rows.numel() % 256 == 0 else -1}")
+
+
+@pytest.mark.parametrize("nrows,erp,P", [(4, (64, 128), 16), (6, (128, 256), 32), (3, (32, 64), 16)])
+def test_resampler_backward_matches_autograd_of_the_oracle(nrows, erp, P):
+    """Training direction: gradients of equi2pers w.r.t. the ERP image and of pers2equi w.r.t. the patches
+    against torch autograd through the CPU restatement (F.grid_sample / gather + weighted sum, as the reference).
+    Scatter-adds are atomic (order not deterministic): tolerance 1e-5 relative to the gradient's magnitude."""
+    from omnifusion_b200.equi_pers.equi2pers_v3 import equi2pers
+    from omnifusion_b200.equi_pers.pers2equi_v3 import pers2equi
+    n = tables.NUM_PATCHES[nrows]
+    img = urand(2, 3, *erp, seed=31).requires_grad_(True)
+    go = rand(2, 3, P, P, n, seed=32)
+    ref_p = oe.equi2pers(img, FOV, nrows, (P, P))[0]
+    ref_p.backward(go)
+    img_d = img.detach().to(DEV).requires_grad_(True)
+    got_p = equi2pers(img_d, FOV, nrows, (P, P))[0]
+    got_p.backward(go.to(DEV))
+    err = (img_d.grad.cpu() - img.grad).abs().max().item() / img.grad.abs().max().item()
+    print(f"[parity] equi2pers backward nrows={nrows}: max err / max |grad| = {err:.2e}")
+    assert err <= 1e-5
+    pers = urand(2, 2, P, P, n, seed=33).requires_grad_(True)
+    ge = rand(2, 2, *erp, seed=34)
+    oe.pers2equi(pers, FOV, nrows, (P, P), erp).backward(ge)
+    pers_d = pers.detach().to(DEV).requires_grad_(True)
+    pers2equi(pers_d, FOV, nrows, (P, P), erp, "x").backward(ge.to(DEV))
+    err = (pers_d.grad.cpu() - pers.grad).abs().max().item() / pers.grad.abs().max().item()
+    print(f"[parity] pers2equi backward nrows={nrows}: max err / max |grad| = {err:.2e}")
+    assert err <= 1e-5
