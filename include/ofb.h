@@ -304,7 +304,8 @@ long long ofb_workspace_generation(ofb_handle* h);
  * activation storage (OFB_FMT_*), "fuse_ups" fold the last decoder upsample into de_conv4_0 (default 1),
  * "check_range" see ofb_range_report, "chain" image-stationary layer chains: 0 off, 1 (default) for the encoder stages whose
  * dependencies stay inside a CTA pair (layer2), 2 also stages that hand images over between clusters (layer3), "heads_tc" heads on the tensor pipe (default 1), "attn_tc" attention core on the tensor pipe (default 1), "lanes" 2 = two concurrent half-batches on two streams
- * (default 1), "cta2" / "pdl" / "store128" / "fill_div" / "direct32" / "khr_bw" / "khr_row64" tcgen05 launch variants (per handle);
+ * (default 1), "cta2" / "pdl" / "store128" / "fill_div" / "direct32" / "khr_bw" / "khr_row64" / "nstack" (tap-stacked MMAs of the
+ * rolling-row kernels: 1 = heads (default), 2 = also the fused-upsample conv) tcgen05 launch variants (per handle);
  * "tc_debug" / "dbg_blocks" switch parts of the pipeline OFF for timing experiments (results are wrong). */
 int ofb_set_option(ofb_handle* h, const char* key, int value);
 
@@ -342,6 +343,7 @@ int64_t ofb_launch_count(int reset);
  * was set (512 tiles x 8 int64) to host_dst (tools/probe_tail.py). */
 int ofb_debug_stamps(long long* host_dst);
 int ofb_debug_set(int tc_debug);      /* "tc_debug" for convs launched directly through ofb_conv_f32 */
+int ofb_debug_nstack(int on);         /* "nstack" for rolling-row kernels launched directly (tools/probe_rolling.py) */
 /* Timing experiments: with "tc_debug" & 256 CTA 0 of every tcgen05 conv launch records eight %globaltimer stamps
  * (kernel entry, prologue done, producer past its dependency wait, first operands landed, last MMA issued, first
  * accumulator complete, last store issued, kernel end).  Copies up to max_slots x 8 int64 of the launches since the

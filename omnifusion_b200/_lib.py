@@ -90,6 +90,7 @@ _SIGNATURES = {
     "ofb_last_conv_variant": (C.c_char_p, []),
     "ofb_debug_stamps": (_I, [_P]),
     "ofb_debug_set": (_I, [_I]),
+    "ofb_debug_nstack": (_I, [_I]),
     "ofb_debug_timeline": (_I, [_P, _I]),
     "ofb_debug_timeline_raw": (_I, [_P]),
     "ofb_range_report": (_I, [_P, C.c_char_p, _I]),

@@ -51,6 +51,8 @@ struct TcOptions {
   bool cta2 = true;       // cta_group::2 CTA pairs for the 128-wide split-half tiles
   bool direct32 = false;  // BN = 32 split-half tiles store straight from registers
   bool khr_row64 = false; // 64-byte K rows for the Cout = 64 kh-reuse layers
+  bool nstack = true;     // heads kernel: input-row-stationary MMAs with the three kh taps stacked along N
+  bool nstack_ups = false;// the same for the fused-upsample conv (measured slower: experiments only)
   int fill_div = 2;       // shrink the N tile while fewer than num_sms / fill_div tiles exist
   int khr_bw = 16;        // tile width of the kh-reuse kernels (16 or 32)
   int sm_share = 1;       // persistent grids use num_sms / sm_share CTAs

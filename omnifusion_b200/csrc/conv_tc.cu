@@ -55,6 +55,7 @@ struct TcParams {
                          // 3 first operands landed, 4 last MMA issued, 5 first accumulator complete, 6 last store issued,
                          // 7 kernel end
   int group64;           // accumulate the three split-half products in the cta_group::2 column grouping (see the MMA warp)
+  int nstack;            // UPS kernels: input-row-stationary MMAs with the three kh taps stacked along N (see the MMA warp)
 };
 
 // ------------------------------------------------------------------ PTX wrappers (mbarrier: ptx.cuh)
@@ -163,6 +164,21 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// zero-fill of 32 / 16 accumulator columns of this warp's 32 TMEM lanes
+__device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+      ::"r"(taddr), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+      ::"r"(taddr), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
 // LBO (unused for swizzled K-major) = 1, SBO = bytes between 8-row groups >> 4, version = 1
@@ -228,7 +244,8 @@ struct TcCfg {
   static constexpr int RES = BRES ? 3 * PLANES * B_BYTES : 0;               // resident weights (all 3 kw)
   static constexpr int OUT_ROW = 32 * ES;                                  // bytes per staged row (32 columns)
   static constexpr int OUT_BUF = TMA_STORE ? PLANES * 128 * OUT_ROW : 0;   // one staging buffer
-  static constexpr int MISC = 1024 /*align*/ + 256 /*barriers*/ + BN * 8;
+  static constexpr int BAR_BYTES = UPS ? 512 : 256;                        // mbarriers (+ the TMEM address slot)
+  static constexpr int MISC = 1024 /*align*/ + BAR_BYTES + BN * 8;
   static constexpr int UPS_WARPS = UPS == 1 ? 8 : 0;                       // interpolating producer warps
   // epilogue warps: two per TMEM lane quarter for tiles of >= 2 column chunks (each takes every other 32-column
   // chunk: the accumulator of a single-wave launch drains in half the time), one per quarter otherwise
@@ -248,7 +265,9 @@ struct TcCfg {
   // K-slice instead of three times, and 2 instead of 3 MMAs are issued.
   static constexpr bool STACK = MODE == MODE_F16X3;
   static constexpr int ACC_COLS = STACK ? 2 * BN : BN;                     // accumulator columns per buffer
-  static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;  // two accumulator buffers
+  // two accumulator buffers; UPS (tap-stacked scheme): six output-row blocks in each of two regions (hi*Whi + lo*Whi |
+  // hi*Wlo) = 12 * BN columns, rounded up to a power of two
+  static constexpr int TMEM_COLS = UPS ? (12 * BN <= 256 ? 256 : 512) : (2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS);
   static constexpr int SMEM = NST * STAGE + 2 * OUT_BUF + RES + LR_BYTES + MISC;
   static_assert(NST >= 2 && NST <= NST_RAW, "pipeline needs at least two stages that fit in shared memory");
   static_assert(!UPS || (KHR && BRES && MODE == MODE_F16X3 && ROW_BYTES == 64 && NST == 8), "UPS is a variant of the resident-filter kh-reuse kernel");
@@ -292,8 +311,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   const uint32_t bars = base + AFTER;                            // full[NST], empty[NST], tfull[2], tempty[2], res
   const uint32_t bar_tfull = bars + 8 * (2 * Cfg::NST), bar_tempty = bar_tfull + 16, bar_res = bar_tempty + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + AFTER + 8 * (2 * Cfg::NST + 5));
-  float* s_scale = reinterpret_cast<float*>(base_ptr + AFTER + 256);
+  float* s_scale = reinterpret_cast<float*>(base_ptr + AFTER + Cfg::BAR_BYTES);
   float* s_shift = s_scale + BN;
+  // UPS, tap-stacked scheme: per output-row block one "complete" and one "drained + zeroed" barrier, and one for the
+  // initial zero fill of the accumulator
+  const uint32_t bar_bfull = bars + 8 * (2 * Cfg::NST + 8), bar_bempty = bar_bfull + 48, bar_zero = bar_bempty + 48;
 
   const int warp = (int)uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;
   // CTA2: cluster c = blockIdx.x / 2 walks pair-tiles; CTA rank r takes M tile 2*mp + r of pair-tile (mp, nt)
@@ -323,6 +345,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       mbar_init(bar_tempty + 8 * i, (CTA2 ? 2 : 1) * Cfg::EPI_WARPS);   // one arrival per epilogue warp (of both CTAs of a pair)
     }
     mbar_init(bar_res, 1);
+    if (UPS) {
+      for (int i = 0; i < 6; ++i) {
+        mbar_init(bar_bfull + 8 * i, 1);
+        mbar_init(bar_bempty + 8 * i, Cfg::EPI_WARPS);
+      }
+      mbar_init(bar_zero, Cfg::EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (UPS != 1) tma_prefetch_desc(&maps.a[0][0]);
     tma_prefetch_desc(&maps.b[0]);
@@ -365,8 +394,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     if (BRES) {      // the whole filter (3 kw x all kh x cin x cout, both planes) once per CTA
       if (elect_one()) {
         mbar_expect_tx(bar_res, Cfg::RES);
-        for (int kw = 0; kw < 3; ++kw)
-          tma_load_4d(res_b + kw * Cfg::PLANES * Cfg::B_BYTES, &maps.b[0], bar_res, 0, 0, 0, kw);
+        for (int kw = 0; kw < 3; ++kw) {
+          if (UPS && p.nstack) {
+            // per kw: [Whi: kh0, kh1, kh2 rows][Wlo: kh0, kh1, kh2 rows] - the kh slices of one plane are contiguous
+            tma_load_4d(res_b + kw * Cfg::PLANES * Cfg::B_BYTES, &maps.b[0], bar_res, 0, 0, 0, kw);
+            tma_load_4d(res_b + kw * Cfg::PLANES * Cfg::B_BYTES + Cfg::B_BYTES, &maps.b[1], bar_res, 0, 0, 0, kw);
+          } else {
+            tma_load_4d(res_b + kw * Cfg::PLANES * Cfg::B_BYTES, &maps.b[0], bar_res, 0, 0, 0, kw);
+          }
+        }
       }
       __syncwarp();
     }
@@ -467,7 +503,88 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       const uint64_t dconst = umma_desc<ROW_BYTES>(0);            // descriptor without the start address
       uint32_t st = 0, ph = 0, i = 0;
       if (BRES) mbar_wait(bar_res, 0);
-      if (UPS) {
+      if (UPS && p.nstack) {
+        // Tap-stacked, input-row-stationary scheme.  An input ring row Y feeds three output rows (y = Y + 1 - kh);
+        // instead of one MMA per (output row, kh) with N = cout, ONE MMA per input row multiplies the row (shifted by
+        // kw) with the kh slices stacked along N - [W(kh0); W(kh1); W(kh2)], N = 3 * cout - and its three column
+        // blocks land in the accumulator blocks of the three output rows.  Output row j (running index) owns block
+        // j % 6 of two 6-block regions (P: hi*Whi + lo*Whi, Q: hi*Wlo) at column BN * (5 - j % 6): descending, so
+        // ascending kh = ascending columns; where the three blocks wrap around the ring the MMA is split in two.
+        // Blocks are zero-filled by the epilogue when it drains them, every MMA accumulates.  18 MMAs of N = 3*cout
+        // per input row instead of 36 of N = cout / 2*cout: the fixed ~38-clock A read of an MMA (tools/mma_probe.cu)
+        // is paid half as often.
+        constexpr int C = BN;
+        const uint32_t idesc_n[4] = {0u, (idesc & ~(0x3Fu << 17)) | ((uint32_t)(C >> 3) << 17),
+                                     (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * C) >> 3) << 17),
+                                     (idesc & ~(0x3Fu << 17)) | ((uint32_t)((3 * C) >> 3) << 17)};
+        mbar_wait(bar_zero, 0);
+        tc_fence_after();
+        uint32_t pc = 0;                 // produced-row counter: ring slot = pc % NST
+        int g = ups_r0;
+        int opened = 0;                  // output rows (running index) whose block has been claimed
+        while (g < ups_r1) {
+          const int img = g / p.H, ys = g - img * p.H;
+          const int ye = min(p.H, ys + (ups_r1 - g));
+          const int obase = g - ups_r0;  // running index of output row ys
+          (void)img;
+          for (int Y = ys - 1; Y <= ye; ++Y, ++pc) {
+            const uint32_t slot = pc % Cfg::NST;
+            const bool mst = (p.dbg & 2048) && blockIdx.x == 0 && lane == 0 && pc < 512;   // timing experiments
+            if (mst) p.dbg_buf[pc * 8 + 0] = clock64();
+            mbar_wait(bars + 8 * slot, (pc / Cfg::NST) & 1);
+            tc_fence_after();
+            if (mst) p.dbg_buf[pc * 8 + 1] = clock64();
+            const bool valid = Y >= 0 && Y < p.H;
+            // kh range whose output row y = Y + 1 - kh lies in [ys, ye)
+            const int kh_lo = max(0, Y + 2 - ye), kh_hi = min(2, Y + 1 - ys);
+            if (valid && kh_lo <= kh_hi) {
+              const int j_top = obase + (Y + 1 - kh_lo - ys);            // highest output row touched
+              while (opened <= j_top) {                                   // claim its block: drained and zeroed?
+                mbar_wait(bar_bempty + 8 * (opened % 6), ((opened / 6) & 1) ^ 1);
+                ++opened;
+              }
+              tc_fence_after();
+              if (mst) p.dbg_buf[pc * 8 + 2] = clock64();
+              if (elect_one()) {
+                // maximal runs of kh whose blocks are adjacent: column index 5 - j % 6 grows with kh until j % 6 == 0
+                int ka = kh_lo;
+                while (ka <= kh_hi) {
+                  const int ja = obase + (Y + 1 - ka - ys);
+                  int kb = ka;
+                  while (kb < kh_hi && ((ja - (kb - ka)) % 6) != 0) ++kb;
+                  const int n = kb - ka + 1;
+                  const uint32_t dcol = (uint32_t)(C * (5 - ja % 6));
+                  const uint32_t accP = tmem + dcol, accQ = tmem + 6 * C + dcol;
+#pragma unroll
+                  for (int kw = 0; kw < 3; ++kw) {
+                    const uint32_t row = slot * Cfg::UPS_PITCH + kw;
+                    const uint32_t a0 = base + row * ROW_BYTES;
+                    const uint32_t b0 = res_b + (uint32_t)(kw * Cfg::PLANES * Cfg::B_BYTES + ka * C * ROW_BYTES);
+                    const uint64_t a_hi = dconst | ((a0 >> 4) & 0x3FFF), a_lo = dconst | (((a0 + Cfg::NST * Cfg::UPS_PLANE) >> 4) & 0x3FFF);
+                    const uint64_t b_hi = dconst | ((b0 >> 4) & 0x3FFF), b_lo = dconst | (((b0 + Cfg::B_BYTES) >> 4) & 0x3FFF);
+#pragma unroll
+                    for (int kk = 0; kk < Cfg::MMA_PER_TILE; ++kk) {
+                      tc_mma<MODE>(accP, a_hi + 2 * kk, b_hi + 2 * kk, idesc_n[n], 1);   // hi*Whi
+                      tc_mma<MODE>(accP, a_lo + 2 * kk, b_hi + 2 * kk, idesc_n[n], 1);   // + lo*Whi
+                      tc_mma<MODE>(accQ, a_hi + 2 * kk, b_lo + 2 * kk, idesc_n[n], 1);   // hi*Wlo
+                    }
+                  }
+                  ka = kb + 1;
+                }
+              }
+              __syncwarp();
+            }
+            if (elect_one()) {
+              tc_commit(bars + 8 * (Cfg::NST + slot));                   // this ring row is consumed
+              // output row Y - 1 has received its last contribution (kh = 2 of row Y, or Y is past the image)
+              if (Y - 1 >= ys && Y - 1 < ye) tc_commit(bar_bfull + 8 * ((obase + (Y - 1 - ys)) % 6));
+            }
+            __syncwarp();
+            if (mst) p.dbg_buf[pc * 8 + 3] = clock64();
+          }
+          g += ye - ys;
+        }
+      } else if (UPS) {
         // produced-row counter of the top halo row of the current output row; ring slot = counter % NST
         uint32_t pb = 0;
         for (int g = ups_r0; g < ups_r1; ++g, ++i) {
@@ -588,12 +705,30 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     const int sub_x = (q * 32) % p.BW, sub_y = ((q * 32) / p.BW) % p.BH, sub_n = (q * 32) / (p.BW * p.BH);
     int last_n0 = -1;
     uint32_t i = 0, chunk_ctr = 0;
+    const bool nstack = UPS && p.nstack;
+    if (nstack) {                               // all twelve accumulator blocks start at zero (every MMA accumulates)
+      for (int c0 = 0; c0 < 12 * BN; c0 += 32) tmem_zero32(tmem + ((uint32_t)(q * 32) << 16) + c0);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_zero);
+    }
+    // rolling-row kernels: tile = one image row; (image, row) advance incrementally - the general decomposition
+    // below costs five integer divisions per tile, which is most of a row's epilogue time there
+    int ups_img = UPS ? ups_r0 / p.H : 0, ups_y = UPS ? ups_r0 - ups_img * p.H : 0;
     for (int t = UPS ? ups_r0 : tile0; t < (UPS ? ups_r1 : p.total_tiles); t += UPS ? 1 : tile_step, ++i) {
-      const int sp = t % p.ksplit, tq = t / p.ksplit;
-      const int nt = tq % p.tiles_n, mt = CTA2 ? 2 * (tq / p.tiles_n) + (int)rank : tq / p.tiles_n;
-      const int grp = mt / tiles_per_group, trem = mt - grp * tiles_per_group;
-      const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
-      const int img0 = grp * p.BNI, y0 = ty * p.BH, x0 = tx * p.BW, n0 = nt * BN;
+      int sp = 0, img0, y0, x0 = 0, n0 = 0;
+      if (UPS) {
+        img0 = ups_img; y0 = ups_y;
+        if (++ups_y == p.H) { ups_y = 0; ++ups_img; }
+      } else {
+        sp = t % p.ksplit;
+        const int tq = t / p.ksplit;
+        const int nt = tq % p.tiles_n, mt = CTA2 ? 2 * (tq / p.tiles_n) + (int)rank : tq / p.tiles_n;
+        const int grp = mt / tiles_per_group, trem = mt - grp * tiles_per_group;
+        const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
+        img0 = grp * p.BNI; y0 = ty * p.BH; x0 = tx * p.BW; n0 = nt * BN;
+      }
       if (n0 != last_n0) {
         epi_bar<32 * Cfg::EPI_WARPS>();          // nobody still reads the previous scale/shift
         for (int j = et; j < BN; j += 32 * Cfg::EPI_WARPS) {
@@ -611,24 +746,37 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       const size_t off = pix * p.cout + n0;
       constexpr int NCH = (BN + 32 * Cfg::EPI_SETS - 1) / (32 * Cfg::EPI_SETS);     // 32-column chunks per epilogue warp
       if (stamp) p.dbg_buf[i * 8 + 0] = clock64();
-      mbar_wait(bar_tfull + 8 * buf, (i >> 1) & 1);
+      // tap-stacked scheme: output row i owns block i % 6 of the regions P and Q (see the MMA warp)
+      const uint32_t blk = i % 6u;
+      const uint32_t colP = nstack ? (uint32_t)(BN * (5 - (int)blk)) : buf * Cfg::ACC_COLS;
+      const uint32_t colQ = nstack ? (uint32_t)(6 * BN) + colP : colP + (uint32_t)BN;
+      if (nstack) mbar_wait(bar_bfull + 8 * blk, (i / 6u) & 1u);
+      else mbar_wait(bar_tfull + 8 * buf, (i >> 1) & 1);
       tc_fence_after();
       if (stamp) p.dbg_buf[i * 8 + 1] = clock64();
       if (tl && et == 0 && i == 0) tl_buf[5] = globaltimer_ns();
 #pragma unroll 1
       if (UPS == 2) {
-        // heads: accumulator columns [0,16) = hi*Whi + lo*Whi, [16,32) = hi*Wlo; channel 0 = pred, 1 = weight_pred
+        // heads: P columns [0,16) = hi*Whi + lo*Whi, Q columns [0,16) = hi*Wlo; channel 0 = pred, 1 = weight_pred
         // (spherical_model_iterative.py:371-374: relu / sigmoid / product)
-        uint32_t v[32];
-        tmem_ld32_issue(tmem + ((uint32_t)(q * 32) << 16) + buf * Cfg::ACC_COLS, v);
+        uint32_t v[32], vq[32];
+        tmem_ld32_issue(tmem + ((uint32_t)(q * 32) << 16) + colP, v);
+        if (nstack) tmem_ld32_issue(tmem + ((uint32_t)(q * 32) << 16) + colQ, vq);
         tmem_ld_wait();
+        if (nstack) {                            // drained: zero the two blocks and hand them back
+          tmem_zero16(tmem + ((uint32_t)(q * 32) << 16) + colP);
+          tmem_zero16(tmem + ((uint32_t)(q * 32) << 16) + colQ);
+          tmem_st_wait();
+        } else {
+          vq[0] = v[16]; vq[1] = v[17];
+        }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        if (lane == 0) mbar_arrive(nstack ? bar_bempty + 8 * blk : bar_tempty + 8 * buf);
         if ((p.dbg & 64) || !ok) continue;
-        float pr = fmaxf((__uint_as_float(v[0]) + __uint_as_float(v[16])) * p.wscale + p.heads_bp, 0.f);
+        float pr = fmaxf((__uint_as_float(v[0]) + __uint_as_float(vq[0])) * p.wscale + p.heads_bp, 0.f);
         if (p.heads_conf) {
-          const float cf = 1.f / (1.f + expf(-((__uint_as_float(v[1]) + __uint_as_float(v[17])) * p.wscale + p.heads_bc)));
+          const float cf = 1.f / (1.f + expf(-((__uint_as_float(v[1]) + __uint_as_float(vq[1])) * p.wscale + p.heads_bc)));
           pr *= cf;
           if (p.heads_il) {
             reinterpret_cast<float2*>(p.heads_pred)[pix] = make_float2(pr, cf);
@@ -644,11 +792,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         const int cb = 32 * eset + ci * 32 * Cfg::EPI_SETS;
         if (cb >= BN) break;
         uint32_t v[32];
-        tmem_ld32_issue(tmem + ((uint32_t)(q * 32) << 16) + buf * Cfg::ACC_COLS + cb, v);
+        tmem_ld32_issue(tmem + ((uint32_t)(q * 32) << 16) + colP + cb, v);
         if (Cfg::STACK) {                        // second column block (hi*Wlo) of the stacked accumulator
           uint32_t v2[32];
           // CTA2: see the column map above TcCfg
-          tmem_ld32_issue(tmem + ((uint32_t)(q * 32) << 16) + buf * Cfg::ACC_COLS + (CTA2 ? (cb < 64 ? 192 : 64) : BN) + cb, v2);
+          tmem_ld32_issue(tmem + ((uint32_t)(q * 32) << 16) + (CTA2 ? colP + (cb < 64 ? 192 : 64) : colQ) + cb, v2);
           tmem_ld_wait();                        // both loads in flight together
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
@@ -656,10 +804,16 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           tmem_ld_wait();
         }
         if (cb + 32 * Cfg::EPI_SETS >= BN) {     // this warp's share of the accumulator is read: hand it back to the MMA warp
+          if (nstack) {                          // (UPS == 1: BN == 32, one chunk) zero the two drained blocks first
+            tmem_zero32(tmem + ((uint32_t)(q * 32) << 16) + colP);
+            tmem_zero32(tmem + ((uint32_t)(q * 32) << 16) + colQ);
+            tmem_st_wait();
+          }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (CTA2 && rank != 0) mbar_arrive_remote(bar_tempty + 8 * buf, 0);
+            if (nstack) mbar_arrive(bar_bempty + 8 * blk);
+            else if (CTA2 && rank != 0) mbar_arrive_remote(bar_tempty + 8 * buf, 0);
             else mbar_arrive(bar_tempty + 8 * buf);
           }
         }
@@ -854,6 +1008,16 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       const int ye = min(p.H, ys + (ups_r1 - g));
       for (int Y = ys - 1; Y <= ye; ++Y, ++pc) {
         const uint32_t slot = pc % Cfg::NST;
+        {
+          // The low-resolution row that the NEXT upsampled rows will need goes into L1 now (one line per plane of
+          // this thread's own column; the neighbours' threads cover x-1 / x+1): the interpolating warps pace this
+          // kernel (probe: 2200 clk per row against 1400 of MMA issue), and a first-touch L2 round trip in load_t
+          // every second row was most of their row time.
+          const int rn = min(((Y + 2) >> 1) + 1, lh - 1);
+          const size_t idx = (((size_t)img * lh + rn) * lw + x) * Cfg::KC + ch * 8;
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(src_hi + idx));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(src_lo + idx));
+        }
         mbar_wait(bars + 8 * (Cfg::NST + slot), ((pc / Cfg::NST) & 1) ^ 1);
         uint4 hi4[2], lo4[2];
         hi4[0] = hi4[1] = lo4[0] = lo4[1] = make_uint4(0u, 0u, 0u, 0u);
@@ -988,6 +1152,7 @@ bool conv_tc_supported(const ofb_conv_desc* d) {
 static thread_local const TcOptions* t_opts = nullptr;
 static TcOptions k_default_opts{};      // options of operator calls made outside an engine forward
 void conv_tc_default_debug(int v) { k_default_opts.dbg = v; }
+void conv_tc_default_nstack(int v) { k_default_opts.nstack = v != 0; k_default_opts.nstack_ups = v >= 2; }
 const TcOptions& tc_opts() { return t_opts ? *t_opts : k_default_opts; }
 TcOptScope::TcOptScope(const TcOptions* o) : prev(t_opts) { t_opts = o; }
 TcOptScope::~TcOptScope() { t_opts = prev; }
@@ -1118,7 +1283,7 @@ static int tc_prepare(const ofb_conv_desc* d, TcPlan& plan) {
   p.residual = d->residual; p.out = d->out; p.act = d->act;
   p.plane = (long long)d->n * oh * ow * d->cout;
   p.dbg = tc_opts().dbg;
-  p.dbg_buf = (tc_opts().dbg & (16 | 256)) ? conv_tc_debug_buffer() : nullptr;
+  p.dbg_buf = (tc_opts().dbg & (16 | 256 | 2048)) ? conv_tc_debug_buffer() : nullptr;
   p.group64 = tc_opts().cta2 ? 1 : 0;
   const int S = d->ksplit > 1 ? d->ksplit : 1;
   OFB_CHECK(S == 1 || (split && d->k == 1 && d->stride == 1 && !d->ups2x && d->partial && (cin / kc) % S == 0),
@@ -1168,7 +1333,19 @@ static int tc_prepare(const ofb_conv_desc* d, TcPlan& plan) {
       if (make_map(&maps.a[src][pl], split, 4, a, dims, box, row_bytes, d->stride)) return -1;
     }
   }
-  if (khr) {
+  // The tap-stacked scheme is used by the heads only: for this 32-channel layer 18 MMAs of N = 96 cost what 36 of
+  // N = 64 / 32 cost (measured with tools/probe_rolling.py: 1630 clk of issue per input row, 172 vs 162 us per launch
+  // with the larger TMEM footprint and the block zero fills), for the heads' N = 48 they are cheaper (123 vs 135 us).
+  p.nstack = (d->ups2x && tc_opts().nstack && tc_opts().nstack_ups) ? 1 : 0;
+  if (khr && p.nstack) {
+    // tap-stacked rolling-row kernel: per plane one map over (cout, kh, kw, cin) seen as dims {cin, cout, kh, kw};
+    // one box = {kc, bn rows, all 3 kh, one kw} -> shared memory [kh][bn rows] = the kh slices of a plane stacked
+    cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)d->cout, 3, 3};
+    cuuint64_t bstr[3] = {(cuuint64_t)9 * cin * es, (cuuint64_t)3 * cin * es, (cuuint64_t)cin * es};
+    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)bn, 3u, 1u};
+    for (int pl = 0; pl < 2; ++pl)
+      if (make_map(&maps.b[pl], split, 4, (char*)d->wgt_split + (size_t)pl * d->cout * 9 * cin * es, dims, box, row_bytes, 1, bstr)) return -1;
+  } else if (khr) {
     // weights: the hi plane (cout, kh, kw, cin) is followed by the lo plane, i.e. one (2*cout, kh, kw, cin)
     // tensor = the stacked [Whi; Wlo] operand.  Seen as dims {cin, 2*cout, kh, kw}: one box = {kc, 2*bn rows,
     // all 3 kh, one kw} -> shared memory [kh][Whi rows; Wlo rows]
@@ -1619,7 +1796,7 @@ int conv_tc_heads(const void* x, int n, int h, int w, const void* wgt_split, flo
   p.heads_pred = pred_out; p.heads_conf = confidence ? conf_out : nullptr; p.heads_bp = b_pred; p.heads_bc = b_conf;
   p.heads_il = interleaved ? 1 : 0;
   p.dbg = tc_opts().dbg;
-  p.dbg_buf = (tc_opts().dbg & (16 | 256)) ? conv_tc_debug_buffer() : nullptr;
+  p.dbg_buf = (tc_opts().dbg & (16 | 256 | 2048)) ? conv_tc_debug_buffer() : nullptr;
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
   const size_t plane = (size_t)n * h * w * 32;               // halves per plane
@@ -1629,7 +1806,14 @@ int conv_tc_heads(const void* x, int n, int h, int w, const void* wgt_split, flo
     if (make_map(&maps.a[0][pl], true, 4, (char*)x + pl * plane * 2, dims, box, 64)) return -1;
     maps.a[1][pl] = maps.a[0][pl];
   }
-  {  // weights: (2*16, kh, kw, 32) = stacked [Whi; Wlo]; one box = {32 channels, 32 rows, all 3 kh, one kw}
+  p.nstack = tc_opts().nstack ? 1 : 0;
+  if (p.nstack) {  // per plane (16, kh, kw, 32): one box = {32 channels, 16 rows, all 3 kh, one kw} -> [kh][16 rows]
+    cuuint64_t dims[4] = {32, 16, 3, 3};
+    cuuint64_t bstr[3] = {(cuuint64_t)9 * 32 * 2, (cuuint64_t)3 * 32 * 2, (cuuint64_t)32 * 2};
+    cuuint32_t box[4] = {32u, 16u, 3u, 1u};
+    for (int pl = 0; pl < 2; ++pl)
+      if (make_map(&maps.b[pl], true, 4, (char*)wgt_split + (size_t)pl * 16 * 9 * 32 * 2, dims, box, 64, 1, bstr)) return -1;
+  } else {  // weights: (2*16, kh, kw, 32) = stacked [Whi; Wlo]; one box = {32 channels, 32 rows, all 3 kh, one kw}
     cuuint64_t dims[4] = {32, 32, 3, 3};
     cuuint64_t bstr[3] = {(cuuint64_t)9 * 32 * 2, (cuuint64_t)3 * 32 * 2, (cuuint64_t)32 * 2};
     cuuint32_t box[4] = {32u, 32u, 3u, 1u};

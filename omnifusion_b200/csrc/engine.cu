@@ -46,6 +46,7 @@ int range_launch(const void* p, size_t n, int fmt, unsigned int* out2, cudaStrea
 long long* conv_tc_debug_buffer();
 int conv_tc_timeline_slots();
 void conv_tc_default_debug(int v);
+void conv_tc_default_nstack(int v);
 const char* conv_tc_last_variant();
 
 int conv_dispatch(const ofb_conv_desc* d, cudaStream_t s) {
@@ -891,6 +892,7 @@ extern "C" int ofb_set_option(ofb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "tc_debug")) h->tc.dbg = value;               // timing experiments only (wrong results)
   else if (!strcmp(key, "fill_div")) h->tc.fill_div = value > 0 ? value : 2;   // N-tile shrink threshold (experiments)
   else if (!strcmp(key, "direct32")) h->tc.direct32 = value != 0;        // (experiments)
+  else if (!strcmp(key, "nstack")) { h->tc.nstack = value != 0; h->tc.nstack_ups = value >= 2; }   // tap-stacked MMAs: 1 heads, 2 also de_conv4_0
   else if (!strcmp(key, "cta2")) h->tc.cta2 = value != 0;               // cta_group::2 CTA pairs
   else if (!strcmp(key, "format")) {
     OFB_CHECK(value == OFB_FMT_F32 || value == OFB_FMT_SPLIT16, "set_option: format must be 0 (float32) or 1 (split-half)");
@@ -956,6 +958,7 @@ extern "C" int ofb_forward_f32(ofb_handle* h, const float* rgb, int B, int iters
 
 // timing experiments: TcParams::dbg of tcgen05 convs launched directly through ofb_conv_f32 (tools/probe_mid.py)
 extern "C" int ofb_debug_set(int v) { conv_tc_default_debug(v); return 0; }
+extern "C" int ofb_debug_nstack(int v) { conv_tc_default_nstack(v); return 0; }   // 0 off, 1 heads, 2 also fused-upsample conv
 
 // timing experiments: copies the clock stamps recorded with tc_debug & 16 (512 x 8 int64) to the host
 extern "C" int ofb_debug_stamps(long long* host_dst) {

@@ -251,7 +251,7 @@ def test_batch_invariance_chunking_dedup_and_graph(fmt):
             net.set_option("fuse_ups", 1)
             d = ((unfused[1] - base[1]).abs() / base[1].abs().clamp_min(1e-6)).max().item()
             print(f"[parity] fused vs materialised upsample: depth max rel diff {d:.3e}")
-            assert d <= 2e-6
+            assert d <= 5e-6
         if FORMATS[fmt] == 1:
             # layer2's seven same-shape convs run as one image-stationary chain launch; separate launches must agree
             # bit for bit (same tiles, same accumulation order)
