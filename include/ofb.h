@@ -210,6 +210,24 @@ int ofb_attention_qkv_f32(const void* qkv, int B, int N, int heads, int head_dim
  * TMEM), softmax per query row out of TMEM.  N <= 64, head_dim == 128. */
 int ofb_attention_tc_f16(const void* qkv_planes, int B, int N, int heads, int head_dim, void* out_planes, void* stream);
 
+/* The whole transformer stack of the patch network (model/blocks.py:50-88, Transformer_Block x nblk, followed by
+ * transformer.encoder_norm; spherical_model_iterative.py:332-333) as ONE launch (csrc/token_tc.cu): a group of 16
+ * CTAs per panorama, weights streamed by TMA, all four linears as tcgen05 MMAs with the weight rows as M and the
+ * tokens as N, exchanges inside the group through L2 and per-panorama arrival counters.  Uses the weights loaded into `h`.  x (B*N, 512) float32 is
+ * the residual stream, updated in place; enc_out (B*N, 512) float32 receives encoder_norm(x) when stop_phase == 0.
+ * stop_phase = k > 0 stops after the first k GEMM phases (4 per block: qkv + attention, proj, fc1, fc2) - tests read
+ * the exchange buffers in `scratch` = [partial scores (B,4 heads,4 quarters,N,N) | attention output (B*N,512) |
+ * fc2 partial sums (B,16,N,512)], ofb_token_stack_scratch_floats(B, N) floats.  N <= 48.  The engine option
+ * "token_fused" (default 1) selects this path inside ofb_forward_f32 for the split-half format. */
+int ofb_token_stack_f32(ofb_handle* h, float* x, float* scratch, long long scratch_floats, float* enc_out, int B, int N,
+                        int nblk, int stop_phase, void* stream);
+long long ofb_token_stack_scratch_floats(int B, int N);
+/* Panoramas (groups of 16 CTAs, one CTA per SM) of that kernel the device runs at once: 9 on a 148-SM B200. */
+int ofb_token_stack_resident_groups(int N);
+/* experiments (tools/probe_token.py): device buffer of 24 x 8 int64 that thread 0 of CTA 0 of the following
+ * token-stack launches fills with clock64 stamps per GEMM phase; NULL switches it off */
+int ofb_debug_token_stamps(long long* dev_buf);
+
 /* The same heads on the tensor pipe (split-half format only): x_planes = split-half planes of (imgs,h,128,32),
  * wgt_split = split-half planes of the (16,3,3,32) filter bank [pred; weight_pred; 14 zero rows] scaled by
  * 1 / wgt_unscale (ofb_split_f16).  Rolling-row tcgen05 kernel, see csrc/conv_tc.cu (conv_tc_heads). */

@@ -68,6 +68,10 @@ _SIGNATURES = {
     "ofb_attention_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "ofb_attention_qkv_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _P]),
     "ofb_attention_tc_f16": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "ofb_token_stack_f32": (_I, [_P, _P, _P, C.c_longlong, _P, _I, _I, _I, _I, _P]),
+    "ofb_token_stack_scratch_floats": (C.c_longlong, [_I, _I]),
+    "ofb_token_stack_resident_groups": (_I, [_I]),
+    "ofb_debug_token_stamps": (_I, [_P]),
     "ofb_heads_tc_f16": (_I, [_P, _I, _I, _I, _P, C.c_float, C.c_float, C.c_float, _I, _P, _P, _P]),
     "ofb_heads_f32": (_I, [_P, _I, _I, _I, _P, C.c_float, _P, C.c_float, _I, _P, _P, _I, _P]),
     "ofb_u8hwc_to_f32chw": (_I, [_P, _I, _I, _I, _I, _P, _P]),

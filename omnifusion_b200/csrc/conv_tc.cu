@@ -23,10 +23,10 @@
 
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tc_ptx.cuh"
 
 namespace ofb {
 
-enum { MODE_TF32 = 0, MODE_F16X3 = 1 };
 
 struct TcParams {
   int n_img, H, W, c0, c1, cout, k, pad, stride;   // H, W: output dims
@@ -57,142 +57,6 @@ struct TcParams {
   int group64;           // accumulate the three split-half products in the cta_group::2 column grouping (see the MMA warp)
   int nstack;            // UPS kernels: input-row-stationary MMAs with the three kh taps stacked along N (see the MMA warp)
 };
-
-// ------------------------------------------------------------------ PTX wrappers (mbarrier: ptx.cuh)
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
-                                            int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-// cta_group::2 variants: both CTAs of a pair load into their own shared memory, the transaction bytes are
-// counted on the LEADER CTA's mbarrier (shared::cluster address with the CTA-rank bit cleared)
-__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
-                                                int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
-  asm volatile(
-      "{\n.reg .b32 ra;\nmapa.shared::cluster.u32 ra, %0, %1;\n"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n}\n" ::"r"(bar), "r"(rank) : "memory");
-}
-// tcgen05.commit of a CTA pair: arrives on the barrier at this offset in both CTAs
-__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-// One lane of a fully converged warp.  The producer and MMA warps run their loops with all 32 lanes (uniform
-// control flow, operands provably warp-uniform so that they live in uniform registers) and only the issue of
-// the TMA / tcgen05 instructions is predicated on this: a `lane == 0` branch around the whole loop makes the
-// compiler wrap every such instruction in a divergence "waterfall" (ELECT + R2UR.BROADCAST x5 + BRA.U.ANY),
-// ~70 clocks of issue per MMA on the one thread that paces the tensor pipe.
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.b32 %0, 1, 0, P;\n}\n" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
-constexpr int kTimelineSlots = 1024;
-__device__ __forceinline__ long long globaltimer_ns() {
-  long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-template <int MODE, bool CTA2 = false>
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  if (CTA2) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-  } else if (MODE == MODE_TF32) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-  } else {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-  }
-}
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
-      "%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// zero-fill of 32 / 16 accumulator columns of this warp's 32 TMEM lanes
-__device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
-  const uint32_t z = 0u;
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
-      ::"r"(taddr), "r"(z) : "memory");
-}
-__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
-  const uint32_t z = 0u;
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
-      ::"r"(taddr), "r"(z) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
-// LBO (unused for swizzled K-major) = 1, SBO = bytes between 8-row groups >> 4, version = 1
-// (Blackwell), layout type 2 = SWIZZLE_128B / 4 = SWIZZLE_64B.
-template <int ROW_BYTES>
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)((8 * ROW_BYTES) >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61;
-  return d;
-}
 
 __device__ __forceinline__ float act_fn(float v, int act) {
   if (act == OFB_ACT_RELU) return fmaxf(v, 0.f);
@@ -282,9 +146,6 @@ struct TcMaps {
   CUtensorMap o[2];
 };
 
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 template <int NTHREADS>
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
@@ -1101,9 +962,8 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-static int make_map(CUtensorMap* m, bool half, int rank, void* addr, const cuuint64_t* dims, const cuuint32_t* box,
-                    int row_bytes, int spatial_stride = 1, const cuuint64_t* byte_strides = nullptr,
-                    const cuuint32_t* elem_strides = nullptr) {
+int tc_make_map(CUtensorMap* m, bool half, int rank, void* addr, const cuuint64_t* dims, const cuuint32_t* box,
+                int row_bytes, int spatial_stride, const cuuint64_t* byte_strides, const cuuint32_t* elem_strides) {
   EncodeTiledFn fn = encode_fn();
   OFB_CHECK(fn, "conv_tc: cuTensorMapEncodeTiled is not available from the driver");
   const int es = half ? 2 : 4;
@@ -1120,6 +980,11 @@ static int make_map(CUtensorMap* m, bool half, int rank, void* addr, const cuuin
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   OFB_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
   return 0;
+}
+static int make_map(CUtensorMap* m, bool half, int rank, void* addr, const cuuint64_t* dims, const cuuint32_t* box,
+                    int row_bytes, int spatial_stride = 1, const cuuint64_t* byte_strides = nullptr,
+                    const cuuint32_t* elem_strides = nullptr) {
+  return tc_make_map(m, half, rank, addr, dims, box, row_bytes, spatial_stride, byte_strides, elem_strides);
 }
 
 static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }

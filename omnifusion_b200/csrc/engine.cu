@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "token_tc.cuh"
 
 namespace ofb {
 
@@ -41,7 +42,8 @@ int blend_conf_launch(const float* pred_w, const float* conf, bool interleaved, 
                       cudaStream_t s);
 int deinterleave_launch(const float* src_pairs, size_t n, int comp, float* dst, cudaStream_t s);
 int zero_stem_pads(void* patches, int imgs, int P, cudaStream_t s);
-int token_pack(const void* down, const float* pos_emb, int imgs, int N, int spatial, int cstride, void* tokens, int fmt, cudaStream_t s);
+int token_pack(const void* down, const float* pos_emb, int imgs, int N, int spatial, int cstride, void* tokens, int fmt, cudaStream_t s, int out_fmt = -1);
+void token_stack_debug_stamps(long long* p);
 int range_launch(const void* p, size_t n, int fmt, unsigned int* out2, cudaStream_t s);
 long long* conv_tc_debug_buffer();
 int conv_tc_timeline_slots();
@@ -97,6 +99,9 @@ struct ofb_handle {
   int splitk = 4;                  // K slices of the two 512-wide token linears on the tcgen05 engine (1 = off)
   int heads_tc = 1;                // run the heads on the tensor pipe (split-half format, 128-pixel rows)
   int attn_tc = 1;                 // attention core on the tensor pipe (split-half format; tcgen05 QK^T and PV)
+  int token_fused = 1;             // the whole transformer stack as one launch of 16-CTA clusters (token_tc.cu)
+  TokStack tok_stack{};            // its kernel argument (weight tensor maps + epilogue constants), built by load_weights
+  bool tok_ready = false;
   int chain = 1;                   // run the same-shape convs of an encoder stage as one image-stationary chain launch
                                    // (1: stages whose dependencies stay inside a CTA pair; 2: also cross-cluster chains)
   int no_point_feat = 0;           // ablation of network_360d.py:325 - layer1 is used without the point-feature add
@@ -382,7 +387,7 @@ struct Plan {
 struct Buffers {
   float *patches, *conv1, *pool, *l1t, *l1a, *l1b, *layer1_pre, *layer1;
   float *l2t, *l2a, *l2b, *l2d, *layer2, *l3t, *l3a, *l3b, *l3d, *layer3, *l4t, *l4a, *l4b, *l4d, *layer4;
-  float *down, *tok, *ln, *q, *kv, *att, *tok2, *fc1, *enc, *part;
+  float *down, *tok, *ln, *q, *kv, *att, *tok2, *fc1, *enc, *part, *tokx;
   float *up0, *d00, *d01, *up1, *d10, *d11, *up2, *d20, *d21, *up3, *d30, *d31, *up4, *d40;
   float *pred, *conf, *depth_p;
 };
@@ -403,6 +408,7 @@ static size_t plan_buffers(ofb_handle* h, int imgs, int P, Buffers* b) {
   b->kv = pl.take(I * 1536); b->att = pl.take(I * 512); b->tok2 = pl.take(I * 512); b->fc1 = pl.take(I * 2048);
   b->enc = pl.take(I * 512);
   b->part = pl.take(I * 512 * 4);                  // split-K partial sums of attn.proj / mlp.fc2 (4 slices)
+  b->tokx = pl.take(I * (512 * 17 + 16 * 48));     // exchange buffers of the fused transformer stack (token_stack_scratch_floats, N <= 48)
   b->up0 = pl.take(I * p16 * p16 * 512); b->d00 = pl.take(I * p16 * p16 * 256); b->d01 = pl.take(I * p16 * p16 * 128);
   b->up1 = pl.take(I * p8 * p8 * 128); b->d10 = pl.take(I * p8 * p8 * 128); b->d11 = pl.take(I * p8 * p8 * 64);
   b->up2 = pl.take(I * p4 * p4 * 64); b->d20 = pl.take(I * p4 * p4 * 64); b->d21 = pl.take(I * p4 * p4 * 64);
@@ -652,13 +658,22 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
       if (run_linear(c16, h->down, b.layer4, nullptr, OFB_ACT_NONE, b.down)) return -1;
     }
     OFB_CHECK(h->pos_patches == N, "forward: pos_emb has %d patches, geometry has %d", h->pos_patches, N);
+    const int nblk = h->dbg_blocks;
+    bool fused_tokens = h->token_fused && h->tok_ready && F == OFB_FMT_SPLIT16 && h->engine != OFB_ENGINE_SIMT &&
+                        nblk > 0 && token_stack_supported(N);
+    fused_tokens = fused_tokens && Bc <= kTokMaxPanos;
     { Prof pr(h, s, "token_pack", 0.0, 4.0*((double)imgs*1024));
-    if (token_pack(b.down, h->pos_emb, imgs, N, S32, h->down.cout, b.tok, F, s)) return -1; }
+    if (token_pack(b.down, h->pos_emb, imgs, N, S32, h->down.cout, b.tok, F, s, fused_tokens ? OFB_FMT_F32 : F)) return -1; }
     float* x = b.tok;
     float* y = b.tok2;
     const int SK = (F == OFB_FMT_SPLIT16 && h->engine != OFB_ENGINE_SIMT) ? h->splitk : 1;
-    const int nblk = h->dbg_blocks;
-    if (SK > 1 && nblk > 0) {
+    if (fused_tokens) {
+      // all Transformer_Blocks (model/blocks.py:50-88) + encoder_norm in one launch: a group of 16 CTAs per panorama
+      TokStack st = h->tok_stack;
+      st.nblk = nblk;
+      Prof pr(h, s, "token_stack", 2.0*(double)imgs*nblk*(512.0*1536 + 512.0*512 + 2*512.0*2048), 4.0*nblk*3.15e6);
+      if (token_stack_launch(st, x, b.tokx, token_stack_scratch_floats(Bc, N), b.enc, Bc, N, 0, h->cur, h->tc.pdl, s)) return -1;
+    } else if (SK > 1 && nblk > 0) {
       // attn.proj and mlp.fc2 run split-K; their finish kernels add bias + residual and apply the NEXT LayerNorm
       { Prof pr(h, s, "layernorm", 0.0, 4.0*((double)imgs*1024));
       if (ofb_layernorm_f32(x, h->blk[0].n1g, h->blk[0].n1b, imgs, 512, 1e-5f, b.ln, F, F, vs)) return -1; }
@@ -796,6 +811,20 @@ extern "C" int ofb_heads_tc_pairs_f16(const void* x_planes, int imgs, int h, int
                        (cudaStream_t)stream);
 }
 
+// The fused transformer stack on its own (tests): x (B, N, 512) float32 is updated in place, scratch holds the
+// exchange buffers [scores (B,4,4,N,N) | attention output (B,N,512) | fc2 partial sums (B,16,N,512)]
+extern "C" int ofb_token_stack_f32(ofb_handle* h, float* x, float* scratch, long long scratch_floats, float* enc_out, int B,
+                                   int N, int nblk, int stop_phase, void* stream) {
+  OFB_CHECK(h && h->has_weights && h->tok_ready, "token_stack: no weights loaded (or no split-half planes)");
+  OFB_CHECK(nblk >= 1 && nblk <= 6, "token_stack: 1..6 blocks (got %d)", nblk);
+  TokStack st = h->tok_stack;
+  st.nblk = nblk;
+  return token_stack_launch(st, x, scratch, (size_t)scratch_floats, enc_out, B, N, stop_phase, 0, false, (cudaStream_t)stream);
+}
+extern "C" int ofb_debug_token_stamps(long long* dev_buf) { token_stack_debug_stamps(dev_buf); return 0; }   // [24 phases][8] clocks, experiments
+extern "C" long long ofb_token_stack_scratch_floats(int B, int N) { return (long long)token_stack_scratch_floats(B, N); }
+extern "C" int ofb_token_stack_resident_groups(int N) { return token_stack_supported(N) ? token_stack_resident_groups(N) : 0; }
+
 extern "C" int ofb_attention_tc_f16(const void* qkv_planes, int B, int N, int heads, int head_dim, void* out_planes,
                                     void* stream) {
   OFB_CHECK(head_dim == 128, "attention_tc: head_dim must be 128 (got %d)", head_dim);
@@ -828,6 +857,7 @@ extern "C" int ofb_destroy(ofb_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   free_weights(h);
+  token_stack_release(&h->tok_stack);
   drop_profile_records(h);
   for (int l = 0; l < 2; ++l)
     if (h->lane[l].ws) cudaFree(h->lane[l].ws);
@@ -866,6 +896,20 @@ extern "C" int ofb_load_weights(ofb_handle* h, const ofb_tensor_desc* tensors, i
   h->single = single_stage != 0;
   if (load_all(h, m, h->single)) { free_weights(h); return -1; }
   OFB_CUDA(cudaStreamSynchronize(nullptr));      // all split-half conversions of the checkpoint
+  {
+    TokBlockDesc tb[6];
+    bool ok = true;
+    for (int i = 0; i < 6; ++i) {
+      Block& B = h->blk[i];
+      const ConvW* cw[4] = {&B.qkv, &B.proj, &B.fc1, &B.fc2};
+      for (int j = 0; j < 4; ++j) {
+        tb[i].lin[j].ws = cw[j]->ws; tb[i].lin[j].bias = cw[j]->shift; tb[i].lin[j].unscale = cw[j]->unscale;
+        ok = ok && cw[j]->ws && (cw[j]->shift || j == 0);
+      }
+      tb[i].n1g = B.n1g; tb[i].n1b = B.n1b; tb[i].n2g = B.n2g; tb[i].n2b = B.n2b;
+    }
+    h->tok_ready = ok && token_stack_prepare(tb, 6, h->enc_g, h->enc_b, &h->tok_stack) == 0;
+  }
   h->has_weights = true;
   return 0;
 }
@@ -879,6 +923,7 @@ extern "C" int ofb_set_option(ofb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "fuse_ups")) h->fuse_ups = value;
   else if (!strcmp(key, "heads_tc")) h->heads_tc = value;
   else if (!strcmp(key, "attn_tc")) h->attn_tc = value;
+  else if (!strcmp(key, "token_fused")) h->token_fused = value;
   else if (!strcmp(key, "check_range")) h->check_range = value;
   else if (!strcmp(key, "chain")) h->chain = value;
   else if (!strcmp(key, "no_point_feat")) h->no_point_feat = value != 0;

@@ -320,7 +320,7 @@ point_embed_kernel(const float* __restrict__ pts, int N, int cin, int p,
 // down (imgs, S, S, Cd) with S*S*Cd == 512 -> tokens (imgs, 512), token index = c*S*S + i*S + j (the reference's
 // reshape of the (B, Cd, S, S, N) map, spherical_model_iterative.py:330-331), + pos_emb.  S = 4, Cd = 32 for 128x128
 // patches; S = 8, Cd = 8 for the 256x256 variant (network_test.py:271).
-template <bool SPLIT>
+template <bool SPLIT, bool OUT_SPLIT>
 __global__ void token_pack_kernel(const void* __restrict__ down, const float* __restrict__ pos,
                                   int imgs, int N, int ss, int cstride, void* __restrict__ tokens) {
   // cstride: channels per position of `down` in memory (>= 512 / ss: narrower reductions are padded to 32 channels)
@@ -330,7 +330,7 @@ __global__ void token_pack_kernel(const void* __restrict__ down, const float* __
   int c = t / ss, ij = t - c * ss;
   const size_t in_plane = (size_t)imgs * ss * cstride, plane = (size_t)imgs * 512;
   float v = act_ld1<SPLIT>(down, ((size_t)img * ss + ij) * cstride + c, in_plane) + __ldg(&pos[(img % N) * 512 + t]);
-  act_st1<SPLIT>(tokens, i, plane, v);
+  act_st1<OUT_SPLIT>(tokens, i, plane, v);
 }
 
 // ------------------------------------------------------------------ layernorm
@@ -738,13 +738,16 @@ extern "C" int ofb_point_embed_f32(const float* pts, int N, int cin, int p, cons
 }
 
 namespace ofb {
-int token_pack(const void* down, const float* pos_emb, int imgs, int N, int spatial, int cstride, void* tokens, int fmt, cudaStream_t s) {
+int token_pack(const void* down, const float* pos_emb, int imgs, int N, int spatial, int cstride, void* tokens, int fmt, cudaStream_t s, int out_fmt = -1);
+int token_pack(const void* down, const float* pos_emb, int imgs, int N, int spatial, int cstride, void* tokens, int fmt, cudaStream_t s, int out_fmt) {
   OFB_CHECK(down && pos_emb && tokens && OFB_FMT_OK(fmt), "token_pack: bad arguments");
+  if (out_fmt < 0) out_fmt = fmt;
   const int ss = spatial * spatial;
   OFB_CHECK(ss > 0 && 512 % ss == 0 && cstride >= 512 / ss, "token_pack: %dx%d positions x %d channels do not hold the 512-wide token", spatial, spatial, cstride);
   int blocks = cdiv((long long)imgs * 512, 256);
-  if (fmt) token_pack_kernel<true><<<blocks, 256, 0, s>>>(down, pos_emb, imgs, N, ss, cstride, tokens);
-  else token_pack_kernel<false><<<blocks, 256, 0, s>>>(down, pos_emb, imgs, N, ss, cstride, tokens);
+  if (fmt && out_fmt) token_pack_kernel<true, true><<<blocks, 256, 0, s>>>(down, pos_emb, imgs, N, ss, cstride, tokens);
+  else if (fmt) token_pack_kernel<true, false><<<blocks, 256, 0, s>>>(down, pos_emb, imgs, N, ss, cstride, tokens);
+  else token_pack_kernel<false, false><<<blocks, 256, 0, s>>>(down, pos_emb, imgs, N, ss, cstride, tokens);
   OFB_LAUNCH_CHECK();
   return 0;
 }
