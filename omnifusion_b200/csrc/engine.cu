@@ -99,9 +99,11 @@ struct ofb_handle {
   int splitk = 4;                  // K slices of the two 512-wide token linears on the tcgen05 engine (1 = off)
   int heads_tc = 1;                // run the heads on the tensor pipe (split-half format, 128-pixel rows)
   int attn_tc = 1;                 // attention core on the tensor pipe (split-half format; tcgen05 QK^T and PV)
-  int token_fused = 1;             // the whole transformer stack as one launch of 16-CTA clusters (token_tc.cu)
+  int token_fused = 1;             // the whole transformer stack as one launch, 16 CTAs per panorama (token_tc.cu):
+                                   // 0 never, 1 when all panoramas of a chunk are resident at once, 2 whenever supported
   TokStack tok_stack{};            // its kernel argument (weight tensor maps + epilogue constants), built by load_weights
   bool tok_ready = false;
+  int tok_groups = -1;             // groups of 16 CTAs of that kernel resident at once (-1: not asked yet)
   int chain = 1;                   // run the same-shape convs of an encoder stage as one image-stationary chain launch
                                    // (1: stages whose dependencies stay inside a CTA pair; 2: also cross-cluster chains)
   int no_point_feat = 0;           // ablation of network_360d.py:325 - layer1 is used without the point-feature add
@@ -661,6 +663,15 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
     const int nblk = h->dbg_blocks;
     bool fused_tokens = h->token_fused && h->tok_ready && F == OFB_FMT_SPLIT16 && h->engine != OFB_ENGINE_SIMT &&
                         nblk > 0 && token_stack_supported(N);
+    if (fused_tokens && h->token_fused == 1) {
+      // The fused stack is the low-latency form: a group of 16 CTAs per panorama, all groups of a launch resident at
+      // once (9 on 148 SMs).  More panoramas than that run in waves that each stream the weights again, and the
+      // 48-token instantiation has a two-stage ring: measured slower than the per-layer path there (32 panoramas:
+      // 1.42 vs 0.84 ms per step; 16 x 46 tokens: 1.86 vs 1.43 ms), faster below (8 x 18: 0.35 vs 0.53 ms, 1 x 18:
+      // -0.14 ms, 8 x 26: -0.13 ms).  Option token_fused = 2 forces it.
+      if (h->tok_groups < 0) h->tok_groups = token_stack_resident_groups(N);
+      fused_tokens = N <= 32 && Bc <= h->tok_groups;
+    }
     fused_tokens = fused_tokens && Bc <= kTokMaxPanos;
     { Prof pr(h, s, "token_pack", 0.0, 4.0*((double)imgs*1024));
     if (token_pack(b.down, h->pos_emb, imgs, N, S32, h->down.cout, b.tok, F, s, fused_tokens ? OFB_FMT_F32 : F)) return -1; }

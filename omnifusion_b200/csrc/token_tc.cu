@@ -99,6 +99,14 @@ __device__ __forceinline__ void fill_rows(uint8_t* xb_ptr, const float* __restri
                                           const float* __restrict__ beta, float eps, bool ln, int N, int warp, int lane) {
   constexpr int CH = TokCfg<NP>::CH;
   float v[R][16];
+  float4 gm[4], bt[4];          // fetched together with the rows: their latency hides behind the same round trip
+  if (ln) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      gm[i] = __ldg(reinterpret_cast<const float4*>(gamma + i * 128 + lane * 4));
+      bt[i] = __ldg(reinterpret_cast<const float4*>(beta + i * 128 + lane * 4));
+    }
+  }
 #pragma unroll
   for (int u = 0; u < R; ++u) {
     const int t = warp + 8 * u < N ? warp + 8 * u : 0;       // rows beyond N: load row 0, never stored
@@ -139,14 +147,12 @@ __device__ __forceinline__ void fill_rows(uint8_t* xb_ptr, const float* __restri
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + i * 128 + lane * 4));
-      const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + i * 128 + lane * 4));
 #pragma unroll
       for (int u = 0; u < R; ++u) {
-        v[u][4 * i] = (v[u][4 * i] - s[u]) * q[u] * gm.x + bt.x;
-        v[u][4 * i + 1] = (v[u][4 * i + 1] - s[u]) * q[u] * gm.y + bt.y;
-        v[u][4 * i + 2] = (v[u][4 * i + 2] - s[u]) * q[u] * gm.z + bt.z;
-        v[u][4 * i + 3] = (v[u][4 * i + 3] - s[u]) * q[u] * gm.w + bt.w;
+        v[u][4 * i] = (v[u][4 * i] - s[u]) * q[u] * gm[i].x + bt[i].x;
+        v[u][4 * i + 1] = (v[u][4 * i + 1] - s[u]) * q[u] * gm[i].y + bt[i].y;
+        v[u][4 * i + 2] = (v[u][4 * i + 2] - s[u]) * q[u] * gm[i].z + bt[i].z;
+        v[u][4 * i + 3] = (v[u][4 * i + 3] - s[u]) * q[u] * gm[i].w + bt[i].w;
       }
     }
   }

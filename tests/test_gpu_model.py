@@ -284,6 +284,29 @@ def test_layer_chains_are_bit_identical_at_every_slot_count():
     net.set_option("chain", 1)
 
 
+@pytest.mark.parametrize("nrows,bs", [(4, 2), (5, 1), (6, 1), (4, 11)])
+def test_fused_transformer_stack_against_per_layer_path(nrows, bs):
+    """Engine option token_fused: the six Transformer_Blocks as one launch (csrc/token_tc.cu; default whenever the
+    chunk's panoramas are resident at once, forced here with 2) against the per-layer launches (0).  Same split-half
+    products, different summation order and an fp32 instead of a split-half residual stream: the depths agree far
+    inside the 1e-3 bar both paths meet against the oracle."""
+    net = model("iterative", nrows)
+    rgb = urand(bs, 3, 64, 128, seed=60 + nrows).to(DEV)
+    try:
+        with torch.no_grad():
+            net.set_option("token_fused", 2)
+            a = [t.clone() for t in net(rgb, iter=2, confidence=True)]
+            net.set_option("token_fused", 0)
+            b = [t.clone() for t in net(rgb, iter=2, confidence=True)]
+    finally:
+        net.set_option("token_fused", 1)
+    for x, y in zip(a, b):
+        assert torch.isfinite(x).all()
+        e = max_rel(x.cpu(), y.cpu())
+        print(f"[parity] fused vs per-layer transformer, nrows={nrows} bs={bs}: depth max rel {e:.2e}")
+        assert e <= 2e-5
+
+
 def test_module_prefix_checkpoint_and_errors():
     from omnifusion_b200 import _lib
     from omnifusion_b200.model.spherical_model_iterative import spherical_fusion
