@@ -74,10 +74,19 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
 __device__ __forceinline__ void red_release_gpu(unsigned int* p, unsigned int v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// mbarrier wait of this kernel: a broken hand-off must fault within about a second
+// Waits of this kernel are bounded in TIME (a group may legitimately wait for a whole wave of earlier groups, and a
+// sanitizer slows everything down by orders of magnitude): a broken hand-off faults after four seconds instead of
+// hanging the GPU.
+__device__ __forceinline__ bool tk_expired(int& spins, long long& t0) {
+  if ((++spins & 1023) != 0) return false;
+  const long long now = globaltimer_ns();
+  if (t0 == 0) t0 = now;
+  return now - t0 > 4000000000LL;
+}
 __device__ __forceinline__ void tk_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   int spins = 0;
+  long long t0 = 0;
   while (true) {
     asm volatile(
         "{\n.reg .pred p;\n"
@@ -85,7 +94,7 @@ __device__ __forceinline__ void tk_wait(uint32_t bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n}\n"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (done) break;
-    if (++spins > (1 << 20)) __trap();
+    if (tk_expired(spins, t0)) __trap();
   }
 }
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TK_WORKERS) : "memory"); }
@@ -348,7 +357,8 @@ token_stack_kernel(const __grid_constant__ TokStack st, float* __restrict__ xg, 
       if (tid == 0) {
         red_release_gpu(ctr, 1u);
         int spins = 0;
-        while (ld_acquire_gpu(ctr) < xtarget) { if (++spins > (1 << 20)) __trap(); }
+        long long t0 = 0;
+        while (ld_acquire_gpu(ctr) < xtarget) { if (tk_expired(spins, t0)) __trap(); }
       }
       worker_sync();
     };
