@@ -133,9 +133,10 @@ typedef struct {
   int in_fmt, out_fmt;
   const void* wgt_split; float wgt_unscale;
   int ups2x;
-  int ksplit;        /* > 1 (tcgen05 engine, split-half 1x1 layers only): K is split over `ksplit` CTAs per tile; the
-                        raw float32 partial sums go to `partial` (ksplit, n*h*w, cout) and scale / shift / residual /
-                        act / out are NOT applied - ofb_splitk_finish_ln_f32 finishes the layer */
+  int ksplit;        /* > 1 (tcgen05 engine, split-half format; 1x1 layers and 3x3 stride-1 layers with cout > 64): the
+                        channel chunks of K are split over `ksplit` CTAs per tile; the raw float32 partial sums go to
+                        `partial` (ksplit, n*h*w, cout) and scale / shift / residual / act / out are NOT applied -
+                        ofb_splitk_finish_ln_f32 (token linears) / ofb_splitk_finish_conv_f16 (convs) finish the layer */
   float* partial;
 } ofb_conv_desc;
 int ofb_conv_f32(const ofb_conv_desc* d, void* stream);
@@ -194,6 +195,14 @@ int ofb_layernorm_f32(const void* x, const float* gamma, const float* beta, int 
 int ofb_splitk_finish_ln_f32(const float* partial, int ksplit, float wscale, const float* bias,
                              const void* residual, int rows, int dim, void* x_out, const float* gamma,
                              const float* beta, float eps, void* ln_out, int ln_fmt, void* stream);
+
+/* Finish of a split-K conv layer (torchvision BasicBlock convs of layer4, spherical_model_iterative.py:328 via
+ * resnet.layer4): out = act((sum_s partial[s]) * (scale * wscale) + shift + residual), partial (ksplit, pixels, cout)
+ * float32 in slice order, residual / out split-half planes of (pixels, cout), act NONE or RELU.  The engine uses it
+ * for the 512 -> 512 convs when a chunk holds at most nine panoramas (option "conv_splitk"). */
+int ofb_splitk_finish_conv_f16(const float* partial, int ksplit, long long pixels, int cout, const float* scale,
+                               const float* shift, float wscale, const void* residual_planes, int act, void* out_planes,
+                               void* stream);
 
 /* Attention core, model/blocks.py:50-62: q (rows,512), kv (rows,1024) [k | v],
  * rows = B*N, heads of 128; softmax(q k^T / sqrt(128)) v -> out (rows,512). */

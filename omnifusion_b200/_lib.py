@@ -68,6 +68,7 @@ _SIGNATURES = {
     "ofb_attention_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "ofb_attention_qkv_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _P]),
     "ofb_attention_tc_f16": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "ofb_splitk_finish_conv_f16": (_I, [_P, _I, C.c_longlong, _I, _P, _P, C.c_float, _P, _I, _P, _P]),
     "ofb_token_stack_f32": (_I, [_P, _P, _P, C.c_longlong, _P, _I, _I, _I, _I, _P]),
     "ofb_token_stack_scratch_floats": (C.c_longlong, [_I, _I]),
     "ofb_token_stack_resident_groups": (_I, [_I]),

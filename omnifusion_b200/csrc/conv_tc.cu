@@ -322,8 +322,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       const int grp = mt / tiles_per_group, trem = mt - grp * tiles_per_group;
       const int ty = trem / p.tiles_x, tx_ = trem - ty * p.tiles_x;
       const int img0 = grp * p.BNI, y0 = ty * p.BH, x0 = tx_ * p.BW, n0 = nt * BN;
-      // split-K exists for single-tap layers only: the slice is a range of channel chunks
-      const int cq_begin = p.ksplit > 1 ? sp * ksteps : 0, cq_end = p.ksplit > 1 ? cq_begin + ksteps : cchunks;
+      // split-K: the slice is a range of channel chunks (of every tap)
+      const int cps = cchunks / p.ksplit;
+      const int cq_begin = sp * cps, cq_end = cq_begin + cps;
       int kh = 0, kw = 0;
       for (int tap = 0; tap < ntap; ++tap) {
         // KHR: `tap` is kw; the box carries rows y0-1 .. y0+BH, the weights all three kh
@@ -1151,8 +1152,8 @@ static int tc_prepare(const ofb_conv_desc* d, TcPlan& plan) {
   p.dbg_buf = (tc_opts().dbg & (16 | 256 | 2048)) ? conv_tc_debug_buffer() : nullptr;
   p.group64 = tc_opts().cta2 ? 1 : 0;
   const int S = d->ksplit > 1 ? d->ksplit : 1;
-  OFB_CHECK(S == 1 || (split && d->k == 1 && d->stride == 1 && !d->ups2x && d->partial && (cin / kc) % S == 0),
-            "conv_tc: split-K needs a split-half 1x1 layer, a partial buffer and %d K-chunks divisible by %d", cin / kc, S);
+  OFB_CHECK(S == 1 || (split && (d->k == 1 || (d->k == 3 && d->cout > 64)) && d->stride == 1 && !d->ups2x && d->partial && (cin / kc) % S == 0),
+            "conv_tc: split-K needs a split-half 1x1 layer (or a 3x3 one with cout > 64), a partial buffer and %d K-chunks divisible by %d", cin / kc, S);
   p.ksplit = S; p.partial = d->partial; p.m_total = (long long)d->n * oh * ow;
   const int groups = (d->n + p.BNI - 1) / p.BNI;
   // kh-reuse tiling for the narrow 3x3 layers: 32x4 / 16x8 pixel tiles inside one image.  Decided from the
@@ -1173,8 +1174,9 @@ static int tc_prepare(const ofb_conv_desc* d, TcPlan& plan) {
   p.tiles_n = d->cout / bn;
   p.total_tiles = groups_k * p.tiles_x * p.tiles_y * p.tiles_n * S;
   // CTA pairs (cta_group::2): two adjacent M tiles share one weight tile.  Decided from the layer shape only.
-  const bool cta2 = tc_opts().cta2 && split && bn == 128 && !khr && row_bytes == 128 && S == 1;
-  if (cta2) p.total_tiles = ((groups_k * p.tiles_x * p.tiles_y + 1) / 2) * p.tiles_n;
+  // (split-K 3x3 layers keep the pair kernel; the split-K linears keep the single-CTA tiles they were tuned with)
+  const bool cta2 = tc_opts().cta2 && split && bn == 128 && !khr && row_bytes == 128 && (S == 1 || d->k == 3);
+  if (cta2) p.total_tiles = ((groups_k * p.tiles_x * p.tiles_y + 1) / 2) * p.tiles_n * S;
 
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));

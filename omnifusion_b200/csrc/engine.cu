@@ -99,6 +99,9 @@ struct ofb_handle {
   int splitk = 4;                  // K slices of the two 512-wide token linears on the tcgen05 engine (1 = off)
   int heads_tc = 1;                // run the heads on the tensor pipe (split-half format, 128-pixel rows)
   int attn_tc = 1;                 // attention core on the tensor pipe (split-half format; tcgen05 QK^T and PV)
+  int conv_splitk = 0;             // 2-way split-K + finish kernel for layer4's 512 -> 512 convs in latency mode (see Ctx).
+                                   // Off: measured neutral at 8 panoramas per step (the conv goes from 36 to 30 us per
+                                   // launch, the finish kernel takes the difference; same-box A/B 1917 / 1924 vs 1921 / 1905)
   int token_fused = 1;             // the whole transformer stack as one launch, 16 CTAs per panorama (token_tc.cu):
                                    // 0 never, 1 when all panoramas of a chunk are resident at once, 2 whenever supported
   TokStack tok_stack{};            // its kernel argument (weight tensor maps + epilogue constants), built by load_weights
@@ -389,7 +392,7 @@ struct Plan {
 struct Buffers {
   float *patches, *conv1, *pool, *l1t, *l1a, *l1b, *layer1_pre, *layer1;
   float *l2t, *l2a, *l2b, *l2d, *layer2, *l3t, *l3a, *l3b, *l3d, *layer3, *l4t, *l4a, *l4b, *l4d, *layer4;
-  float *down, *tok, *ln, *q, *kv, *att, *tok2, *fc1, *enc, *part, *tokx;
+  float *down, *tok, *ln, *q, *kv, *att, *tok2, *fc1, *enc, *part, *tokx, *cpart;
   float *up0, *d00, *d01, *up1, *d10, *d11, *up2, *d20, *d21, *up3, *d30, *d31, *up4, *d40;
   float *pred, *conf, *depth_p;
 };
@@ -410,6 +413,7 @@ static size_t plan_buffers(ofb_handle* h, int imgs, int P, Buffers* b) {
   b->kv = pl.take(I * 1536); b->att = pl.take(I * 512); b->tok2 = pl.take(I * 512); b->fc1 = pl.take(I * 2048);
   b->enc = pl.take(I * 512);
   b->part = pl.take(I * 512 * 4);                  // split-K partial sums of attn.proj / mlp.fc2 (4 slices)
+  b->cpart = pl.take(2 * s4);                      // partial sums of layer4's split-K convs (2 slices)
   b->tokx = pl.take(I * (512 * 17 + 16 * 48));     // exchange buffers of the fused transformer stack (token_stack_scratch_floats, N <= 48)
   b->up0 = pl.take(I * p16 * p16 * 512); b->d00 = pl.take(I * p16 * p16 * 256); b->d01 = pl.take(I * p16 * p16 * 128);
   b->up1 = pl.take(I * p8 * p8 * 128); b->d10 = pl.take(I * p8 * p8 * 128); b->d11 = pl.take(I * p8 * p8 * 64);
@@ -440,7 +444,9 @@ static int ensure_workspace(ofb_handle* h, int imgs, int P, Buffers* b) {
 }
 
 // ----------------------------------------------------------------- schedule
-struct Ctx { ofb_handle* h; cudaStream_t s; int imgs; };
+struct Ctx { ofb_handle* h; cudaStream_t s; int imgs; bool latency = false; float* cpart = nullptr; };
+// latency: the chunk holds so few panoramas (<= 9) that the small layers cannot fill the GPU - the forward then uses
+// the fused transformer stack and 2-way split-K for layer4's 512 -> 512 convs (cpart = their partial-sum buffer)
 
 // Brackets one launch with CUDA events on the launch stream when profiling is on.
 struct Prof {
@@ -517,6 +523,26 @@ static int run_linear(Ctx& c, const ConvW& w, const float* in, const float* resi
   return conv_dispatch(&d, c.s);
 }
 
+// One conv of a residual stage.  In latency mode a 3x3 stride-1 conv with K >= 4608 and few pixels (layer4: 18 M tiles
+// at 8 panoramas) runs 2-way split-K: every CTA then fetches half of the activations and weights, which is what
+// bounds these launches (L2 -> SM at the slice cap), and a finish kernel applies BN / residual / ReLU.
+static int run_stage_conv(Ctx& c, ofb_conv_desc d) {
+  double f, b_;
+  conv_work(d, &f, &b_);
+  const bool sk = c.latency && c.cpart && c.h->conv_splitk && c.h->fmt == OFB_FMT_SPLIT16 && c.h->engine != OFB_ENGINE_SIMT &&
+                  d.k == 3 && d.stride == 1 && !d.in1 && !d.ups2x && d.cout >= 256 && 9 * d.c0 >= 4608 && d.h * d.w <= 16;
+  if (!sk) {
+    Prof pr(c.h, c.s, conv_class(d), f, b_);
+    return conv_dispatch(&d, c.s);
+  }
+  d.ksplit = 2; d.partial = c.cpart;
+  { Prof pr(c.h, c.s, conv_class(d) + "_splitk2", f, b_);
+    if (conv_dispatch(&d, c.s)) return -1; }
+  const long long pixels = (long long)d.n * d.h * d.w;
+  Prof pr(c.h, c.s, "splitk_finish_conv", 0.0, 4.0 * pixels * d.cout * (2 + 1 + (d.residual ? 1 : 0)));
+  return ofb_splitk_finish_conv_f16(c.cpart, 2, pixels, d.cout, d.scale, d.shift, d.wgt_unscale, d.residual, d.act, d.out, (void*)c.s);
+}
+
 // torchvision BasicBlock stack: relu(bn2(conv2(relu(bn1(conv1 x)))) + identity/downsample)
 static int run_res_layer(Ctx& c, int l, const float* in, int cin, int hin, float* tmp, float* pa, float* pb,
                          float* ds, float* out_final) {
@@ -566,12 +592,8 @@ static int run_res_layer(Ctx& c, int l, const float* in, int cin, int hin, float
       if (rc == 0) return 0;
       // not chainable for this shape: the launches above are exactly the loop's first two; continue it from conv2
       if (c.h->profile) { cudaEventDestroy(c.h->recs.back().e0); cudaEventDestroy(c.h->recs.back().e1); c.h->recs.pop_back(); }
-      for (auto& d : ds_) {
-        double f, b_;
-        conv_work(d, &f, &b_);
-        Prof pr(c.h, c.s, conv_class(d), f, b_);
-        if (conv_dispatch(&d, c.s)) return -1;
-      }
+      for (auto& d : ds_)
+        if (run_stage_conv(c, d)) return -1;
       return 0;
     }
   }
@@ -579,14 +601,14 @@ static int run_res_layer(Ctx& c, int l, const float* in, int cin, int hin, float
     std::string p = "layer" + std::to_string(l + 1) + "." + std::to_string(b);
     int st = b == 0 ? stride : 1;
     float* y = (b == nb - 1) ? out_final : ((b & 1) ? pb : pa);
-    if (run_conv(c, c.h->conv[p + ".conv1"], x, xc, nullptr, 0, xh, xh, st, 1, nullptr, OFB_ACT_RELU, tmp)) return -1;
+    if (run_stage_conv(c, conv_desc(c, c.h->conv[p + ".conv1"], x, xc, nullptr, 0, xh, xh, st, 1, nullptr, OFB_ACT_RELU, tmp))) return -1;
     const float* idn = x;
     auto it = c.h->conv.find(p + ".ds");
     if (it != c.h->conv.end()) {
       if (run_conv(c, it->second, x, xc, nullptr, 0, xh, xh, st, 0, nullptr, OFB_ACT_NONE, ds)) return -1;
       idn = ds;
     }
-    if (run_conv(c, c.h->conv[p + ".conv2"], tmp, ch, nullptr, 0, hout, hout, 1, 1, idn, OFB_ACT_RELU, y)) return -1;
+    if (run_stage_conv(c, conv_desc(c, c.h->conv[p + ".conv2"], tmp, ch, nullptr, 0, hout, hout, 1, 1, idn, OFB_ACT_RELU, y))) return -1;
     x = y; xc = ch; xh = hout;
   }
   return 0;
@@ -605,6 +627,9 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
   Buffers b;
   if (ensure_workspace(h, imgs, P, &b)) return -1;
   Ctx c{h, s, imgs};
+  if (h->tok_groups < 0) h->tok_groups = token_stack_resident_groups(N <= 32 ? 18 : 46);
+  c.latency = Bc <= h->tok_groups;       // few panoramas per chunk: fused transformer stack, split-K layer4 (see Ctx)
+  c.cpart = b.cpart;
   void* vs = (void*)s;
   const int F = h->fmt;
   bool pairs = false;          // head outputs of the last iteration are an interleaved pair map
@@ -669,8 +694,7 @@ static int forward_chunk(ofb_handle* h, const float* rgb, int Bc, int iters, int
       // 48-token instantiation has a two-stage ring: measured slower than the per-layer path there (32 panoramas:
       // 1.42 vs 0.84 ms per step; 16 x 46 tokens: 1.86 vs 1.43 ms), faster below (8 x 18: 0.35 vs 0.53 ms, 1 x 18:
       // -0.14 ms, 8 x 26: -0.13 ms).  Option token_fused = 2 forces it.
-      if (h->tok_groups < 0) h->tok_groups = token_stack_resident_groups(N);
-      fused_tokens = N <= 32 && Bc <= h->tok_groups;
+      fused_tokens = N <= 32 && c.latency;
     }
     fused_tokens = fused_tokens && Bc <= kTokMaxPanos;
     { Prof pr(h, s, "token_pack", 0.0, 4.0*((double)imgs*1024));
@@ -935,6 +959,7 @@ extern "C" int ofb_set_option(ofb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "heads_tc")) h->heads_tc = value;
   else if (!strcmp(key, "attn_tc")) h->attn_tc = value;
   else if (!strcmp(key, "token_fused")) h->token_fused = value;
+  else if (!strcmp(key, "conv_splitk")) h->conv_splitk = value;
   else if (!strcmp(key, "check_range")) h->check_range = value;
   else if (!strcmp(key, "chain")) h->chain = value;
   else if (!strcmp(key, "no_point_feat")) h->no_point_feat = value != 0;

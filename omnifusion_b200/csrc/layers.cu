@@ -772,6 +772,71 @@ extern "C" int ofb_layernorm_f32(const void* x, const float* gamma, const float*
   return 0;
 }
 
+// ------------------------------------------------------ split-K finish of a conv layer
+// layer4's 512 -> 512 convs at 4x4 pixels per patch have K = 4608 and, at a few panoramas per step, only 18 M tiles:
+// they run 2-way split-K on the tcgen05 engine (halves the operand traffic per CTA, which is what bounds them) and
+// this kernel finishes them: sum of the partial sums in slice order, BN scale / shift (same expression as the conv
+// epilogue), residual, ReLU, split-half store.  8 channels per thread.
+__global__ void splitk_conv_finish_kernel(const float* __restrict__ partial, int ksplit, size_t m_total, int cout,
+                                          const float* __restrict__ scale, const float* __restrict__ shift, float wscale,
+                                          const __half* __restrict__ residual, size_t plane, int act,
+                                          __half* __restrict__ out) {
+  const size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 8;
+  if (i >= m_total * cout) return;
+  const int c = (int)(i % cout);
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = 0.f;
+  for (int s = 0; s < ksplit; ++s) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(partial + s * m_total * cout + i));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(partial + s * m_total * cout + i + 4));
+    f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = f[j] * ((scale ? __ldg(scale + c + j) : 1.f) * wscale) + (shift ? __ldg(shift + c + j) : 0.f);
+  if (residual) {
+    const uint4 rh = __ldg(reinterpret_cast<const uint4*>(residual + i));
+    const uint4 rl = __ldg(reinterpret_cast<const uint4*>(residual + plane + i));
+    const __half2* ah = reinterpret_cast<const __half2*>(&rh);
+    const __half2* bh = reinterpret_cast<const __half2*>(&rl);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 x = __half22float2(ah[t]), y = __half22float2(bh[t]);
+      f[2 * t] += x.x + y.x;
+      f[2 * t + 1] += x.y + y.y;
+    }
+  }
+  if (act == OFB_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+  }
+  uint4 hi4, lo4;
+  __half2* hh = reinterpret_cast<__half2*>(&hi4);
+  __half2* ll = reinterpret_cast<__half2*>(&lo4);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const __half2 h = __floats2half2_rn(f[2 * t], f[2 * t + 1]);
+    const float2 hf = __half22float2(h);
+    hh[t] = h;
+    ll[t] = __floats2half2_rn(f[2 * t] - hf.x, f[2 * t + 1] - hf.y);
+  }
+  *reinterpret_cast<uint4*>(out + i) = hi4;
+  *reinterpret_cast<uint4*>(out + plane + i) = lo4;
+}
+
+extern "C" int ofb_splitk_finish_conv_f16(const float* partial, int ksplit, long long pixels, int cout, const float* scale,
+                                          const float* shift, float wscale, const void* residual_planes, int act,
+                                          void* out_planes, void* stream) {
+  OFB_CHECK(partial && out_planes && ksplit >= 1 && pixels > 0 && cout > 0 && cout % 8 == 0, "splitk_finish_conv: bad arguments");
+  OFB_CHECK(act == OFB_ACT_NONE || act == OFB_ACT_RELU, "splitk_finish_conv: activation %d is not supported", act);
+  const size_t n = (size_t)pixels * cout;
+  const int blocks = cdiv((long long)(n / 8), 256);
+  splitk_conv_finish_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(partial, ksplit, (size_t)pixels, cout, scale, shift, wscale,
+      reinterpret_cast<const __half*>(residual_planes), n, act, reinterpret_cast<__half*>(out_planes));
+  OFB_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int ofb_splitk_finish_ln_f32(const float* partial, int ksplit, float wscale, const float* bias,
                                         const void* residual, int rows, int dim, void* x_out, const float* gamma,
                                         const float* beta, float eps, void* ln_out, int ln_fmt, void* stream) {

@@ -290,6 +290,37 @@ def test_splitk_linear_and_finish_layernorm(rows, cin, ksplit):
         assert ex <= 2e-5 and el <= 5e-5
 
 
+@pytest.mark.parametrize("n,cin,cout,hw", [(144, 512, 512, 4), (18, 512, 512, 4), (36, 256, 256, 8)])
+def test_splitk_conv3x3_and_finish(n, cin, cout, hw):
+    """layer4's 512 -> 512 BasicBlock convs (torchvision resnet34 via spherical_model_iterative.py:328) as a 2-way
+    split-K 3x3 conv on the tcgen05 engine (CTA-pair kernel, each slice = half of the channel chunks of every tap) +
+    ofb_splitk_finish_conv_f16 (BN scale / shift, residual, ReLU, split-half store), against torch-CPU fp32."""
+    o = ops()
+    x = rand(n, hw, hw, cin, seed=71)
+    w = rand(cout, 3, 3, cin, seed=72, scale=(1.0 / (9 * cin)) ** 0.5)
+    scale = 0.5 + torch.rand(cout, generator=torch.Generator().manual_seed(73))
+    shift, res = rand(cout, seed=74, scale=0.1), rand(n, hw, hw, cout, seed=75)
+    want = F.relu(F.conv2d(x.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), padding=1) * scale.view(1, -1, 1, 1)
+                  + shift.view(1, -1, 1, 1) + res.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+    part, unscale = o.conv_fmt(x.to(DEV), w.to(DEV), 3, 1, 1, engine=_lib.ENGINE_TC, in_fmt=_lib.FMT_SPLIT16,
+                               out_fmt=_lib.FMT_SPLIT16, ksplit=2)
+    variant = o.last_conv_variant()
+    resd, sc_d, sh_d = o.split16(res.to(DEV)), scale.to(DEV), shift.to(DEV)
+    out = torch.full((2 * n * hw * hw * cout,), float("nan"), dtype=torch.float16, device=DEV)
+    _lib.check(_lib.lib().ofb_splitk_finish_conv_f16(_lib.ptr(part), 2, n * hw * hw, cout, _lib.ptr(sc_d), _lib.ptr(sh_d),
+                                                      unscale, _lib.ptr(resd), 1, _lib.ptr(out),
+                                                      _lib.stream_of(torch.device(DEV))))
+    torch.cuda.synchronize()
+    got = o.merge16(out, (n, hw, hw, cout)).cpu()
+    err = (got - want).abs()
+    print(f"[parity] split-K conv3x3 n={n} {cin}->{cout} @{hw}x{hw} variant={variant}: max_abs_err={err.max().item():.3e} "
+          f"ref_absmax={want.abs().max().item():.3e}")
+    assert torch.isfinite(got).all()
+    assert (err <= 1.5e-4 + 5e-5 * want.abs()).all()
+    # the two slices really are halves of K: each partial sum alone differs from the total
+    assert (part[0] - part[1]).abs().max().item() > 0
+
+
 @pytest.mark.parametrize("B,n_tok", [(8, 18), (3, 18), (16, 46), (5, 26), (13, 10), (1, 64)])
 def test_attention_on_tensor_cores_matches_torch_cpu(B, n_tok):
     """Attention core of model/blocks.py:50-62 on tcgen05 (ofb_attention_tc_f16): one CTA per head and tile of

@@ -298,13 +298,17 @@ def test_fused_transformer_stack_against_per_layer_path(nrows, bs):
             a = [t.clone() for t in net(rgb, iter=2, confidence=True)]
             net.set_option("token_fused", 0)
             b = [t.clone() for t in net(rgb, iter=2, confidence=True)]
+            # option conv_splitk: layer4's 512 -> 512 convs as 2-way split-K + finish kernel (off by default)
+            net.set_option("conv_splitk", 1)
+            c = [t.clone() for t in net(rgb, iter=2, confidence=True)]
     finally:
         net.set_option("token_fused", 1)
-    for x, y in zip(a, b):
-        assert torch.isfinite(x).all()
-        e = max_rel(x.cpu(), y.cpu())
-        print(f"[parity] fused vs per-layer transformer, nrows={nrows} bs={bs}: depth max rel {e:.2e}")
-        assert e <= 2e-5
+        net.set_option("conv_splitk", 0)
+    for x, y, z in zip(a, b, c):
+        assert torch.isfinite(x).all() and torch.isfinite(z).all()
+        e, e2 = max_rel(x.cpu(), y.cpu()), max_rel(z.cpu(), y.cpu())
+        print(f"[parity] fused vs per-layer transformer, nrows={nrows} bs={bs}: depth max rel {e:.2e}; split-K layer4: {e2:.2e}")
+        assert e <= 2e-5 and e2 <= 2e-5
 
 
 def test_module_prefix_checkpoint_and_errors():
