@@ -277,6 +277,20 @@ int ofb_median_scale_f32(const float* pred, const float* gt, const uint8_t* mask
 int ofb_depth_to_points_f32(const float* depth, const float* rays, int B, int He, int We, float max_depth,
                             float* pts, void* stream);
 
+/* Training-side losses (supervision/direct.py:3-27; train_erp_depth_iterative.py:271): mode 1 = reverse Huber
+ * (BerHu) loss calculate_berhu_loss(pred, gt, mask, weights), mode 0 = calculate_l1_loss(pred, gt, mask) (weights
+ * NULL).  pred / gt / mask / weights: bs x per_sample float32 (mask as mask.float()).  c = max|gt - pred| / 5 over the
+ * whole UNMASKED batch (a constant for the gradient), loss = mean_b(sum(loss * mask * weights)_b / sum(mask)_b);
+ * degenerate inputs give NaN exactly where the reference does (c == 0, a sample without valid pixels).
+ * work: ofb_loss_work_bytes(bs) bytes of device scratch; stats: 1 + bs floats (c, per-sample counts) kept for
+ * ofb_depth_loss_backward_f32, which writes d loss / d pred * (*grad_out) into grad_pred. */
+long long ofb_loss_work_bytes(int bs);
+int ofb_depth_loss_f32(const float* pred, const float* gt, const float* mask, const float* weights, int bs,
+                       long long per_sample, int mode, void* work, float* stats, float* loss, void* stream);
+int ofb_depth_loss_backward_f32(const float* pred, const float* gt, const float* mask, const float* weights, int bs,
+                                long long per_sample, int mode, const float* stats, const float* grad_out,
+                                float* grad_pred, void* stream);
+
 /* Abs-Rel partial sums, metrics.py:7-9: out[0] += sum(|p*scale-g|/g over mask), out[1] += count.
  * `out` must be zeroed by the caller. */
 int ofb_absrel_partial(const float* pred, const float* gt, const uint8_t* mask, size_t n,

@@ -76,6 +76,9 @@ _SIGNATURES = {
     "ofb_heads_tc_f16": (_I, [_P, _I, _I, _I, _P, C.c_float, C.c_float, C.c_float, _I, _P, _P, _P]),
     "ofb_heads_f32": (_I, [_P, _I, _I, _I, _P, C.c_float, _P, C.c_float, _I, _P, _P, _I, _P]),
     "ofb_u8hwc_to_f32chw": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "ofb_loss_work_bytes": (C.c_longlong, [_I]),
+    "ofb_depth_loss_f32": (_I, [_P, _P, _P, _P, _I, C.c_longlong, _I, _P, _P, _P, _P]),
+    "ofb_depth_loss_backward_f32": (_I, [_P, _P, _P, _P, _I, C.c_longlong, _I, _P, _P, _P, _P]),
     "ofb_absrel_partial": (_I, [_P, _P, _P, C.c_size_t, C.c_float, _P, _P]),
     "ofb_depth_metrics_partial": (_I, [_P, _P, _P, C.c_size_t, C.c_float, _P, _P]),
     "ofb_depth_metrics_partial_ds": (_I, [_P, _P, _P, C.c_size_t, _P, _P, _P]),
