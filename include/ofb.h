@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OFB_VERSION 102
+#define OFB_VERSION 103
 
 typedef struct ofb_handle ofb_handle;
 

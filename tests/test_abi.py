@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(handle, s), f"{s} declared in include/ofb.h but not exported"
     assert sorted(_lib._SIGNATURES) == syms, "python binding and header disagree on the symbol set"
-    assert _lib.lib().ofb_version() == 102
+    assert _lib.lib().ofb_version() == 103
 
 
 def test_errors_are_reported_not_swallowed():
