@@ -39,6 +39,15 @@ def test_errors_are_reported_not_swallowed():
         _lib.check(L.ofb_layernorm_f32(None, None, None, 1, 512, 1e-5, None, 0, 0, None))
     with pytest.raises(_lib.OfbError):
         _lib.require_cuda(torch.zeros(1, 3, 8, 16), "x")          # no CPU fallback
+    # the newer entry points validate before they touch the device too
+    assert L.ofb_depth_loss_f32(None, None, None, None, 2, 16, 1, None, None, None, None) < 0
+    assert L.ofb_token_stack_f32(None, None, None, 0, None, 1, 18, 6, 0, None) < 0
+    assert L.ofb_splitk_finish_conv_f16(None, 2, 16, 512, None, None, 1.0, None, 1, None, None) < 0
+    assert L.ofb_loss_work_bytes(4) >= 16 and L.ofb_token_stack_scratch_floats(8, 18) > 8 * 18 * 512 * 17
+    from omnifusion_b200.supervision import direct
+    x = torch.zeros(2, 1, 4, 8)
+    with pytest.raises(_lib.OfbError):
+        direct.calculate_berhu_loss(x, x, x > 0, x)                # CPU tensors: the losses have no CPU path either
 
 
 def test_product_never_imports_the_oracle():
