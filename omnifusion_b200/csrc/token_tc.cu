@@ -2,11 +2,10 @@
 // tokens of a panorama, width 512, 4 heads of 128, MLP 2048; spherical_model_iterative.py:330-335) as ONE launch.
 //
 // Attention only mixes the tokens of one panorama, so a panorama is a closed problem: a GROUP OF 16 CTAs per
-// panorama (consecutive block indices, all resident: 9 groups fit the 148 SMs) walks all blocks without any grid-wide
-// synchronisation.  The work of a block is 3.1 M weights against
-// 18-46 tokens: it is bound by streaming the weights out of L2, so every CTA of the cluster streams 1/16 of them
-// through its own TMA ring, and the GEMMs run "swapped": the WEIGHT rows are the M = 128 dimension of a tcgen05
-// MMA, the tokens (padded to NP = 32 or 48) its N dimension.
+// panorama (consecutive block indices; 9 groups are resident on 148 SMs) walks all blocks without any grid-wide
+// synchronisation.  The work of a block is 3.1 M weights against 18-46 tokens: it is bound by streaming the weights
+// out of L2, so every CTA of the group streams 1/16 of them through its own TMA ring, and the GEMMs run "swapped":
+// the WEIGHT rows are the M = 128 dimension of a tcgen05 MMA, the tokens (padded to NP = 32 or 48) its N dimension.
 //
 //   CTA r = (head h = r / 4, quarter qd = r % 4) of its group
 //   phase 0  q|k|v rows of dims [32 qd, 32 qd + 32) of head h   (3 x 32 weight rows, K = 512)  -> partial scores over
@@ -25,11 +24,11 @@
 // per CTA adds to the panorama's arrival counter (red.release.gpu) and polls it (ld.acquire.gpu), readers use
 // ld.global.cg.  (A hardware cluster of 16 with remote mbarrier arrives works too, but B200 keeps only 7 such
 // clusters resident: 8 panoramas took two waves.)  A group that is only partly resident spins until the earlier
-// groups retire - block dispatch is in index order, the scheme of every decoupled look-back scan.  Five exchanges per block; a LayerNorm is computed redundantly by every CTA from the
-// exchanged fp32 residual stream while it builds its B operand.  The weight stream does not depend on any of this:
-// a producer warp runs ahead through the whole stack (it starts before the previous kernel has finished), so
-// the ring is full whenever a phase starts.  Results do not depend on the batch size or position (one group per
-// panorama, fixed summation orders).
+// groups retire - block dispatch is in index order, the scheme of every decoupled look-back scan.  Five exchanges
+// per block; a LayerNorm is computed redundantly by every CTA from the exchanged fp32 residual stream while it
+// builds its B operand.  The weight stream does not depend on any of this: a producer warp runs ahead through the
+// whole stack (it starts before the previous kernel has finished), so the ring is full whenever a phase starts.
+// Results do not depend on the batch size or position (one group per panorama, fixed summation orders).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
