@@ -496,6 +496,14 @@ def main():
                             "executed tensor work = 3 x achieved; ceiling of this design = peak / 3",
                     "all_conv_launches": {"achieved": conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None,
                                           "share_of_step": conv_ms / total_ms}}
+        # `achieved` divides by event-bracketed EAGER launches (launch latency and the event pair inside every
+        # interval, no overlap between consecutive launches).  The timed region itself is a CUDA-graph replay with
+        # programmatic dependent launches: the class's share of that step gives the duration it has there.
+        graph_step_ms = ms / K
+        in_graph = (w_fl / 2) / (roofline["share_of_step"] * graph_step_ms * 1e-3) / 1e12
+        roofline["in_graph_replay"] = {
+            "achieved": in_graph, "frac": in_graph / pk["tensor"],
+            "how": "algorithmic FLOPs of the class per step / (share_of_step x ms_per_step of the graph replay)"}
     top = sorted(prof_rows, key=lambda r: -r["ms"])
     value = world * B * K / (ms * 1e-3)
     e2e_value = world * B * K / (e2e_ms * 1e-3)
