@@ -474,7 +474,7 @@ def main():
         w_ms, w_fl, w_n = sum(r["ms"] for r in wide), sum(r["flops"] for r in wide), sum(r["launches"] for r in wide)
         achieved = w_fl / (w_ms * 1e-3) / 1e12
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r02_v27_ncu_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r02_v35_ncu_traffic.json")
         if os.path.exists(tpath):
             t = json.load(open(tpath))
             k = t["kernels"].get("conv_tc_kernel<128, 1, 128, 1, 0, 0, 0, 1>")
