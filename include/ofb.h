@@ -345,7 +345,8 @@ long long ofb_workspace_generation(ofb_handle* h);
  * activation storage (OFB_FMT_*), "fuse_ups" fold the last decoder upsample into de_conv4_0 (default 1),
  * "check_range" see ofb_range_report, "chain" image-stationary layer chains: 0 off, 1 (default) for the encoder stages whose
  * dependencies stay inside a CTA pair (layer2), 2 also stages that hand images over between clusters (layer3), "heads_tc" heads on the tensor pipe (default 1), "attn_tc" attention core on the tensor pipe (default 1), "lanes" 2 = two concurrent half-batches on two streams
- * (default 1), "cta2" / "pdl" / "store128" / "fill_div" / "direct32" / "khr_bw" / "khr_row64" / "nstack" (tap-stacked MMAs of the
+ * (default 1), "cta2" / "pdl" / "store128" / "fill_div" / "direct32" / "khr_bw" / "khr_row64" / "wmc" (weight multicast between the two CTAs of a cluster in
+ * the kh-reuse kernels, off) / "nstack" (tap-stacked MMAs of the
  * rolling-row kernels: 1 = heads (default), 2 = also the fused-upsample conv) tcgen05 launch variants (per handle);
  * "tc_debug" / "dbg_blocks" switch parts of the pipeline OFF for timing experiments (results are wrong). */
 int ofb_set_option(ofb_handle* h, const char* key, int value);

@@ -51,6 +51,9 @@ struct TcOptions {
   bool cta2 = true;       // cta_group::2 CTA pairs for the 128-wide split-half tiles
   bool direct32 = false;  // BN = 32 split-half tiles store straight from registers
   bool khr_row64 = false; // 64-byte K rows for the Cout = 64 kh-reuse layers
+  bool wmc = false;       // kh-reuse kernels: clusters of two CTAs share each stage's weight loads by TMA multicast
+                          // (measured: the weight share of the L2 -> SM traffic - 37 % for 128 -> 32 @64x64 - is halved,
+                          // the launch times do not move: these layers are bound by MMA issue, not by L2)
   bool nstack = true;     // heads kernel: input-row-stationary MMAs with the three kh taps stacked along N
   bool nstack_ups = false;// the same for the fused-upsample conv (measured slower: experiments only)
   int fill_div = 2;       // shrink the N tile while fewer than num_sms / fill_div tiles exist

@@ -56,6 +56,8 @@ struct TcParams {
                          // 7 kernel end
   int group64;           // accumulate the three split-half products in the cta_group::2 column grouping (see the MMA warp)
   int nstack;            // UPS kernels: input-row-stationary MMAs with the three kh taps stacked along N (see the MMA warp)
+  int wmc;               // kh-reuse kernels (weights in the ring): launched as clusters of two CTAs that walk their tiles
+                         // in lockstep; each loads HALF of a stage's weight box and multicasts it to both
 };
 
 __device__ __forceinline__ float act_fn(float v, int act) {
@@ -185,6 +187,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   // UPS: the CTA owns the contiguous output rows [ups_r0, ups_r1) (global row index = image * H + y)
   const int ups_per = UPS ? (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int ups_r0 = UPS ? min((int)blockIdx.x * ups_per, p.total_tiles) : 0, ups_r1 = UPS ? min(ups_r0 + ups_per, p.total_tiles) : 0;
+  // weight multicast (p.wmc): the two CTAs of a cluster run the same number of (tile, K-step) ring steps - a CTA whose
+  // last tile does not exist repeats the layer's last tile (the same values are stored twice)
+  const bool wmc = KHR && !BRES && !UPS && !CTA2 && p.wmc != 0;
+  const uint32_t wrank = wmc ? uniform(cluster_ctarank()) : 0u;
+  const int iter_first = wmc ? (tile0 & ~1) : tile0;
+  const int n_iter = UPS || iter_first >= p.total_tiles ? 0 : (p.total_tiles - iter_first + tile_step - 1) / tile_step;
   const int cin = p.c0 + p.c1;
   const int cchunks = cin / Cfg::KC;
   const int ksteps = ((KHR ? 3 : p.taps) * cchunks) / p.ksplit;      // K-steps of one tile (of one split)
@@ -199,7 +207,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < Cfg::NST; ++i) {
       mbar_init(bars + 8 * i, UPS == 1 ? Cfg::UPS_WARPS : 1);     // full: the TMA thread, or one arrival per producer warp
-      mbar_init(bars + 8 * (Cfg::NST + i), 1);
+      mbar_init(bars + 8 * (Cfg::NST + i), wmc ? 2 : 1);          // (weight multicast: freed by both CTAs' MMAs)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
@@ -231,7 +239,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (CTA2) cluster_sync_all();          // the peer's barriers are initialised before anything signals them
+  if (CTA2 || wmc) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem = uniform(*tmem_slot);
   const uint32_t tl_slot = tl_on ? uniform(tmem_slot[1]) : 0u;
@@ -301,7 +309,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       const uint32_t full = bars + 8 * stg;
       const uint32_t sb = base + stg * Cfg::STAGE + Cfg::PLANES * Cfg::A_BYTES;
       if (CTA2) { if (rank == 0) mbar_expect_tx(full, 2 * tx); } else mbar_expect_tx(full, tx);
-      if (KHR) {
+      if (KHR && wmc) {
+        // the stage's weights = [kh][Whi rows ; Wlo rows] = six half boxes {kc, BN rows, one kh}: this CTA fetches
+        // three of them and writes each into BOTH CTAs' stage (their bytes count on both full barriers)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int hb = (int)wrank * 3 + j, kh = hb >> 1, half = hb & 1;
+          tma_load_4d_mc(sb + (uint32_t)((kh * 2 + half) * BN * ROW_BYTES), &maps.b[1], full, cq * Cfg::KC, half * BN, kh, tap, (uint16_t)3);
+        }
+      } else if (KHR) {
         // one box = {kc, stacked [Whi; Wlo] rows, all 3 kh, this kw}
         tma_load_4d(sb, &maps.b[0], full, cq * Cfg::KC, 0, 0, tap);
       } else {
@@ -316,7 +332,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       }
     };
     if (tl && lane == 0) tl_buf[2] = globaltimer_ns();
-    for (int t = tile0; !UPS && t < p.total_tiles; t += tile_step) {
+    for (int it = 0; it < n_iter; ++it) {
+      const int t = min(tile0 + it * tile_step, p.total_tiles - 1);
       const int sp = t % p.ksplit, tq = t / p.ksplit;            // split-K slice (ksplit == 1: tq == t)
       const int nt = tq % p.tiles_n, mt = CTA2 ? 2 * (tq / p.tiles_n) + (int)rank : tq / p.tiles_n;
       const int grp = mt / tiles_per_group, trem = mt - grp * tiles_per_group;
@@ -489,7 +506,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           pb += seg_end ? 3 : 1;
         }
       }
-      for (int t = tile0; !UPS && t < p.total_tiles; t += tile_step, ++i) {
+      for (int it = 0; it < n_iter; ++it, ++i) {
+        const int t = min(tile0 + it * tile_step, p.total_tiles - 1);
         const uint32_t buf = i & 1;
         mbar_wait(bar_tempty + 8 * buf, ((i >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
@@ -545,7 +563,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
               }
             }
             // frees this smem stage when the MMAs retire
-            if (CTA2) tc_commit_2sm(bars + 8 * (Cfg::NST + st)); else tc_commit(bars + 8 * (Cfg::NST + st));
+            if (CTA2) tc_commit_2sm(bars + 8 * (Cfg::NST + st));
+            else if (wmc) tc_commit_mc(bars + 8 * (Cfg::NST + st));       // both CTAs' copies of this stage hold the peer's half
+            else tc_commit(bars + 8 * (Cfg::NST + st));
             if (ks == ksteps - 1) {                         // accumulator complete
               if (CTA2) tc_commit_2sm(bar_tfull + 8 * buf); else tc_commit(bar_tfull + 8 * buf);
             }
@@ -578,7 +598,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     // rolling-row kernels: tile = one image row; (image, row) advance incrementally - the general decomposition
     // below costs five integer divisions per tile, which is most of a row's epilogue time there
     int ups_img = UPS ? ups_r0 / p.H : 0, ups_y = UPS ? ups_r0 - ups_img * p.H : 0;
-    for (int t = UPS ? ups_r0 : tile0; t < (UPS ? ups_r1 : p.total_tiles); t += UPS ? 1 : tile_step, ++i) {
+    const int epi_cnt = UPS ? ups_r1 - ups_r0 : n_iter;
+    for (int it = 0; it < epi_cnt; ++it, ++i) {
+      const int t = UPS ? ups_r0 + it : min(tile0 + it * tile_step, p.total_tiles - 1);
       int sp = 0, img0, y0, x0 = 0, n0 = 0;
       if (UPS) {
         img0 = ups_img; y0 = ups_y;
@@ -937,7 +959,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (CTA2) cluster_sync_all();          // the leader's MMAs read the peer's shared memory until the very end
+  if (CTA2 || wmc) cluster_sync_all();   // the leader's MMAs read the peer's shared memory until the very end
   if (tl && threadIdx.x == 32) tl_buf[7] = globaltimer_ns();
   if (warp == 1) {
     tc_fence_after();
@@ -1068,6 +1090,8 @@ static int launch_tc(const TcMaps& maps, const TcParams& p, cudaStream_t s) {
   // persistent: one CTA per SM (CTA2: one CTA pair per TPC, total_tiles counts pair-tiles)
   const int units = (CTA2 ? num_sms() / 2 : num_sms()) / tc_opts().sm_share;
   int grid = (p.total_tiles < units ? p.total_tiles : units) * (CTA2 ? 2 : 1);
+  const bool wmc = KHR && !BRES && !UPS && !CTA2 && p.wmc;
+  if (wmc) grid &= ~1;                        // clusters of two
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;
   cudaLaunchAttribute attrs[2];
@@ -1077,7 +1101,7 @@ static int launch_tc(const TcMaps& maps, const TcParams& p, cudaStream_t s) {
     attrs[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
   }
-  if (CTA2) {
+  if (CTA2 || wmc) {
     attrs[na].id = cudaLaunchAttributeClusterDimension;
     attrs[na].val.clusterDim.x = 2; attrs[na].val.clusterDim.y = 1; attrs[na].val.clusterDim.z = 1;
     ++na;
@@ -1204,6 +1228,8 @@ static int tc_prepare(const ofb_conv_desc* d, TcPlan& plan) {
   // N = 64 / 32 cost (measured with tools/probe_rolling.py: 1630 clk of issue per input row, 172 vs 162 us per launch
   // with the larger TMEM footprint and the block zero fills), for the heads' N = 48 they are cheaper (123 vs 135 us).
   p.nstack = (d->ups2x && tc_opts().nstack && tc_opts().nstack_ups) ? 1 : 0;
+  // weight multicast: kh-reuse layers whose weights travel through the ring (everything but the 32 -> 32 layers)
+  p.wmc = (khr && !d->ups2x && tc_opts().wmc && !(row_bytes == 64 && cin == 32 && d->cout == 32) && p.total_tiles >= 2) ? 1 : 0;
   if (khr && p.nstack) {
     // tap-stacked rolling-row kernel: per plane one map over (cout, kh, kw, cin) seen as dims {cin, cout, kh, kw};
     // one box = {kc, bn rows, all 3 kh, one kw} -> shared memory [kh][bn rows] = the kh slices of a plane stacked
@@ -1220,7 +1246,8 @@ static int tc_prepare(const ofb_conv_desc* d, TcPlan& plan) {
     cuuint64_t bstr[3] = {(cuuint64_t)9 * cin * es, (cuuint64_t)3 * cin * es, (cuuint64_t)cin * es};
     cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(2 * bn), 3u, 1u};
     if (make_map(&maps.b[0], split, 4, (char*)d->wgt_split, dims, box, row_bytes, 1, bstr)) return -1;
-    maps.b[1] = maps.b[0];
+    cuuint32_t hbox[4] = {(cuuint32_t)kc, (cuuint32_t)bn, 1u, 1u};        // half of one kh slice (weight multicast)
+    if (make_map(&maps.b[1], split, 4, (char*)d->wgt_split, dims, hbox, row_bytes, 1, bstr)) return -1;
   } else {
     cuuint64_t dims[2] = {(cuuint64_t)d->k * d->k * cin, (cuuint64_t)d->cout};
     cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)(cta2 ? bn / 2 : bn)};      // a CTA pair splits the weight tile

@@ -965,6 +965,7 @@ extern "C" int ofb_set_option(ofb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "no_point_feat")) h->no_point_feat = value != 0;
   else if (!strcmp(key, "no_transformer")) h->no_transformer = value != 0;
   else if (!strcmp(key, "splitk")) h->splitk = value == 2 || value == 4 ? value : 1;
+  else if (!strcmp(key, "wmc")) h->tc.wmc = value != 0;                 // weight multicast in the kh-reuse kernels
   else if (!strcmp(key, "khr_row64")) h->tc.khr_row64 = value != 0;
   else if (!strcmp(key, "khr_bw")) h->tc.khr_bw = value == 32 ? 32 : 16;    // tile width of the kh-reuse kernels
   else if (!strcmp(key, "dbg_blocks")) h->dbg_blocks = value < 0 ? 0 : (value > 6 ? 6 : value);   // timing experiments (wrong results)

@@ -262,6 +262,13 @@ def test_batch_invariance_chunking_dedup_and_graph(fmt):
             chained2 = net(rgb, iter=2, confidence=True)
             net.set_option("chain", 1)
             assert torch.equal(chained2[0], base[0]) and torch.equal(chained2[1], base[1]), "cross-cluster chains"
+        if FORMATS[fmt] == 1:
+            # option wmc: the kh-reuse kernels as 2-CTA clusters sharing each stage's weights by TMA multicast (a CTA
+            # whose last tile does not exist repeats the layer's last tile) - same arithmetic, bit-identical
+            net.set_option("wmc", 1)
+            mc = net(rgb, iter=2, confidence=True)
+            net.set_option("wmc", 0)
+            assert torch.equal(mc[0], base[0]) and torch.equal(mc[1], base[1]), "weight multicast"
         g = net.forward_graphed(rgb, 2, True)
         assert torch.equal(g[1], base[1])
         g2 = net.forward_graphed(rgb.flip(0).contiguous(), 2, True)
