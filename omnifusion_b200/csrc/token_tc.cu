@@ -421,6 +421,7 @@ token_stack_kernel(const __grid_constant__ TokStack st, float* __restrict__ xg, 
           }
         }
         worker_sync();
+        stamp(g, 7);
         for (int i0 = warp * 4; i0 < N; i0 += TK_WORKERS / 8) {      // four rows per warp: the loop is warp-uniform
           const int i = i0 + (lane >> 3), l8 = lane & 7;
           const bool row = i < N;
@@ -440,10 +441,19 @@ token_stack_kernel(const __grid_constant__ TokStack st, float* __restrict__ xg, 
         for (int o = tid; o < N * 32; o += TK_WORKERS) {
           const int i = o >> 5, d = o & 31;
           const float* pr = ps + i * (NP + 1);
-          float a0 = 0.f, a1 = 0.f;
-          int j = 0;
-          for (; j + 1 < N; j += 2) { a0 += pr[j] * qs[(2 * NP + j) * QP + d]; a1 += pr[j + 1] * qs[(2 * NP + j + 1) * QP + d]; }
-          if (j < N) a0 += pr[j] * qs[(2 * NP + j) * QP + d];
+          float a0 = 0.f, a1 = 0.f;          // even / odd keys, ascending
+#pragma unroll 1
+          for (int j0 = 0; j0 < N; j0 += 8) {      // eight keys per step: all sixteen shared-memory loads first
+            float pj[8], vj[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const bool in = j0 + u < N;
+              pj[u] = in ? pr[j0 + u] : 0.f;
+              vj[u] = in ? qs[(2 * NP + j0 + u) * QP + d] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) { a0 += pj[u] * vj[u]; a1 += pj[u + 1] * vj[u + 1]; }
+          }
           ag[xoff + (size_t)i * 512 + 32 * rank + d] = a0 + a1;
         }
         stamp(g, 5);

@@ -60,4 +60,5 @@ for g in range(4, 8):        # second block: steady state
     row = st[g]
     d = [int(row[k + 1] - row[k]) for k in range(len(names[g & 3]))]
     print(f"phase {g & 3}: " + " | ".join(f"{n} {v}" for n, v in zip(names[g & 3], d)))
+print("phase 0 detail: partial-score reads + sum -> shared", int(st[4][7] - st[4][4]), "| softmax + PV + store", int(st[4][5] - st[4][7]))
 print("block 1 total clk:", int(st[8][0] - st[4][0]), " whole stack:", int(st[23][6] - st[0][0]))
